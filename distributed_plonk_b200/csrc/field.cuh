@@ -1,0 +1,257 @@
+// Prime-field arithmetic for BLS12-381 Fr (8 x u32) and Fq (12 x u32), Montgomery form.
+//
+// Replaces ark-ff 0.3.0 Fp256<FrParameters> / Fp384<FqParameters> (4 / 6 x u64 Montgomery,
+// R = 2^256 / 2^384) that every arithmetic line of the reference hot path goes through
+// (src/worker.rs:76-93,104-114,118,179; Cargo.toml:31-36).  The in-memory bytes are identical:
+// 8 (12) little-endian u32 limbs == 4 (6) little-endian u64 limbs, same R, fully reduced.
+//
+// Multiplication is word-serial Montgomery with the products split into two accumulators of
+// non-overlapping 64-bit columns ("even" columns start at even word positions, "odd" ones at odd
+// positions) so each row a[*]*b[i] and m*p[*] is two straight carry chains of fused
+// multiply-adds (IMAD.WIDE.U32 + carry) with no per-product carry fix-up.
+#pragma once
+#include "ptx_arith.cuh"
+
+namespace dp {
+
+template <int N>
+struct alignas(16) Limbs {
+    uint32_t l[N];
+};
+
+// ------------------------------------------------------------------------------ parameters
+struct FrParams {
+    static constexpr int N = 8;
+    DP_HD static constexpr uint32_t mod(int i) {
+        constexpr uint32_t m[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
+                                   0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+        return m[i];
+    }
+    // R mod r (Montgomery one)
+    DP_HD static constexpr uint32_t one(int i) {
+        constexpr uint32_t m[8] = {0xfffffffeu, 0x00000001u, 0x00034802u, 0x5884b7fau,
+                                   0xecbc4ff5u, 0x998c4fefu, 0xacc5056fu, 0x1824b159u};
+        return m[i];
+    }
+    // R^2 mod r
+    DP_HD static constexpr uint32_t r2(int i) {
+        constexpr uint32_t m[8] = {0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu,
+                                   0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u};
+        return m[i];
+    }
+    static constexpr uint32_t INV = 0xffffffffu;  // -r^-1 mod 2^32
+};
+
+struct FqParams {
+    static constexpr int N = 12;
+    DP_HD static constexpr uint32_t mod(int i) {
+        constexpr uint32_t m[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu,
+                                    0xf6b0f624u, 0x6730d2a0u, 0xf38512bfu, 0x64774b84u,
+                                    0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
+        return m[i];
+    }
+    DP_HD static constexpr uint32_t one(int i) {
+        constexpr uint32_t m[12] = {0x0002fffdu, 0x76090000u, 0xc40c0002u, 0xebf4000bu,
+                                    0x53c758bau, 0x5f489857u, 0x70525745u, 0x77ce5853u,
+                                    0xa256ec6du, 0x5c071a97u, 0xfa80e493u, 0x15f65ec3u};
+        return m[i];
+    }
+    DP_HD static constexpr uint32_t r2(int i) {
+        constexpr uint32_t m[12] = {0x1c341746u, 0xf4df1f34u, 0x09d104f1u, 0x0a76e6a6u,
+                                    0x4c95b6d5u, 0x8de5476cu, 0x939d83c0u, 0x67eb88a9u,
+                                    0xb519952du, 0x9a793e85u, 0x92cae3aau, 0x11988fe5u};
+        return m[i];
+    }
+    static constexpr uint32_t INV = 0xfffcfffdu;  // -p^-1 mod 2^32
+};
+
+// ------------------------------------------------------------------------------ field
+template <class P>
+struct Field : Limbs<P::N> {
+    static constexpr int N = P::N;
+    using Limbs<P::N>::l;
+
+    DP_HD static Field zero() {
+        Field z;
+#pragma unroll
+        for (int i = 0; i < N; i++) z.l[i] = 0;
+        return z;
+    }
+    DP_HD static Field one() {
+        Field z;
+#pragma unroll
+        for (int i = 0; i < N; i++) z.l[i] = P::one(i);
+        return z;
+    }
+    DP_HD static Field r2() {
+        Field z;
+#pragma unroll
+        for (int i = 0; i < N; i++) z.l[i] = P::r2(i);
+        return z;
+    }
+    DP_HD bool is_zero() const {
+        uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) o |= l[i];
+        return o == 0;
+    }
+    DP_HD bool operator==(const Field &b) const {
+        uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) o |= l[i] ^ b.l[i];
+        return o == 0;
+    }
+    DP_HD bool operator!=(const Field &b) const { return !(*this == b); }
+
+    // t in [0, 2p) -> [0, p)
+    DP_HD static void final_sub(uint32_t *t) {
+        uint32_t d[N];
+        d[0] = ptx::sub_cc(t[0], P::mod(0));
+#pragma unroll
+        for (int i = 1; i < N; i++) d[i] = ptx::subc_cc(t[i], P::mod(i));
+        uint32_t borrow = ptx::subc(0u, 0u);  // 0 or 0xffffffff
+#pragma unroll
+        for (int i = 0; i < N; i++) t[i] = borrow ? t[i] : d[i];
+    }
+
+    DP_HD friend Field operator+(const Field &a, const Field &b) {
+        Field z;
+        z.l[0] = ptx::add_cc(a.l[0], b.l[0]);
+#pragma unroll
+        for (int i = 1; i < N; i++) z.l[i] = ptx::addc_cc(a.l[i], b.l[i]);
+        // p < 2^(32N-1): no carry out of the top limb
+        final_sub(z.l);
+        return z;
+    }
+    DP_HD friend Field operator-(const Field &a, const Field &b) {
+        Field z;
+        z.l[0] = ptx::sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+        for (int i = 1; i < N; i++) z.l[i] = ptx::subc_cc(a.l[i], b.l[i]);
+        uint32_t borrow = ptx::subc(0u, 0u);  // 0 or 0xffffffff
+        z.l[0] = ptx::add_cc(z.l[0], P::mod(0) & borrow);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) z.l[i] = ptx::addc_cc(z.l[i], P::mod(i) & borrow);
+        z.l[N - 1] = ptx::addc(z.l[N - 1], P::mod(N - 1) & borrow);
+        return z;
+    }
+    DP_HD Field neg() const { return zero() - *this; }
+    DP_HD Field dbl() const { return *this + *this; }
+
+    // ---- Montgomery product building blocks ------------------------------------------------
+    // acc[0..N) (64-bit columns at word 0,2,4..)  =  {a[0],a[2],...} * bi          (no carries)
+    DP_HD static void mul_row(uint32_t *acc, const uint32_t *a, uint32_t bi) {
+#pragma unroll
+        for (int j = 0; j < N; j += 2) ptx::mul_wide(acc[j], acc[j + 1], a[j], bi);
+    }
+    // acc += {a[0],a[2],...} * bi as one carry chain; carry-out left in CC
+    DP_HD static void mad_row(uint32_t *acc, const uint32_t *a, uint32_t bi) {
+        ptx::mad_wide_cc(acc[0], acc[1], a[0], bi);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) ptx::madc_wide_cc(acc[j], acc[j + 1], a[j], bi);
+    }
+    // constant-operand variant with the modulus limbs {p[off], p[off+2], ...}
+    template <int OFF>
+    DP_HD static void mad_row_mod(uint32_t *acc, uint32_t mi) {
+        ptx::mad_wide_cc(acc[0], acc[1], P::mod(OFF), mi);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) ptx::madc_wide_cc(acc[j], acc[j + 1], P::mod(OFF + j), mi);
+    }
+    // acc = (acc >> 64) + {a[0],a[2],...} * bi, continuing the carry in CC (carry-in consumed)
+    DP_HD static void mad_row_shift(uint32_t *acc, const uint32_t *a, uint32_t bi) {
+#pragma unroll
+        for (int j = 0; j < N - 2; j += 2) ptx::madc_wide_cc(acc[j], acc[j + 1], a[j], bi, acc[j + 2], acc[j + 3]);
+        ptx::madc_wide_last(acc[N - 2], acc[N - 1], a[N - 2], bi);
+    }
+    // One word-serial step.  `lo` holds the columns starting at the current word 0, `hi` those
+    // starting at word 1 (from the previous step `hi` still holds the old `lo`-role array, whose
+    // words 1.. are pending).  Adds a*bi, then m*p with m chosen to clear word 0.
+    DP_HD static void mont_step(uint32_t *lo, uint32_t *hi, const uint32_t *a, uint32_t bi, bool first) {
+        if (first) {
+            mul_row(hi, a + 1, bi);
+            mul_row(lo, a, bi);
+        } else {
+            lo[0] = ptx::add_cc(lo[0], hi[1]);      // pending word of the old array
+            mad_row_shift(hi, a + 1, bi);           // hi = (old >> 64) + a_odd*bi (+carry)
+            mad_row(lo, a, bi);
+            hi[N - 1] = ptx::addc(hi[N - 1], 0u);
+        }
+        uint32_t mi = lo[0] * P::INV;
+        mad_row_mod<1>(hi, mi);
+        // p < 2^(32N-2) and the running value < 2p*2^32: the hi chain cannot carry out
+        mad_row_mod<0>(lo, mi);
+        hi[N - 1] = ptx::addc(hi[N - 1], 0u);
+    }
+
+    DP_HD friend Field operator*(const Field &a, const Field &b) {
+        uint32_t even[N], odd[N];
+#pragma unroll
+        for (int i = 0; i < N; i += 2) {
+            mont_step(even, odd, a.l, b.l[i], i == 0);
+            mont_step(odd, even, a.l, b.l[i + 1], false);
+        }
+        // after an even number of steps: value/2^32 = even (word 0..) + odd[1..] pending
+        Field z;
+        z.l[0] = ptx::add_cc(even[0], odd[1]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) z.l[i] = ptx::addc_cc(even[i], odd[i + 1]);
+        z.l[N - 1] = ptx::addc(even[N - 1], 0u);
+        final_sub(z.l);
+        return z;
+    }
+    DP_HD Field sqr() const { return (*this) * (*this); }
+
+    DP_HD Field &operator+=(const Field &b) { return *this = *this + b; }
+    DP_HD Field &operator-=(const Field &b) { return *this = *this - b; }
+    DP_HD Field &operator*=(const Field &b) { return *this = *this * b; }
+
+    // canonical integer <-> Montgomery (ark: from_repr / into_repr)
+    DP_HD Field to_mont() const { return (*this) * r2(); }
+    DP_HD Field from_mont() const {
+        Field o = zero();
+        o.l[0] = 1;
+        return (*this) * o;
+    }
+
+    // x^e for a 64-bit exponent (Fr::pow([e]); worker.rs:79,93,113)
+    DP_HD Field pow(uint64_t e) const {
+        Field acc = one();
+        bool started = false;
+        for (int b = 63; b >= 0; b--) {
+            if (started) acc = acc.sqr();
+            if ((e >> b) & 1) {
+                acc = started ? acc * (*this) : *this;
+                started = true;
+            }
+        }
+        return acc;
+    }
+    // x^(p-2) (Fermat); x != 0
+    DP_HD Field inverse() const {
+        uint32_t e[N];
+        uint32_t borrow = 2;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            uint32_t m = P::mod(i);
+            e[i] = m - borrow;
+            borrow = m < borrow ? 1u : 0u;
+        }
+        Field acc = one();
+        bool started = false;
+        for (int i = N - 1; i >= 0; i--) {
+            for (int b = 31; b >= 0; b--) {
+                if (started) acc = acc.sqr();
+                if ((e[i] >> b) & 1) {
+                    acc = started ? acc * (*this) : *this;
+                    started = true;
+                }
+            }
+        }
+        return acc;
+    }
+};
+
+using Fr = Field<FrParams>;
+using Fq = Field<FqParams>;
+
+}  // namespace dp

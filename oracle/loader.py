@@ -1,0 +1,166 @@
+"""ctypes loader for the tier-1 C oracle (oracle/c/ark_oracle.c).  Test infrastructure only."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libark_oracle.so")
+_lib = None
+
+
+def _cpu_tag() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def build(force: bool = False) -> str:
+    """(Re)build with -march=native; rebuilt when the source is newer or the host CPU changed
+    (the .so travels to the GPU box with the repo snapshot)."""
+    src = os.path.join(_HERE, "c", "ark_oracle.c")
+    stamp = os.path.join(_HERE, "_build", "host.txt")
+    tag = _cpu_tag()
+    same_host = os.path.exists(stamp) and open(stamp).read() == tag
+    if force or not same_host or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-B", "-C", _HERE])
+        with open(stamp, "w") as f:
+            f.write(tag)
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        u64, p, i = C.c_uint64, C.c_void_p, C.c_int
+        sig = {
+            "orc_fft_in_place": (None, [p, u64, i]),
+            "orc_coset_fft_in_place": (None, [p, u64, i]),
+            "orc_fft1_helper": (None, [p, u64, i, i, u64, i]),
+            "orc_fft2_helper": (None, [p, u64, i, i, u64, i]),
+            "orc_distributed_fft": (None, [p, p, u64, i, i, u64, i]),
+            "orc_fr_mul": (None, [p, p, p]),
+            "orc_fr_add": (None, [p, p, p]),
+            "orc_fr_sub": (None, [p, p, p]),
+            "orc_fq_mul": (None, [p, p, p]),
+            "orc_fq_add": (None, [p, p, p]),
+            "orc_fq_sub": (None, [p, p, p]),
+            "orc_fr_into_repr": (None, [p, p, u64]),
+            "orc_fr_from_repr": (None, [p, p, u64]),
+            "orc_g1_normalize": (None, [p, p]),
+            "orc_g1_add": (None, [p, p, p]),
+            "orc_g1_mul": (None, [p, p, p]),
+            "orc_g1_generator": (None, [p]),
+            "orc_gen_fr": (None, [u64, u64, p, i]),
+            "orc_gen_bases": (None, [u64, u64, u64, i, p]),
+            "orc_msm_window_c": (u64, [u64]),
+            "orc_msm_work_adds": (C.c_double, [u64, u64]),
+            "orc_msm": (None, [p, p, u64, p]),
+            "orc_commit": (None, [p, u64, p, u64, p]),
+            "orc_num_threads": (i, []),
+        }
+        for name, (res, args) in sig.items():
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _ptr(a: np.ndarray):
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ---- numpy-level helpers (arrays are uint64 [n,4] for Fr, uint8 [n,104] bases, uint8[144] points)
+def gen_fr(seed: int, n: int, montgomery: bool = True) -> np.ndarray:
+    out = np.empty((n, 4), dtype=np.uint64)
+    lib().orc_gen_fr(seed, n, _ptr(out), int(montgomery))
+    return out
+
+
+def gen_bases(seed: int, n: int, distinct: int = 2048, with_infinity: bool = True) -> np.ndarray:
+    out = np.zeros((n, 104), dtype=np.uint8)
+    lib().orc_gen_bases(seed, n, distinct, int(with_infinity), _ptr(out))
+    return out
+
+
+def fft(x: np.ndarray, inverse: bool = False, coset: bool = False) -> np.ndarray:
+    y = np.ascontiguousarray(x, dtype=np.uint64).copy()
+    n = y.shape[0]
+    (lib().orc_coset_fft_in_place if coset else lib().orc_fft_in_place)(_ptr(y), n, int(inverse))
+    return y
+
+
+def fft1_helper(v, i, is_coset, is_inv, domain_size, as_written=False):
+    y = np.ascontiguousarray(v, dtype=np.uint64).copy()
+    lib().orc_fft1_helper(_ptr(y), i, int(is_coset), int(is_inv), domain_size, int(as_written))
+    return y
+
+
+def fft2_helper(v, i, is_coset, is_inv, domain_size, as_written=False):
+    y = np.ascontiguousarray(v, dtype=np.uint64).copy()
+    lib().orc_fft2_helper(_ptr(y), i, int(is_coset), int(is_inv), domain_size, int(as_written))
+    return y
+
+
+def distributed_fft(x, domain_size, is_inv, is_coset, n_workers=1, as_written=False):
+    xin = np.zeros((domain_size, 4), dtype=np.uint64)
+    xin[: x.shape[0]] = x
+    out = np.empty_like(xin)
+    lib().orc_distributed_fft(_ptr(xin), _ptr(out), domain_size, int(is_inv), int(is_coset), n_workers, int(as_written))
+    return out
+
+
+def into_repr(x: np.ndarray) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.uint64)
+    out = np.empty_like(x)
+    lib().orc_fr_into_repr(_ptr(x), _ptr(out), x.shape[0])
+    return out
+
+
+def from_repr(x: np.ndarray) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.uint64)
+    out = np.empty_like(x)
+    lib().orc_fr_from_repr(_ptr(x), _ptr(out), x.shape[0])
+    return out
+
+
+def msm(bases: np.ndarray, scalars: np.ndarray) -> np.ndarray:
+    n = min(bases.shape[0], scalars.shape[0])
+    bases = np.ascontiguousarray(bases[:n])
+    scalars = np.ascontiguousarray(scalars[:n], dtype=np.uint64)
+    out = np.zeros(144, dtype=np.uint8)
+    lib().orc_msm(_ptr(bases), _ptr(scalars), n, _ptr(out))
+    return out
+
+
+def commit(bases: np.ndarray, fr_mont: np.ndarray) -> np.ndarray:
+    bases = np.ascontiguousarray(bases)
+    fr_mont = np.ascontiguousarray(fr_mont, dtype=np.uint64)
+    out = np.zeros(144, dtype=np.uint8)
+    lib().orc_commit(_ptr(bases), bases.shape[0], _ptr(fr_mont), fr_mont.shape[0], _ptr(out))
+    return out
+
+
+def normalize(jac144: np.ndarray) -> np.ndarray:
+    jac144 = np.ascontiguousarray(jac144, dtype=np.uint8)
+    out = np.zeros(104, dtype=np.uint8)
+    lib().orc_g1_normalize(_ptr(jac144), _ptr(out))
+    return out
+
+
+def g1_add(a144: np.ndarray, b144: np.ndarray) -> np.ndarray:
+    out = np.zeros(144, dtype=np.uint8)
+    lib().orc_g1_add(_ptr(np.ascontiguousarray(a144)), _ptr(np.ascontiguousarray(b144)), _ptr(out))
+    return out

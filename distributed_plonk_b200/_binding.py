@@ -1,0 +1,196 @@
+"""ctypes binding of the C ABI declared in include/dplonk.h (one Python method per entry point)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+DP_OK, DP_E_ARG, DP_E_STATE, DP_E_OOM, DP_E_CUDA, DP_E_COMM = 0, -1, -2, -3, -4, -5
+FR_BYTES, G1_AFFINE_BYTES, G1_PROJECTIVE_BYTES = 32, 104, 144
+
+EXPORTS = [
+    "dp_create", "dp_destroy", "dp_last_error", "dp_version", "dp_init", "dp_msm", "dp_commit", "dp_fft_init",
+    "dp_fft1", "dp_fft1_rows", "dp_fft2_prepare", "dp_fft_exchange_begin", "dp_fft_exchange_end", "dp_fft2",
+    "dp_ntt", "dp_round1", "dp_get_wire", "dp_peer_arena_create", "dp_peer_attach", "dp_last_timing",
+    "dp_launch_count", "dp_sync", "dp_msm_dev", "dp_ntt_dev", "dp_fft_dev", "dp_debug_set_limits",
+]
+
+
+class DpError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"dplonk error {code}: {msg}")
+        self.code = code
+
+
+class FftWorkload(C.Structure):
+    """utils.rs:3-19 / hello_world.capnp:8-13"""
+    _fields_ = [("row_start", C.c_uint64), ("row_end", C.c_uint64), ("col_start", C.c_uint64), ("col_end", C.c_uint64)]
+
+
+def bind(cdll: C.CDLL) -> C.CDLL:
+    u64, vp, i, sz, u32 = C.c_uint64, C.c_void_p, C.c_int, C.c_size_t, C.c_uint32
+    sig = {
+        "dp_create": (i, [i, u64, u64, C.POINTER(vp)]),
+        "dp_destroy": (i, [vp]),
+        "dp_last_error": (C.c_char_p, [vp]),
+        "dp_version": (C.c_char_p, []),
+        "dp_init": (i, [vp, vp, sz, u64, u64]),
+        "dp_msm": (i, [vp, u64, u64, vp, sz, vp]),
+        "dp_commit": (i, [vp, vp, sz, vp]),
+        "dp_fft_init": (i, [vp, u64, C.POINTER(FftWorkload), sz, i, i, i]),
+        "dp_fft1": (i, [vp, u64, u64, vp, sz]),
+        "dp_fft1_rows": (i, [vp, u64, u64, u64, vp]),
+        "dp_fft2_prepare": (i, [vp, u64]),
+        "dp_fft_exchange_begin": (i, [vp, u64, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]),
+        "dp_fft_exchange_end": (i, [vp, u64]),
+        "dp_fft2": (i, [vp, u64, vp, sz]),
+        "dp_ntt": (i, [vp, vp, sz, u32, i, i]),
+        "dp_round1": (i, [vp, vp, sz, vp, vp]),
+        "dp_get_wire": (i, [vp, vp, sz, C.POINTER(sz)]),
+        "dp_peer_arena_create": (i, [vp, u64, vp]),
+        "dp_peer_attach": (i, [vp, u64, vp]),
+        "dp_last_timing": (i, [vp, C.POINTER(C.c_float), C.POINTER(u64)]),
+        "dp_launch_count": (u64, [vp]),
+        "dp_sync": (i, [vp]),
+        "dp_msm_dev": (i, [vp, u64, u64, vp, sz, vp]),
+        "dp_ntt_dev": (i, [vp, vp, u32, i, i]),
+        "dp_fft_dev": (i, [vp, vp, vp, i, i, i]),
+        "dp_debug_set_limits": (i, [vp, u32, u32, i]),
+    }
+    assert set(sig) == set(EXPORTS)
+    for name, (res, args) in sig.items():
+        f = getattr(cdll, name)  # AttributeError here = the library does not export what dplonk.h declares
+        f.restype = res
+        f.argtypes = args
+    return cdll
+
+
+def _addr(buf) -> int:
+    """host address of a numpy array / bytes-like / raw int address."""
+    if isinstance(buf, int):
+        return buf
+    if isinstance(buf, np.ndarray):
+        assert buf.flags["C_CONTIGUOUS"]
+        return buf.ctypes.data
+    return C.addressof(C.c_char.from_buffer(buf))
+
+
+class Context:
+    """One dp_ctx (one GPU).  Thin: arguments are numpy arrays in the reference's raw layouts."""
+
+    def __init__(self, cdll: C.CDLL, device: int = 0, me: int = 0, n_workers: int = 1):
+        self.lib = cdll
+        self.me, self.n_workers = me, n_workers
+        h = C.c_void_p()
+        rc = cdll.dp_create(device, me, n_workers, C.byref(h))
+        if rc != DP_OK:
+            raise DpError(rc, (cdll.dp_last_error(None) or b"").decode())
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.lib.dp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc: int):
+        if rc != DP_OK:
+            raise DpError(rc, (self.lib.dp_last_error(self.h) or b"").decode())
+
+    # ---- PlonkSlave surface
+    def init(self, bases: np.ndarray, domain_size: int, quot_domain_size: int):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        n = bases.size // G1_AFFINE_BYTES
+        self._ck(self.lib.dp_init(self.h, _addr(bases) if n else None, n, domain_size, quot_domain_size))
+
+    def msm(self, start: int, end: int, scalars: np.ndarray) -> np.ndarray:
+        scalars = np.ascontiguousarray(scalars)
+        n = scalars.nbytes // 32
+        out = np.zeros(G1_PROJECTIVE_BYTES, dtype=np.uint8)
+        self._ck(self.lib.dp_msm(self.h, start, end, _addr(scalars) if n else None, n, _addr(out)))
+        return out
+
+    def commit(self, coeffs: np.ndarray) -> np.ndarray:
+        coeffs = np.ascontiguousarray(coeffs)
+        n = coeffs.nbytes // 32
+        out = np.zeros(G1_PROJECTIVE_BYTES, dtype=np.uint8)
+        self._ck(self.lib.dp_commit(self.h, _addr(coeffs) if n else None, n, _addr(out)))
+        return out
+
+    def fft_init(self, task_id: int, workloads, is_quot: bool, is_inv: bool, is_coset: bool):
+        arr = (FftWorkload * len(workloads))(*[FftWorkload(*w) for w in workloads])
+        self._ck(self.lib.dp_fft_init(self.h, task_id, arr, len(workloads), int(is_quot), int(is_inv), int(is_coset)))
+
+    def fft1(self, task_id: int, i: int, row: np.ndarray):
+        row = np.ascontiguousarray(row)
+        self._ck(self.lib.dp_fft1(self.h, task_id, i, _addr(row), row.nbytes // 32))
+
+    def fft1_rows(self, task_id: int, i_first: int, rows: np.ndarray, n_rows: int):
+        rows = np.ascontiguousarray(rows)
+        self._ck(self.lib.dp_fft1_rows(self.h, task_id, i_first, n_rows, _addr(rows)))
+
+    def fft2_prepare(self, task_id: int):
+        self._ck(self.lib.dp_fft2_prepare(self.h, task_id))
+
+    def fft_exchange_begin(self, task_id: int):
+        s, r, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        self._ck(self.lib.dp_fft_exchange_begin(self.h, task_id, C.byref(s), C.byref(r), C.byref(n)))
+        return s.value, r.value, n.value
+
+    def fft_exchange_end(self, task_id: int):
+        self._ck(self.lib.dp_fft_exchange_end(self.h, task_id))
+
+    def fft2(self, task_id: int, n_cols: int, r: int) -> np.ndarray:
+        out = np.empty((n_cols, r, 4), dtype=np.uint64)
+        self._ck(self.lib.dp_fft2(self.h, task_id, _addr(out), out.nbytes))
+        return out
+
+    def ntt(self, data: np.ndarray, log_n: int, is_inv: bool, is_coset: bool) -> np.ndarray:
+        n = data.nbytes // 32
+        buf = np.zeros((1 << log_n, 4), dtype=np.uint64)
+        buf.reshape(-1)[: n * 4] = np.ascontiguousarray(data).view(np.uint64).reshape(-1)
+        self._ck(self.lib.dp_ntt(self.h, _addr(buf), n, log_n, int(is_inv), int(is_coset)))
+        return buf
+
+    def round1(self, evals: np.ndarray, blind: np.ndarray | None) -> np.ndarray:
+        evals = np.ascontiguousarray(evals)
+        out = np.zeros(G1_PROJECTIVE_BYTES, dtype=np.uint8)
+        b = np.ascontiguousarray(blind) if blind is not None else None
+        self._ck(self.lib.dp_round1(self.h, _addr(evals), evals.nbytes // 32, _addr(b) if b is not None else None, _addr(out)))
+        return out
+
+    def get_wire(self) -> np.ndarray:
+        n = C.c_size_t()
+        self._ck(self.lib.dp_get_wire(self.h, None, 0, C.byref(n)))
+        out = np.empty((n.value, 4), dtype=np.uint64)
+        self._ck(self.lib.dp_get_wire(self.h, _addr(out), out.nbytes, C.byref(n)))
+        return out
+
+    # ---- device-pointer variants (bench)
+    def msm_dev(self, start, end, scalars_ptr: int, n: int, out_ptr: int):
+        self._ck(self.lib.dp_msm_dev(self.h, start, end, scalars_ptr, n, out_ptr))
+
+    def ntt_dev(self, data_ptr: int, log_n: int, is_inv: bool, is_coset: bool):
+        self._ck(self.lib.dp_ntt_dev(self.h, data_ptr, log_n, int(is_inv), int(is_coset)))
+
+    def fft_dev(self, rows_ptr: int, cols_ptr: int, is_quot: bool, is_inv: bool, is_coset: bool):
+        self._ck(self.lib.dp_fft_dev(self.h, rows_ptr, cols_ptr, int(is_quot), int(is_inv), int(is_coset)))
+
+    def debug_set_limits(self, max_contig_log_k=11, max_strided_log_k=9, msm_window_bits=0):
+        self._ck(self.lib.dp_debug_set_limits(self.h, max_contig_log_k, max_strided_log_k, msm_window_bits))
+
+    def sync(self):
+        self._ck(self.lib.dp_sync(self.h))
+
+    def last_timing(self):
+        ms, n = C.c_float(), C.c_uint64()
+        self.lib.dp_last_timing(self.h, C.byref(ms), C.byref(n))
+        return ms.value, n.value
+
+    def launch_count(self) -> int:
+        return int(self.lib.dp_launch_count(self.h))

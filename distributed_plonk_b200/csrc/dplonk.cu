@@ -1,0 +1,1097 @@
+// C ABI (include/dplonk.h) over the NTT / MSM kernels: device-resident worker state that mirrors
+// the reference's `State` / `FftTask` (src/worker.rs:32-59) and the bodies of its RPC methods
+// (src/worker.rs:125-439).  Host code only plans launches and moves bytes; every field / curve
+// operation that contributes to a result runs in a CUDA kernel.
+#include "../../include/dplonk.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "msm.cuh"
+#include "ntt.cuh"
+
+using namespace dp;
+
+namespace {
+
+// ------------------------------------------------------------------ device memory pool
+// cudaFree synchronises the device; tasks allocate the same few sizes over and over, so freed
+// blocks are kept and handed back by exact size.  Single stream => stream-ordered reuse is safe.
+struct DevPool {
+    std::multimap<size_t, void *> free_blocks;
+    std::unordered_map<void *, size_t> live;
+    size_t total = 0;
+    void *alloc(size_t bytes) {
+        bytes = (bytes + 511) & ~(size_t)511;
+        if (bytes == 0) bytes = 512;
+        auto it = free_blocks.find(bytes);
+        if (it != free_blocks.end()) {
+            void *p = it->second;
+            free_blocks.erase(it);
+            live[p] = bytes;
+            return p;
+        }
+        void *p = nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) {
+            purge();  // drop cached blocks and retry once
+            if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+        }
+        total += bytes;
+        live[p] = bytes;
+        return p;
+    }
+    void release(void *p) {
+        if (!p) return;
+        auto it = live.find(p);
+        if (it == live.end()) return;
+        free_blocks.emplace(it->second, p);
+        live.erase(it);
+    }
+    void purge() {
+        for (auto &kv : free_blocks) {
+            cudaFree(kv.second);
+            total -= kv.first;
+        }
+        free_blocks.clear();
+    }
+    void destroy() {
+        purge();
+        for (auto &kv : live) cudaFree(kv.first);
+        live.clear();
+    }
+};
+
+struct DomainDev {
+    uint32_t log_n = 0, log_r = 0, log_c = 0;
+    Fr *H = nullptr;       // omega_N^e, e < N/2
+    Fr *g_row = nullptr;   // g^i, i < r                (forward coset, by global row)
+    Fr *g_col = nullptr;   // g^(r*j), j < c
+    Fr *gi_col = nullptr;  // g^-i / r, i < c           (inverse coset + 1/r, by global column)
+    Fr *gi_pt = nullptr;   // g^-(c*j), j < r
+    Fr c_inv, r_inv, n_inv;
+    uint64_t n() const { return (uint64_t)1 << log_n; }
+    uint64_t r() const { return (uint64_t)1 << log_r; }
+    uint64_t c() const { return (uint64_t)1 << log_c; }
+};
+
+struct FftTask {
+    bool is_quot, is_inv, is_coset;
+    std::vector<dp_fft_workload> wl;
+    uint64_t n_rows, n_cols, row_start, col_start;
+    Fr *rows = nullptr;  // [n_rows][c]
+    Fr *send = nullptr;  // W blocks of [n_rows][c/W]           (aliases rows when W == 1)
+    Fr *recv = nullptr;  // [r][n_cols] = W blocks of [r/W][n_cols] (aliases send when W == 1)
+    uint64_t rows_filled = 0;
+    std::vector<uint8_t> row_seen;
+    bool row_phase_done = false, exchanged = false;
+};
+
+}  // namespace
+
+struct dp_ctx {
+    int device = 0;
+    uint64_t me = 0, W = 1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    uint64_t launches = 0, launches_at_call = 0;
+    float last_ms = 0.f;
+    DevPool pool;
+    uint4 *wf_lo = nullptr, *wf_hi = nullptr, *wi_lo = nullptr, *wi_hi = nullptr;
+    G1Affine *bases = nullptr;
+    uint64_t n_bases = 0;
+    DomainDev dom[2];
+    bool inited = false;
+    std::map<uint64_t, FftTask> tasks;
+    Fr *wire = nullptr;
+    uint64_t wire_len = 0;
+    uint64_t rng_state = 0x9E3779B97F4A7C15ull;
+    // pass-planning limits (dp_debug_set_limits lowers them so small tests reach the multi-pass plans)
+    uint32_t max_contig_log_k = NTT_WTAB_LOG, max_strided_log_k = NTT_MAX_STRIDED_LOG_K;
+    int msm_force_c = 0;
+};
+
+namespace {
+
+thread_local std::string g_err_noctx;
+
+int fail(dp_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx)
+        ctx->err = buf;
+    else
+        g_err_noctx = buf;
+    return code;
+}
+
+#define DP_CUDA(ctx, expr)                                                                              \
+    do {                                                                                                \
+        cudaError_t e__ = (expr);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return fail(ctx, DP_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+#define DP_TRY(expr)               \
+    do {                           \
+        int rc__ = (expr);         \
+        if (rc__ != DP_OK) return rc__; \
+    } while (0)
+
+inline uint32_t log2_ceil_u64(uint64_t n) {
+    uint32_t l = 0;
+    while (((uint64_t)1 << l) < n) l++;
+    return l;
+}
+inline unsigned blocks_for(uint64_t n, unsigned tpb) { return (unsigned)((n + tpb - 1) / tpb); }
+
+void call_begin(dp_ctx *ctx) {
+    ctx->launches_at_call = ctx->launches;
+    cudaEventRecord(ctx->ev0, ctx->stream);
+}
+int call_end(dp_ctx *ctx, bool sync) {
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    if (sync) {
+        DP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        DP_CUDA(ctx, cudaGetLastError());
+        cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+    }
+    return DP_OK;
+}
+
+// ------------------------------------------------------------------ NTT planning
+NttPass pass_base(dp_ctx *ctx, bool inverse) {
+    NttPass p;
+    memset((void *)&p, 0, sizeof p);
+    p.w_lo = inverse ? ctx->wi_lo : ctx->wf_lo;
+    p.w_hi = inverse ? ctx->wi_hi : ctx->wf_hi;
+    p.n_outer = 1;
+    p.lane_tiles = 1;
+    p.tw_inverse = inverse ? 1 : 0;
+    return p;
+}
+
+// lanes per tile: fill the 2048-element tile but never exceed the number of lanes
+uint32_t pick_log_g(uint32_t log_k, uint64_t n_lanes) {
+    uint32_t lg = NTT_TILE_LOG > log_k ? NTT_TILE_LOG - log_k : 0;
+    while (((uint64_t)1 << lg) > n_lanes) lg--;
+    return lg;
+}
+
+int launch_pass(dp_ctx *ctx, NttPass &p, uint64_t n_lanes) {
+    p.lane_tiles = (uint32_t)(n_lanes >> p.log_g);
+    const uint64_t grid = (uint64_t)p.n_outer * p.lane_tiles;
+    if (grid == 0 || grid > 0x7fffffffull) return fail(ctx, DP_E_ARG, "ntt pass grid %llu out of range", (unsigned long long)grid);
+    const size_t smem = ntt_pass_smem_bytes(p.log_k, p.log_g);
+    DP_LAUNCH(ntt_tile_kernel, dim3((unsigned)grid), dim3(NTT_TPB), smem, ctx->stream, p);
+    ctx->launches++;
+    DP_CUDA(ctx, cudaGetLastError());
+    return DP_OK;
+}
+
+// Row phase of the 2-D transform (fft1_helper, worker.rs:66-94) over all local rows:
+//   src  [n_rows][c] row-major;  dst = exchange layout: W blocks of [n_rows][c/W]
+// scratch ([n_rows][c]) is used when c > 2^11 (row split into two passes).
+int plan_row_phase(dp_ctx *ctx, const DomainDev &d, const Fr *src, Fr *dst, Fr *scratch, uint64_t n_rows,
+                   uint64_t row_start, bool is_inv, bool is_coset, uint64_t W) {
+    const uint32_t lc = d.log_c;
+    const uint64_t c = d.c();
+    const uint32_t log_ncq = lc - log2_ceil_u64(W);
+    const bool pre = is_coset && !is_inv;
+    auto finish = [&](NttPass &p) {
+        p.tw_tab = d.H;
+        p.tw_log_n = d.log_n;
+        if (W > 1) {
+            p.split_on = 1;
+            p.split_log = log_ncq;
+            p.split_stride = n_rows << log_ncq;
+        }
+        if (is_inv) {
+            p.post_const_on = 1;
+            p.post_const = d.c_inv;
+        }
+    };
+    if (lc <= ctx->max_contig_log_k) {
+        NttPass p = pass_base(ctx, is_inv);
+        p.in = src;
+        p.out = dst;
+        p.log_k = lc;
+        p.log_g = pick_log_g(lc, n_rows);
+        p.in_ls = c;
+        p.in_ps = 1;
+        p.out_ls = W > 1 ? ((uint64_t)1 << log_ncq) : c;
+        p.out_ps = 1;
+        // omega_N^(+-(row_start + lane) * f)
+        p.tw_la = 1;
+        p.tw_c0 = row_start;
+        p.tw_fb = 1;
+        if (pre) {
+            p.pre_a = d.g_row + row_start;
+            p.pa_l = 1;
+            p.pre_b = d.g_col;
+            p.pb_m = 1;
+        }
+        finish(p);
+        return launch_pass(ctx, p, n_rows);
+    }
+    // c = L1 * L2: pass 1 strided (points L2 apart, lanes = p2 contiguous), pass 2 contiguous chunks
+    const uint32_t l1 = lc / 2, l2 = lc - l1;
+    const uint64_t L1 = (uint64_t)1 << l1, L2 = (uint64_t)1 << l2;
+    {
+        NttPass p = pass_base(ctx, is_inv);
+        p.in = src;
+        p.out = scratch;
+        p.log_k = l1;
+        p.log_g = pick_log_g(l1, L2);
+        p.n_outer = (uint32_t)n_rows;
+        p.in_os = p.out_os = c;
+        p.in_ls = p.out_ls = 1;
+        p.in_ps = p.out_ps = L2;
+        // omega_c^(+-f*lane) = omega_N^(+-(N/c)*lane*f)
+        p.tw_tab = d.H;
+        p.tw_log_n = d.log_n;
+        p.tw_la = d.n() >> lc;
+        p.tw_fb = 1;
+        if (pre) {
+            p.pre_a = d.g_row + row_start;
+            p.pa_o = 1;
+            p.pre_b = d.g_col;
+            p.pb_m = L2;
+            p.pb_l = 1;
+        }
+        DP_TRY(launch_pass(ctx, p, L2));
+    }
+    {
+        NttPass p = pass_base(ctx, is_inv);
+        p.in = scratch;
+        p.out = dst;
+        p.log_k = l2;
+        p.log_g = pick_log_g(l2, L1);
+        p.n_outer = (uint32_t)n_rows;
+        p.in_os = c;
+        p.in_ls = L2;
+        p.in_ps = 1;
+        // output column index = lane + L1 * f
+        p.out_os = W > 1 ? ((uint64_t)1 << log_ncq) : c;
+        p.out_ls = 0;
+        p.out_lc = 1;
+        p.out_ps = L1;
+        // omega_N^(+-(row_start + o) * (lane + L1*f))
+        p.tw_oa = 1;
+        p.tw_c0 = row_start;
+        p.tw_lb = 1;
+        p.tw_fb = L1;
+        finish(p);
+        return launch_pass(ctx, p, L1);
+    }
+}
+
+// Column phase (fft2_helper, worker.rs:96-115): src = [r][ncq] row-major (column k = src[j*ncq+k]),
+// dst = [ncq][r] (column k contiguous).  src is overwritten when r > 2^9 (two passes).
+int plan_col_phase(dp_ctx *ctx, const DomainDev &d, Fr *src, Fr *dst, uint64_t ncq, uint64_t col_start, bool is_inv,
+                   bool is_coset) {
+    const uint32_t lr = d.log_r;
+    const uint64_t r = d.r();
+    const bool post = is_coset && is_inv;
+    auto finish = [&](NttPass &p) {
+        if (post) {
+            p.post_a = d.gi_col + col_start;  // carries the 1/r of the inverse transform
+            p.qa_l = 1;
+            p.post_b = d.gi_pt;
+        } else if (is_inv) {
+            p.post_const_on = 1;
+            p.post_const = d.r_inv;
+        }
+    };
+    if (lr <= ctx->max_strided_log_k) {
+        NttPass p = pass_base(ctx, is_inv);
+        p.in = src;
+        p.out = dst;
+        p.log_k = lr;
+        p.log_g = pick_log_g(lr, ncq);
+        p.in_ls = 1;
+        p.in_ps = ncq;
+        p.out_ls = r;
+        p.out_ps = 1;
+        if (post) p.qb_f = 1;
+        finish(p);
+        return launch_pass(ctx, p, ncq);
+    }
+    const uint32_t l1 = lr / 2, l2 = lr - l1;
+    const uint64_t R1 = (uint64_t)1 << l1, R2 = (uint64_t)1 << l2;
+    {
+        NttPass p = pass_base(ctx, is_inv);
+        p.in = src;
+        p.out = src;
+        p.log_k = l1;
+        p.log_g = pick_log_g(l1, ncq);
+        p.n_outer = (uint32_t)R2;  // o = j2
+        p.in_os = p.out_os = ncq;
+        p.in_ls = p.out_ls = 1;
+        p.in_ps = p.out_ps = R2 * ncq;
+        // omega_r^(+-f*j2) = omega_N^(+-(N/r)*o*f)
+        p.tw_tab = d.H;
+        p.tw_log_n = d.log_n;
+        p.tw_oa = d.n() >> lr;
+        p.tw_fb = 1;
+        DP_TRY(launch_pass(ctx, p, ncq));
+    }
+    {
+        NttPass p = pass_base(ctx, is_inv);
+        p.in = src;
+        p.out = dst;
+        p.log_k = l2;
+        p.log_g = pick_log_g(l2, ncq);
+        p.n_outer = (uint32_t)R1;  // o = f1
+        p.in_os = R2 * ncq;
+        p.in_ls = 1;
+        p.in_ps = ncq;
+        // out[k][f1 + R1*f2]
+        p.out_os = 1;
+        p.out_ls = r;
+        p.out_ps = R1;
+        if (post) {
+            p.qb_o = 1;
+            p.qb_f = R1;
+        }
+        finish(p);
+        return launch_pass(ctx, p, ncq);
+    }
+}
+
+// Whole-domain transform of 2^L elements: x (in place) with scratch of the same size.
+int plan_whole_ntt(dp_ctx *ctx, const DomainDev *d, Fr *x, Fr *scratch, uint32_t L, bool is_inv, bool is_coset,
+                   const Fr *H, uint32_t H_log_n) {
+    const uint64_t N = (uint64_t)1 << L;
+    (void)d;
+    Fr g = fr_from_u64(7), ninv = fr_from_u64(N).inverse();
+    if (is_coset && !is_inv) {
+        DP_LAUNCH(fr_scale_powers_kernel, dim3(blocks_for(N, 256)), dim3(256), 0, ctx->stream, x, N, g, Fr::one());
+        ctx->launches++;
+    }
+    auto set_final = [&](NttPass &p) {
+        if (is_inv && !is_coset) {
+            p.post_const_on = 1;
+            p.post_const = ninv;
+        }
+    };
+    const uint64_t tw_mul = (uint64_t)1 << (H_log_n - L);  // omega_N = omega_H^(tw_mul)
+    if (L <= ctx->max_contig_log_k) {
+        NttPass p = pass_base(ctx, is_inv);
+        p.in = x;
+        p.out = x;
+        p.log_k = L;
+        p.log_g = 0;
+        p.in_ps = p.out_ps = 1;
+        set_final(p);
+        DP_TRY(launch_pass(ctx, p, 1));
+    } else if (L <= 2 * ctx->max_strided_log_k) {
+        const uint32_t l1 = L / 2, l2 = L - l1;
+        const uint64_t N1 = (uint64_t)1 << l1, N2 = (uint64_t)1 << l2;
+        NttPass p = pass_base(ctx, is_inv);
+        p.in = x;
+        p.out = scratch;
+        p.log_k = l1;
+        p.log_g = pick_log_g(l1, N2);
+        p.in_ls = p.out_ls = 1;
+        p.in_ps = p.out_ps = N2;
+        p.tw_tab = H;
+        p.tw_log_n = H_log_n;
+        p.tw_la = tw_mul;
+        p.tw_fb = 1;
+        DP_TRY(launch_pass(ctx, p, N2));
+        NttPass q = pass_base(ctx, is_inv);
+        q.in = scratch;
+        q.out = x;
+        q.log_k = l2;
+        q.log_g = pick_log_g(l2, N1);
+        q.in_ls = N2;
+        q.in_ps = 1;
+        q.out_ls = 1;
+        q.out_ps = N1;
+        set_final(q);
+        DP_TRY(launch_pass(ctx, q, N1));
+    } else {
+        if (L > 3 * ctx->max_strided_log_k) return fail(ctx, DP_E_ARG, "dp_ntt: log_n %u too large for one device pass plan", L);
+        const uint32_t l1 = L / 3, l2 = (L - l1) / 2, l3 = L - l1 - l2;
+        const uint64_t N1 = (uint64_t)1 << l1, N2 = (uint64_t)1 << l2, N3 = (uint64_t)1 << l3;
+        NttPass a = pass_base(ctx, is_inv);
+        a.in = x;
+        a.out = scratch;
+        a.log_k = l1;
+        a.log_g = pick_log_g(l1, N2 * N3);
+        a.in_ls = a.out_ls = 1;
+        a.in_ps = a.out_ps = N2 * N3;
+        a.tw_tab = H;
+        a.tw_log_n = H_log_n;
+        a.tw_la = tw_mul;
+        a.tw_fb = 1;
+        DP_TRY(launch_pass(ctx, a, N2 * N3));
+        NttPass b = pass_base(ctx, is_inv);
+        b.in = scratch;
+        b.out = scratch;
+        b.log_k = l2;
+        b.log_g = pick_log_g(l2, N3);
+        b.n_outer = (uint32_t)N1;
+        b.in_os = b.out_os = N2 * N3;
+        b.in_ls = b.out_ls = 1;
+        b.in_ps = b.out_ps = N3;
+        b.tw_tab = H;
+        b.tw_log_n = H_log_n;
+        b.tw_la = tw_mul * N1;
+        b.tw_fb = 1;
+        DP_TRY(launch_pass(ctx, b, N3));
+        NttPass c3 = pass_base(ctx, is_inv);
+        c3.in = scratch;
+        c3.out = x;
+        c3.log_k = l3;
+        c3.log_g = pick_log_g(l3, N1);
+        c3.n_outer = (uint32_t)N2;  // o = k2
+        c3.in_os = N3;
+        c3.out_os = N1;
+        c3.in_ls = N2 * N3;  // lane = k1
+        c3.out_ls = 1;
+        c3.in_ps = 1;
+        c3.out_ps = N1 * N2;
+        set_final(c3);
+        DP_TRY(launch_pass(ctx, c3, N1));
+    }
+    if (is_coset && is_inv) {
+        DP_LAUNCH(fr_scale_powers_kernel, dim3(blocks_for(N, 256)), dim3(256), 0, ctx->stream, x, N, g.inverse(), ninv);
+        ctx->launches++;
+    }
+    DP_CUDA(ctx, cudaGetLastError());
+    return DP_OK;
+}
+
+int gen_powers(dp_ctx *ctx, Fr *out, uint64_t n, const Fr &base, uint64_t first, uint64_t step, const Fr &mulc) {
+    DP_LAUNCH(fr_gen_powers_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, ctx->stream, out, n, base, first, step, mulc);
+    ctx->launches++;
+    DP_CUDA(ctx, cudaGetLastError());
+    return DP_OK;
+}
+
+int build_domain(dp_ctx *ctx, DomainDev &d, uint64_t min_size) {
+    d.log_n = log2_ceil_u64(min_size);
+    if (d.log_n > 32) return fail(ctx, DP_E_ARG, "domain size 2^%u exceeds the two-adicity of Fr", d.log_n);
+    d.log_r = d.log_n >> 1;  // worker.rs:144-147
+    d.log_c = d.log_n - d.log_r;
+    const uint64_t N = d.n(), r = d.r(), c = d.c();
+    const uint64_t half = N >= 2 ? N / 2 : 1;
+    d.H = (Fr *)ctx->pool.alloc(half * sizeof(Fr));
+    d.g_row = (Fr *)ctx->pool.alloc(r * sizeof(Fr));
+    d.g_col = (Fr *)ctx->pool.alloc(c * sizeof(Fr));
+    d.gi_col = (Fr *)ctx->pool.alloc(c * sizeof(Fr));
+    d.gi_pt = (Fr *)ctx->pool.alloc(r * sizeof(Fr));
+    if (!d.H || !d.g_row || !d.g_col || !d.gi_col || !d.gi_pt) return fail(ctx, DP_E_OOM, "domain tables (2^%u)", d.log_n);
+    const Fr g = fr_from_u64(7), gi = g.inverse(), one = Fr::one();
+    d.c_inv = fr_from_u64(c).inverse();
+    d.r_inv = fr_from_u64(r).inverse();
+    d.n_inv = fr_from_u64(N).inverse();
+    DP_TRY(gen_powers(ctx, d.H, half, fr_domain_gen(d.log_n), 0, 1, one));
+    DP_TRY(gen_powers(ctx, d.g_row, r, g, 0, 1, one));
+    DP_TRY(gen_powers(ctx, d.g_col, c, g, 0, r, one));
+    DP_TRY(gen_powers(ctx, d.gi_col, c, gi, 0, 1, d.r_inv));
+    DP_TRY(gen_powers(ctx, d.gi_pt, r, gi, 0, c, one));
+    return DP_OK;
+}
+
+void free_domain(dp_ctx *ctx, DomainDev &d) {
+    ctx->pool.release(d.H);
+    ctx->pool.release(d.g_row);
+    ctx->pool.release(d.g_col);
+    ctx->pool.release(d.gi_col);
+    ctx->pool.release(d.gi_pt);
+    d = DomainDev();
+}
+
+void free_task(dp_ctx *ctx, FftTask &t) {
+    if (t.recv && t.recv != t.send) ctx->pool.release(t.recv);
+    if (t.send && t.send != t.rows) ctx->pool.release(t.send);
+    ctx->pool.release(t.rows);
+    t.rows = t.send = t.recv = nullptr;
+}
+
+// ------------------------------------------------------------------ MSM driver (device pointers)
+int msm_device(dp_ctx *ctx, const G1Affine *bases, const uint4 *scalars_dev, uint64_t n, G1JacobianOut *out_dev,
+               uint32_t *err_host_out) {
+    if (n == 0) {
+        const G1JacobianOut id = G1JacobianOut::from_affine(G1Affine::inf());
+        DP_CUDA(ctx, cudaMemcpyAsync(out_dev, &id, sizeof id, cudaMemcpyHostToDevice, ctx->stream));
+        DP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return DP_OK;
+    }
+    if (n >= ((uint64_t)1 << 31)) return fail(ctx, DP_E_ARG, "msm: %llu points exceed 2^31", (unsigned long long)n);
+    const MsmGeom g = msm_geometry(n, ctx->msm_force_c);
+    const uint64_t max_digits = n * g.n_windows;
+    const uint64_t max_tasks = (uint64_t)g.n_keys + max_digits / MSM_TSEG + 1;
+    const uint32_t n_segs = g.n_windows * g.segs_per_window;
+    DevPool &P = ctx->pool;
+    uint32_t *counts = (uint32_t *)P.alloc((g.n_keys + 1) * 4ull);
+    uint32_t *offsets = (uint32_t *)P.alloc((g.n_keys + 1) * 4ull);
+    uint32_t *cursor = (uint32_t *)P.alloc((g.n_keys + 1) * 4ull);
+    uint32_t *task_off = (uint32_t *)P.alloc((g.n_keys + 1) * 4ull);
+    uint32_t *sorted = (uint32_t *)P.alloc(max_digits * 4ull);
+    uint2 *tasks = (uint2 *)P.alloc(max_tasks * sizeof(uint2));
+    G1XYZZ *partials = (G1XYZZ *)P.alloc(max_tasks * sizeof(G1XYZZ));
+    G1XYZZ *seg_sums = (G1XYZZ *)P.alloc((uint64_t)n_segs * sizeof(G1XYZZ));
+    G1XYZZ *win_sums = (G1XYZZ *)P.alloc((uint64_t)g.n_windows * sizeof(G1XYZZ));
+    uint32_t *err = (uint32_t *)P.alloc(4);
+    auto cleanup = [&]() {
+        P.release(counts); P.release(offsets); P.release(cursor); P.release(task_off); P.release(sorted);
+        P.release(tasks); P.release(partials); P.release(seg_sums); P.release(win_sums); P.release(err);
+    };
+    if (!counts || !offsets || !cursor || !task_off || !sorted || !tasks || !partials || !seg_sums || !win_sums || !err) {
+        cleanup();
+        return fail(ctx, DP_E_OOM, "msm scratch for %llu points", (unsigned long long)n);
+    }
+    cudaStream_t st = ctx->stream;
+    cudaMemsetAsync(counts, 0, (g.n_keys + 1) * 4ull, st);
+    cudaMemsetAsync(err, 0, 4, st);
+    DP_LAUNCH(msm_count_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, scalars_dev, n, g, counts, err);
+    DP_LAUNCH(scan_exclusive_kernel, dim3(1), dim3(1024), 0, st, counts, offsets, g.n_keys, 0u);
+    DP_LAUNCH(scan_exclusive_kernel, dim3(1), dim3(1024), 0, st, counts, task_off, g.n_keys, MSM_TSEG);
+    cudaMemcpyAsync(cursor, offsets, (g.n_keys + 1) * 4ull, cudaMemcpyDeviceToDevice, st);
+    DP_LAUNCH(msm_scatter_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, scalars_dev, n, g, cursor, sorted);
+    DP_LAUNCH(msm_tasks_kernel, dim3(blocks_for(g.n_keys, 256)), dim3(256), 0, st, offsets, task_off, g.n_keys, tasks);
+    DP_LAUNCH(msm_accumulate_kernel, dim3(blocks_for(max_tasks, MSM_TPB)), dim3(MSM_TPB), 0, st, tasks,
+              task_off + g.n_keys, sorted, bases, partials);
+    DP_LAUNCH(msm_reduce_kernel, dim3(blocks_for(n_segs, MSM_TPB)), dim3(MSM_TPB), 0, st, partials, task_off, g, seg_sums);
+    DP_LAUNCH(msm_window_sum_kernel, dim3(g.n_windows), dim3(MSM_TPB), 0, st, seg_sums, g, win_sums);
+    DP_LAUNCH(msm_final_kernel, dim3(1), dim3(32), 0, st, win_sums, g, out_dev);
+    ctx->launches += 9;
+    uint32_t err_host = 0;
+    cudaError_t e = cudaMemcpyAsync(&err_host, err, 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cleanup();
+    if (e != cudaSuccess) return fail(ctx, DP_E_CUDA, "msm kernels: %s", cudaGetErrorString(e));
+    if (err_host_out) *err_host_out = err_host;
+    if (err_host) return fail(ctx, DP_E_ARG, "msm: a scalar is not a canonical Fr integer (>= 2^255)");
+    return DP_OK;
+}
+
+FftTask *find_task(dp_ctx *ctx, uint64_t id) {
+    auto it = ctx->tasks.find(id);
+    return it == ctx->tasks.end() ? nullptr : &it->second;
+}
+
+int run_row_phase(dp_ctx *ctx, FftTask &t) {
+    if (t.row_phase_done) return DP_OK;
+    if (t.rows_filled != t.n_rows) return fail(ctx, DP_E_STATE, "fft task: %llu of %llu rows received", (unsigned long long)t.rows_filled, (unsigned long long)t.n_rows);
+    const DomainDev &d = ctx->dom[t.is_quot ? 1 : 0];
+    const uint64_t c = d.c();
+    Fr *scratch = nullptr;
+    if (d.log_c > ctx->max_contig_log_k) {
+        scratch = (Fr *)ctx->pool.alloc(t.n_rows * c * sizeof(Fr));
+        if (!scratch) return fail(ctx, DP_E_OOM, "row-phase scratch");
+    }
+    if (ctx->W > 1 && !t.send) {
+        t.send = (Fr *)ctx->pool.alloc(t.n_rows * c * sizeof(Fr));
+        if (!t.send) return fail(ctx, DP_E_OOM, "exchange send buffer");
+    } else if (ctx->W == 1) {
+        t.send = t.rows;
+    }
+    int rc = plan_row_phase(ctx, d, t.rows, t.send, scratch, t.n_rows, t.row_start, t.is_inv, t.is_coset, ctx->W);
+    ctx->pool.release(scratch);
+    if (rc == DP_OK) t.row_phase_done = true;
+    return rc;
+}
+
+}  // namespace
+
+// =================================================================== C ABI
+extern "C" {
+
+const char *dp_version(void) { return "distributed_plonk_b200 0.1 (sm_100a)"; }
+
+const char *dp_last_error(const dp_ctx *ctx) { return ctx ? ctx->err.c_str() : g_err_noctx.c_str(); }
+
+int dp_create(int cuda_device, uint64_t me, uint64_t n_workers, dp_ctx **out) {
+    if (!out) return fail(nullptr, DP_E_ARG, "dp_create: out is NULL");
+    *out = nullptr;
+    if (n_workers == 0 || (n_workers & (n_workers - 1)) || me >= n_workers)
+        return fail(nullptr, DP_E_ARG, "dp_create: n_workers must be a power of two and me < n_workers");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+        return fail(nullptr, DP_E_CUDA, "dp_create: no CUDA device (this library has no CPU path)");
+    if (cuda_device < 0 || cuda_device >= n_dev) return fail(nullptr, DP_E_ARG, "dp_create: device %d of %d", cuda_device, n_dev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cuda_device) != cudaSuccess) return fail(nullptr, DP_E_CUDA, "cudaGetDeviceProperties");
+    if (prop.major < 10) return fail(nullptr, DP_E_CUDA, "dp_create: device %d is sm_%d%d, need sm_100", cuda_device, prop.major, prop.minor);
+    dp_ctx *ctx = new dp_ctx();
+    ctx->device = cuda_device;
+    ctx->me = me;
+    ctx->W = n_workers;
+    int rc = DP_OK;
+    do {
+        if (cudaSetDevice(cuda_device) != cudaSuccess) { rc = DP_E_CUDA; break; }
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = DP_E_CUDA; break; }
+        cudaEventCreate(&ctx->ev0);
+        cudaEventCreate(&ctx->ev1);
+        if (cudaFuncSetAttribute(ntt_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)ntt_pass_smem_bytes(NTT_WTAB_LOG, 0)) != cudaSuccess) { rc = DP_E_CUDA; break; }
+        const size_t wb = ((size_t)1 << NTT_WTAB_LOG) * sizeof(uint4);
+        ctx->wf_lo = (uint4 *)ctx->pool.alloc(wb);
+        ctx->wf_hi = (uint4 *)ctx->pool.alloc(wb);
+        ctx->wi_lo = (uint4 *)ctx->pool.alloc(wb);
+        ctx->wi_hi = (uint4 *)ctx->pool.alloc(wb);
+        if (!ctx->wf_lo || !ctx->wf_hi || !ctx->wi_lo || !ctx->wi_hi) { rc = DP_E_OOM; break; }
+        const unsigned nb = (1u << NTT_WTAB_LOG) / 256;
+        DP_LAUNCH(ntt_gen_level_table_kernel, dim3(nb), dim3(256), 0, ctx->stream, ctx->wf_lo, ctx->wf_hi, 0u);
+        DP_LAUNCH(ntt_gen_level_table_kernel, dim3(nb), dim3(256), 0, ctx->stream, ctx->wi_lo, ctx->wi_hi, 1u);
+        ctx->launches += 2;
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) { rc = DP_E_CUDA; break; }
+    } while (0);
+    if (rc != DP_OK) {
+        fail(nullptr, rc, "dp_create: CUDA initialisation failed on device %d", cuda_device);
+        ctx->pool.destroy();
+        delete ctx;
+        return rc;
+    }
+    *out = ctx;
+    return DP_OK;
+}
+
+int dp_destroy(dp_ctx *ctx) {
+    if (!ctx) return DP_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->pool.destroy();
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return DP_OK;
+}
+
+int dp_sync(dp_ctx *ctx) {
+    if (!ctx) return DP_E_ARG;
+    DP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DP_OK;
+}
+
+int dp_last_timing(const dp_ctx *ctx, float *kernel_ms, uint64_t *launches) {
+    if (!ctx) return DP_E_ARG;
+    if (kernel_ms) *kernel_ms = ctx->last_ms;
+    if (launches) *launches = ctx->launches - ctx->launches_at_call;
+    return DP_OK;
+}
+
+uint64_t dp_launch_count(const dp_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int dp_init(dp_ctx *ctx, const void *bases, size_t n_bases, uint64_t domain_size, uint64_t quot_domain_size) {
+    if (!ctx) return DP_E_ARG;
+    if (n_bases && !bases) return fail(ctx, DP_E_ARG, "dp_init: bases is NULL");
+    if (domain_size == 0 || quot_domain_size == 0) return fail(ctx, DP_E_ARG, "dp_init: domain sizes must be >= 1");
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    call_begin(ctx);
+    // drop previous state (init may be called again, worker.rs:135-141 overwrites)
+    for (auto &kv : ctx->tasks) free_task(ctx, kv.second);
+    ctx->tasks.clear();
+    ctx->pool.release(ctx->bases);
+    ctx->bases = nullptr;
+    free_domain(ctx, ctx->dom[0]);
+    free_domain(ctx, ctx->dom[1]);
+    ctx->inited = false;
+    ctx->n_bases = n_bases;
+    if (n_bases) {
+        ctx->bases = (G1Affine *)ctx->pool.alloc(n_bases * sizeof(G1Affine));
+        void *staging = ctx->pool.alloc(n_bases * (size_t)DP_G1_AFFINE_BYTES);
+        if (!ctx->bases || !staging) return fail(ctx, DP_E_OOM, "dp_init: %zu bases", n_bases);
+        DP_CUDA(ctx, cudaMemcpyAsync(staging, bases, n_bases * (size_t)DP_G1_AFFINE_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+        DP_LAUNCH(g1_import_ark_kernel, dim3(blocks_for(n_bases, 256)), dim3(256), 0, ctx->stream,
+                  (const uint64_t *)staging, ctx->bases, (uint64_t)n_bases);
+        ctx->launches++;
+        ctx->pool.release(staging);
+    }
+    DP_TRY(build_domain(ctx, ctx->dom[0], domain_size));
+    DP_TRY(build_domain(ctx, ctx->dom[1], quot_domain_size));
+    for (int k = 0; k < 2; k++) {
+        const DomainDev &d = ctx->dom[k];
+        if (d.r() < ctx->W || d.c() < ctx->W)
+            return fail(ctx, DP_E_ARG, "dp_init: domain 2^%u too small to split over %llu workers", d.log_n, (unsigned long long)ctx->W);
+    }
+    DP_TRY(call_end(ctx, true));
+    ctx->inited = true;
+    return DP_OK;
+}
+
+int dp_msm(dp_ctx *ctx, uint64_t start, uint64_t end, const void *scalars, size_t n_scalars, void *out) {
+    if (!ctx || !out) return fail(ctx, DP_E_ARG, "dp_msm: NULL argument");
+    if (!ctx->inited) return fail(ctx, DP_E_STATE, "dp_msm before dp_init");
+    if (start > end || end > ctx->n_bases) return fail(ctx, DP_E_ARG, "dp_msm: range [%llu,%llu) outside %llu bases", (unsigned long long)start, (unsigned long long)end, (unsigned long long)ctx->n_bases);
+    if (n_scalars && !scalars) return fail(ctx, DP_E_ARG, "dp_msm: scalars is NULL");
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t n = (end - start) < n_scalars ? (end - start) : n_scalars;
+    call_begin(ctx);
+    uint4 *sc = (uint4 *)ctx->pool.alloc((n ? n : 1) * 32);
+    G1JacobianOut *od = (G1JacobianOut *)ctx->pool.alloc(sizeof(G1JacobianOut));
+    if (!sc || !od) return fail(ctx, DP_E_OOM, "dp_msm buffers");
+    if (n) DP_CUDA(ctx, cudaMemcpyAsync(sc, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = msm_device(ctx, ctx->bases + start, sc, n, od, nullptr);
+    if (rc == DP_OK) {
+        cudaError_t e = cudaMemcpyAsync(out, od, sizeof(G1JacobianOut), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) rc = fail(ctx, DP_E_CUDA, "dp_msm D2H: %s", cudaGetErrorString(e));
+    }
+    if (rc == DP_OK) rc = call_end(ctx, true);
+    ctx->pool.release(sc);
+    ctx->pool.release(od);
+    return rc;
+}
+
+int dp_msm_dev(dp_ctx *ctx, uint64_t start, uint64_t end, const void *scalars_dev, size_t n_scalars, void *out_dev) {
+    if (!ctx || !out_dev) return fail(ctx, DP_E_ARG, "dp_msm_dev: NULL argument");
+    if (!ctx->inited) return fail(ctx, DP_E_STATE, "dp_msm_dev before dp_init");
+    if (start > end || end > ctx->n_bases) return fail(ctx, DP_E_ARG, "dp_msm_dev: bad range");
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t n = (end - start) < n_scalars ? (end - start) : n_scalars;
+    call_begin(ctx);
+    DP_TRY(msm_device(ctx, ctx->bases + start, (const uint4 *)scalars_dev, n, (G1JacobianOut *)out_dev, nullptr));
+    return call_end(ctx, true);
+}
+
+static int commit_device(dp_ctx *ctx, const Fr *coeffs_dev, uint64_t n, G1JacobianOut *out_dev) {
+    // into_repr + zero-pad to bases.len() (worker.rs:118-120)
+    const uint64_t nb = ctx->n_bases;
+    if (n > nb) return fail(ctx, DP_E_ARG, "commit: %llu coefficients > %llu bases", (unsigned long long)n, (unsigned long long)nb);
+    Fr *sc = (Fr *)ctx->pool.alloc((nb ? nb : 1) * sizeof(Fr));
+    if (!sc) return fail(ctx, DP_E_OOM, "commit scalars");
+    if (nb) {
+        DP_LAUNCH(fr_into_repr_kernel, dim3(blocks_for(nb, 256)), dim3(256), 0, ctx->stream, coeffs_dev, sc, n, nb);
+        ctx->launches++;
+    }
+    int rc = msm_device(ctx, ctx->bases, (const uint4 *)sc, nb, out_dev, nullptr);
+    ctx->pool.release(sc);
+    return rc;
+}
+
+int dp_commit(dp_ctx *ctx, const void *coeffs, size_t n, void *out) {
+    if (!ctx || !out) return fail(ctx, DP_E_ARG, "dp_commit: NULL argument");
+    if (!ctx->inited) return fail(ctx, DP_E_STATE, "dp_commit before dp_init");
+    if (n && !coeffs) return fail(ctx, DP_E_ARG, "dp_commit: coeffs is NULL");
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    call_begin(ctx);
+    Fr *cd = (Fr *)ctx->pool.alloc((n ? n : 1) * sizeof(Fr));
+    G1JacobianOut *od = (G1JacobianOut *)ctx->pool.alloc(sizeof(G1JacobianOut));
+    if (!cd || !od) return fail(ctx, DP_E_OOM, "dp_commit buffers");
+    if (n) DP_CUDA(ctx, cudaMemcpyAsync(cd, coeffs, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = commit_device(ctx, cd, n, od);
+    if (rc == DP_OK) {
+        cudaError_t e = cudaMemcpyAsync(out, od, sizeof(G1JacobianOut), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) rc = fail(ctx, DP_E_CUDA, "dp_commit D2H: %s", cudaGetErrorString(e));
+    }
+    if (rc == DP_OK) rc = call_end(ctx, true);
+    ctx->pool.release(cd);
+    ctx->pool.release(od);
+    return rc;
+}
+
+int dp_fft_init(dp_ctx *ctx, uint64_t id, const dp_fft_workload *workloads, size_t n_workloads, int is_quot, int is_inv,
+                int is_coset) {
+    if (!ctx || !workloads) return fail(ctx, DP_E_ARG, "dp_fft_init: NULL argument");
+    if (!ctx->inited) return fail(ctx, DP_E_STATE, "dp_fft_init before dp_init");
+    if (n_workloads != ctx->W) return fail(ctx, DP_E_ARG, "dp_fft_init: %zu workloads for %llu workers", n_workloads, (unsigned long long)ctx->W);
+    if (ctx->tasks.count(id)) return fail(ctx, DP_E_STATE, "dp_fft_init: task %llu already open", (unsigned long long)id);
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const DomainDev &d = ctx->dom[is_quot ? 1 : 0];
+    const uint64_t r = d.r(), c = d.c(), W = ctx->W;
+    for (uint64_t w = 0; w < W; w++) {
+        const dp_fft_workload &x = workloads[w];
+        if (x.row_start != w * r / W || x.row_end != (w + 1) * r / W || x.col_start != w * c / W || x.col_end != (w + 1) * c / W)
+            return fail(ctx, DP_E_ARG, "dp_fft_init: workload %llu is not the equal block split of %llu x %llu", (unsigned long long)w, (unsigned long long)r, (unsigned long long)c);
+    }
+    FftTask t;
+    t.is_quot = is_quot != 0;
+    t.is_inv = is_inv != 0;
+    t.is_coset = is_coset != 0;
+    t.wl.assign(workloads, workloads + n_workloads);
+    const dp_fft_workload &mine = workloads[ctx->me];
+    t.n_rows = mine.row_end - mine.row_start;
+    t.n_cols = mine.col_end - mine.col_start;
+    t.row_start = mine.row_start;
+    t.col_start = mine.col_start;
+    t.rows = (Fr *)ctx->pool.alloc(t.n_rows * c * sizeof(Fr));
+    if (!t.rows) return fail(ctx, DP_E_OOM, "dp_fft_init: rows buffer");
+    t.row_seen.assign(t.n_rows, 0);
+    ctx->tasks.emplace(id, std::move(t));
+    return DP_OK;
+}
+
+int dp_fft1_rows(dp_ctx *ctx, uint64_t id, uint64_t i_first, uint64_t n_rows, const void *rows) {
+    if (!ctx || !rows) return fail(ctx, DP_E_ARG, "dp_fft1: NULL argument");
+    FftTask *t = find_task(ctx, id);
+    if (!t) return fail(ctx, DP_E_ARG, "dp_fft1: unknown task %llu", (unsigned long long)id);
+    if (t->row_phase_done) return fail(ctx, DP_E_STATE, "dp_fft1 after fft2_prepare");
+    if (i_first + n_rows > t->n_rows) return fail(ctx, DP_E_ARG, "dp_fft1: rows [%llu,%llu) of %llu", (unsigned long long)i_first, (unsigned long long)(i_first + n_rows), (unsigned long long)t->n_rows);
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t c = ctx->dom[t->is_quot ? 1 : 0].c();
+    DP_CUDA(ctx, cudaMemcpyAsync(t->rows + i_first * c, rows, n_rows * c * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    for (uint64_t i = i_first; i < i_first + n_rows; i++)
+        if (!t->row_seen[i]) {
+            t->row_seen[i] = 1;
+            t->rows_filled++;
+        }
+    return DP_OK;
+}
+
+int dp_fft1(dp_ctx *ctx, uint64_t id, uint64_t i, const void *row, size_t len) {
+    if (!ctx) return DP_E_ARG;
+    FftTask *t = find_task(ctx, id);
+    if (!t) return fail(ctx, DP_E_ARG, "dp_fft1: unknown task %llu", (unsigned long long)id);
+    const uint64_t c = ctx->dom[t->is_quot ? 1 : 0].c();
+    if (len != c) return fail(ctx, DP_E_ARG, "dp_fft1: row of %zu elements, expected %llu", len, (unsigned long long)c);
+    return dp_fft1_rows(ctx, id, i, 1, row);
+}
+
+int dp_fft_exchange_begin(dp_ctx *ctx, uint64_t id, void **send_dev, void **recv_dev, uint64_t *block_elems) {
+    if (!ctx || !send_dev || !recv_dev || !block_elems) return fail(ctx, DP_E_ARG, "dp_fft_exchange_begin: NULL argument");
+    FftTask *t = find_task(ctx, id);
+    if (!t) return fail(ctx, DP_E_ARG, "dp_fft_exchange_begin: unknown task %llu", (unsigned long long)id);
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    call_begin(ctx);
+    DP_TRY(run_row_phase(ctx, *t));
+    if (!t->recv) {
+        if (ctx->W == 1) {
+            t->recv = t->send;
+        } else {
+            const uint64_t r = ctx->dom[t->is_quot ? 1 : 0].r();
+            t->recv = (Fr *)ctx->pool.alloc(r * t->n_cols * sizeof(Fr));
+            if (!t->recv) return fail(ctx, DP_E_OOM, "exchange recv buffer");
+        }
+    }
+    DP_TRY(call_end(ctx, true));  // buffers must be complete before the caller's collective reads them
+    *send_dev = t->send;
+    *recv_dev = t->recv;
+    *block_elems = t->n_rows * t->n_cols;
+    return DP_OK;
+}
+
+int dp_fft_exchange_end(dp_ctx *ctx, uint64_t id) {
+    if (!ctx) return DP_E_ARG;
+    FftTask *t = find_task(ctx, id);
+    if (!t) return fail(ctx, DP_E_ARG, "dp_fft_exchange_end: unknown task %llu", (unsigned long long)id);
+    if (!t->row_phase_done || !t->recv) return fail(ctx, DP_E_STATE, "dp_fft_exchange_end before dp_fft_exchange_begin");
+    t->exchanged = true;
+    return DP_OK;
+}
+
+int dp_fft2_prepare(dp_ctx *ctx, uint64_t id) {
+    if (!ctx) return DP_E_ARG;
+    FftTask *t = find_task(ctx, id);
+    if (!t) return fail(ctx, DP_E_ARG, "dp_fft2_prepare: unknown task %llu", (unsigned long long)id);
+    if (ctx->W > 1)
+        return fail(ctx, DP_E_COMM, "dp_fft2_prepare: %llu workers but no peer transport attached; use dp_fft_exchange_begin/_end around an all-to-all", (unsigned long long)ctx->W);
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    call_begin(ctx);
+    DP_TRY(run_row_phase(ctx, *t));
+    t->recv = t->send;
+    t->exchanged = true;
+    return call_end(ctx, false);
+}
+
+static int col_phase_to(dp_ctx *ctx, FftTask &t, Fr *cols_dev) {
+    const DomainDev &d = ctx->dom[t.is_quot ? 1 : 0];
+    return plan_col_phase(ctx, d, t.recv, cols_dev, t.n_cols, t.col_start, t.is_inv, t.is_coset);
+}
+
+int dp_fft2(dp_ctx *ctx, uint64_t id, void *out, size_t out_bytes) {
+    if (!ctx || !out) return fail(ctx, DP_E_ARG, "dp_fft2: NULL argument");
+    FftTask *t = find_task(ctx, id);
+    if (!t) return fail(ctx, DP_E_ARG, "dp_fft2: unknown task %llu", (unsigned long long)id);
+    if (!t->exchanged) return fail(ctx, DP_E_STATE, "dp_fft2 before fft2_prepare / exchange");
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t r = ctx->dom[t->is_quot ? 1 : 0].r();
+    const size_t bytes = t->n_cols * r * sizeof(Fr);
+    if (out_bytes < bytes) return fail(ctx, DP_E_ARG, "dp_fft2: out buffer %zu < %zu bytes", out_bytes, bytes);
+    call_begin(ctx);
+    Fr *cols = (Fr *)ctx->pool.alloc(bytes);
+    if (!cols) return fail(ctx, DP_E_OOM, "dp_fft2: cols buffer");
+    int rc = col_phase_to(ctx, *t, cols);
+    if (rc == DP_OK) {
+        cudaError_t e = cudaMemcpyAsync(out, cols, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) rc = fail(ctx, DP_E_CUDA, "dp_fft2 D2H: %s", cudaGetErrorString(e));
+    }
+    if (rc == DP_OK) rc = call_end(ctx, true);
+    ctx->pool.release(cols);
+    free_task(ctx, *t);  // worker.rs:378
+    ctx->tasks.erase(id);
+    return rc;
+}
+
+int dp_fft_dev(dp_ctx *ctx, const void *rows_dev, void *cols_dev, int is_quot, int is_inv, int is_coset) {
+    if (!ctx || !rows_dev || !cols_dev) return fail(ctx, DP_E_ARG, "dp_fft_dev: NULL argument");
+    if (!ctx->inited) return fail(ctx, DP_E_STATE, "dp_fft_dev before dp_init");
+    if (ctx->W != 1) return fail(ctx, DP_E_COMM, "dp_fft_dev: multi-worker exchange needs the split API");
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const DomainDev &d = ctx->dom[is_quot ? 1 : 0];
+    const uint64_t N = d.n();
+    call_begin(ctx);
+    Fr *work = (Fr *)ctx->pool.alloc(N * sizeof(Fr));
+    const bool need_scratch = d.log_c > ctx->max_contig_log_k;
+    Fr *scratch = need_scratch ? (Fr *)ctx->pool.alloc(N * sizeof(Fr)) : nullptr;
+    if (!work || (need_scratch && !scratch)) return fail(ctx, DP_E_OOM, "dp_fft_dev buffers");
+    int rc = plan_row_phase(ctx, d, (const Fr *)rows_dev, work, scratch, d.r(), 0, is_inv != 0, is_coset != 0, 1);
+    if (rc == DP_OK) rc = plan_col_phase(ctx, d, work, (Fr *)cols_dev, d.c(), 0, is_inv != 0, is_coset != 0);
+    ctx->pool.release(work);
+    ctx->pool.release(scratch);
+    if (rc != DP_OK) return rc;
+    return call_end(ctx, true);
+}
+
+static int ntt_device(dp_ctx *ctx, Fr *x, uint32_t log_n, bool is_inv, bool is_coset) {
+    // twiddles: reuse a resident domain table when it is at least as large, else build one
+    const DomainDev *d = nullptr;
+    for (int k = 0; k < 2; k++)
+        if (ctx->dom[k].H && ctx->dom[k].log_n >= log_n && (!d || ctx->dom[k].log_n < d->log_n)) d = &ctx->dom[k];
+    const uint64_t N = (uint64_t)1 << log_n;
+    Fr *tmpH = nullptr;
+    const Fr *H = d ? d->H : nullptr;
+    uint32_t H_log = d ? d->log_n : log_n;
+    const bool multi = log_n > ctx->max_contig_log_k;
+    if (!H && multi) {
+        tmpH = (Fr *)ctx->pool.alloc((N / 2) * sizeof(Fr));
+        if (!tmpH) return fail(ctx, DP_E_OOM, "dp_ntt twiddles");
+        DP_TRY(gen_powers(ctx, tmpH, N / 2, fr_domain_gen(log_n), 0, 1, Fr::one()));
+        H = tmpH;
+    }
+    Fr *scratch = multi ? (Fr *)ctx->pool.alloc(N * sizeof(Fr)) : nullptr;
+    if (multi && !scratch) return fail(ctx, DP_E_OOM, "dp_ntt scratch");
+    int rc = plan_whole_ntt(ctx, d, x, scratch, log_n, is_inv, is_coset, H, H_log);
+    ctx->pool.release(scratch);
+    ctx->pool.release(tmpH);
+    return rc;
+}
+
+int dp_ntt_dev(dp_ctx *ctx, void *data_dev, uint32_t log_n, int is_inv, int is_coset) {
+    if (!ctx || !data_dev) return fail(ctx, DP_E_ARG, "dp_ntt_dev: NULL argument");
+    if (log_n > 32) return fail(ctx, DP_E_ARG, "dp_ntt_dev: log_n %u", log_n);
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    call_begin(ctx);
+    DP_TRY(ntt_device(ctx, (Fr *)data_dev, log_n, is_inv != 0, is_coset != 0));
+    return call_end(ctx, true);
+}
+
+int dp_ntt(dp_ctx *ctx, void *data, size_t n, uint32_t log_n, int is_inv, int is_coset) {
+    if (!ctx || !data) return fail(ctx, DP_E_ARG, "dp_ntt: NULL argument");
+    if (log_n > 32) return fail(ctx, DP_E_ARG, "dp_ntt: log_n %u", log_n);
+    const uint64_t N = (uint64_t)1 << log_n;
+    if (n > N) return fail(ctx, DP_E_ARG, "dp_ntt: %zu elements > domain 2^%u", n, log_n);
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    call_begin(ctx);
+    Fr *x = (Fr *)ctx->pool.alloc(N * sizeof(Fr));
+    if (!x) return fail(ctx, DP_E_OOM, "dp_ntt buffer");
+    int rc = DP_OK;
+    cudaError_t e = cudaMemcpyAsync(x, data, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && n < N) e = cudaMemsetAsync(x + n, 0, (N - n) * sizeof(Fr), ctx->stream);
+    if (e != cudaSuccess) rc = fail(ctx, DP_E_CUDA, "dp_ntt H2D: %s", cudaGetErrorString(e));
+    if (rc == DP_OK) rc = ntt_device(ctx, x, log_n, is_inv != 0, is_coset != 0);
+    if (rc == DP_OK) {
+        e = cudaMemcpyAsync(data, x, N * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) rc = fail(ctx, DP_E_CUDA, "dp_ntt D2H: %s", cudaGetErrorString(e));
+    }
+    if (rc == DP_OK) rc = call_end(ctx, true);
+    ctx->pool.release(x);
+    return rc;
+}
+
+// wire = (b0 + b1*X) * (X^n - 1) + poly   (worker.rs:400-401)
+__global__ void round1_blind_kernel(Fr *wire, uint64_t n, Fr b0, Fr b1) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    if (n >= 2) {
+        wire[0] = wire[0] - b0;
+        wire[1] = wire[1] - b1;
+        wire[n] = b0;
+        wire[n + 1] = b1;
+    } else {  // n == 1: X^1 - 1
+        wire[0] = wire[0] - b0;
+        wire[1] = b0 - b1;
+        wire[2] = b1;
+    }
+}
+
+int dp_round1(dp_ctx *ctx, const void *evals, size_t n, const void *blind, void *out) {
+    if (!ctx || !evals || !out) return fail(ctx, DP_E_ARG, "dp_round1: NULL argument");
+    if (!ctx->inited) return fail(ctx, DP_E_STATE, "dp_round1 before dp_init");
+    const DomainDev &d = ctx->dom[0];
+    const uint64_t N = d.n();
+    if (n > N) return fail(ctx, DP_E_ARG, "dp_round1: %zu evaluations > domain %llu", n, (unsigned long long)N);
+    if (N + 2 > ctx->n_bases) return fail(ctx, DP_E_ARG, "dp_round1: %llu bases cannot commit a degree-%llu polynomial", (unsigned long long)ctx->n_bases, (unsigned long long)(N + 1));
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    call_begin(ctx);
+    ctx->pool.release(ctx->wire);
+    ctx->wire = (Fr *)ctx->pool.alloc((N + 2) * sizeof(Fr));
+    G1JacobianOut *od = (G1JacobianOut *)ctx->pool.alloc(sizeof(G1JacobianOut));
+    if (!ctx->wire || !od) return fail(ctx, DP_E_OOM, "dp_round1 buffers");
+    ctx->wire_len = N + 2;
+    DP_CUDA(ctx, cudaMemcpyAsync(ctx->wire, evals, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    DP_CUDA(ctx, cudaMemsetAsync(ctx->wire + n, 0, (N + 2 - n) * sizeof(Fr), ctx->stream));
+    DP_TRY(ntt_device(ctx, ctx->wire, d.log_n, true, false));
+    Fr b[2];
+    if (blind) {
+        memcpy(b, blind, sizeof b);
+    } else {  // SplitMix64-driven blinders (the reference uses ThreadRng: not reproducible either way)
+        for (int k = 0; k < 2; k++) {
+            Fr v = Fr::zero();
+            for (int w = 0; w < 8; w += 2) {
+                uint64_t z = (ctx->rng_state += 0x9E3779B97F4A7C15ull);
+                z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+                z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+                z ^= z >> 31;
+                v.l[w] = (uint32_t)z;
+                v.l[w + 1] = (uint32_t)(z >> 32);
+            }
+            v.l[7] &= 0x3fffffffu;  // < 2^254 < r: already a valid (Montgomery-form) residue
+            b[k] = v;
+        }
+    }
+    DP_LAUNCH(round1_blind_kernel, dim3(1), dim3(32), 0, ctx->stream, ctx->wire, N, b[0], b[1]);
+    ctx->launches++;
+    int rc = commit_device(ctx, ctx->wire, N + 2, od);
+    if (rc == DP_OK) {
+        cudaError_t e = cudaMemcpyAsync(out, od, sizeof(G1JacobianOut), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) rc = fail(ctx, DP_E_CUDA, "dp_round1 D2H: %s", cudaGetErrorString(e));
+    }
+    if (rc == DP_OK) rc = call_end(ctx, true);
+    ctx->pool.release(od);
+    return rc;
+}
+
+int dp_get_wire(dp_ctx *ctx, void *out, size_t out_bytes, size_t *n_coeffs) {
+    if (!ctx) return DP_E_ARG;
+    if (!ctx->wire) return fail(ctx, DP_E_STATE, "dp_get_wire before dp_round1");
+    if (n_coeffs) *n_coeffs = ctx->wire_len;
+    if (!out) return DP_OK;
+    if (out_bytes < ctx->wire_len * sizeof(Fr)) return fail(ctx, DP_E_ARG, "dp_get_wire: buffer too small");
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    DP_CUDA(ctx, cudaMemcpyAsync(out, ctx->wire, ctx->wire_len * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    DP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DP_OK;
+}
+
+int dp_debug_set_limits(dp_ctx *ctx, uint32_t max_contig_log_k, uint32_t max_strided_log_k, int msm_window_bits) {
+    if (!ctx) return DP_E_ARG;
+    if (max_contig_log_k < 1 || max_contig_log_k > NTT_WTAB_LOG || max_strided_log_k < 1 || max_strided_log_k > NTT_MAX_STRIDED_LOG_K ||
+        msm_window_bits < 0 || msm_window_bits > 20 || msm_window_bits == 1)
+        return fail(ctx, DP_E_ARG, "dp_debug_set_limits: out of range");
+    ctx->max_contig_log_k = max_contig_log_k;
+    ctx->max_strided_log_k = max_strided_log_k;
+    ctx->msm_force_c = msm_window_bits;
+    return DP_OK;
+}
+
+int dp_peer_arena_create(dp_ctx *ctx, uint64_t, void *) {
+    return fail(ctx, DP_E_COMM, "peer arena: not available in this build; use the split exchange API");
+}
+int dp_peer_attach(dp_ctx *ctx, uint64_t, const void *) {
+    return fail(ctx, DP_E_COMM, "peer arena: not available in this build; use the split exchange API");
+}
+
+}  // extern "C"

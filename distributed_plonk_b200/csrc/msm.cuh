@@ -1,0 +1,280 @@
+// Pippenger-bucket multi-scalar multiplication over BLS12-381 G1 for sm_100a.
+//
+// Replaces ark-ec 0.3.0 VariableBaseMSM::multi_scalar_mul as called by the reference worker
+// (src/worker.rs:117-123 commit_polynomial, 159-185 var_msm; twin call sites
+// src/dispatcher.rs:1042-1060, src/dispatcher2.rs:834-843).  Same function (sum_i s_i * P_i over
+// canonical 256-bit scalars and affine bases, zero scalars and infinity bases contribute nothing),
+// different schedule - chosen for a GPU, which is legal because the result is a unique group
+// element:
+//
+//   1. msm_count      signed-digit recode (digits in [-2^(c-1), 2^(c-1)]), histogram of
+//                     (window, |digit|) keys with L2 atomics; 128-bit coalesced scalar loads
+//   2. scan           exclusive prefix sums -> bucket offsets and task offsets
+//   3. msm_scatter    counting-sort the point indices by key (sign kept in bit 31)
+//   4. msm_tasks      cut every bucket into tasks of <= TSEG points (load balance for skewed
+//                     scalars: witness vectors are full of 0/1/small values)
+//   5. msm_accumulate one thread per task: XYZZ accumulator in registers, mixed additions of the
+//                     gathered affine bases (96 B = 6 x 128-bit loads each)
+//   6. msm_reduce     per window, per segment of buckets: running-sum reduction
+//                     sum_k k*B_k (+ small scalar multiple for the segment offset)
+//   7. msm_window_sum block per window: tree reduction of the segment sums
+//   8. msm_final      Horner over windows (c doublings each), normalise, emit 144-byte Jacobian
+//
+// Work: N*ceil(256/c) mixed additions (10 Fq mul) dominate; HBM traffic is ~96 B gathered per
+// addition plus 32 B per scalar per pass - the kernel set is bound by the INT32 multiply pipe,
+// not by HBM (see DESIGN.md for the roofline numbers).
+#pragma once
+#include "g1.cuh"
+#include "rt.cuh"
+
+namespace dp {
+
+constexpr uint32_t MSM_TSEG = 256;      // max points per accumulate task
+constexpr uint32_t MSM_SEG = 32;        // buckets per reduce segment
+constexpr int MSM_TPB = 128;
+
+struct MsmGeom {
+    uint32_t c;          // window bits
+    uint32_t n_windows;  // ceil(256 / c)
+    uint32_t bpw;        // buckets per window = 2^(c-1)
+    uint32_t n_keys;     // n_windows * bpw
+    uint32_t seg;        // buckets per reduce segment
+    uint32_t segs_per_window;
+};
+
+inline MsmGeom msm_geometry(uint64_t n, int force_c = 0) {
+    // cost model in Fq multiplications: n*W mixed adds (10) + 2*W*2^(c-1) full adds (14)
+    // + Horner/normalise tail; pick the cheapest c in [4, 18]
+    uint32_t best_c = 4;
+    double best = 1e300;
+    for (uint32_t c = 4; c <= 18; c++) {
+        double w = (double)((256 + c - 1) / c);
+        double cost = (double)n * w * 10.0 + 2.0 * w * (double)(1u << (c - 1)) * 14.0;
+        if (cost < best) {
+            best = cost;
+            best_c = c;
+        }
+    }
+    MsmGeom g;
+    g.c = force_c ? (uint32_t)force_c : best_c;
+    g.n_windows = (256 + g.c - 1) / g.c;
+    g.bpw = 1u << (g.c - 1);
+    g.n_keys = g.n_windows * g.bpw;
+    g.seg = g.bpw < MSM_SEG ? g.bpw : MSM_SEG;
+    g.segs_per_window = g.bpw / g.seg;
+    return g;
+}
+
+// ------------------------------------------------------------------ bases import (init time)
+// raw ark GroupAffine<G1> (104 B: x@0, y@48 Fq Montgomery, infinity flag @96; utils.rs:27-43)
+// -> device affine (96 B, infinity = (0,0))
+__global__ void g1_import_ark_kernel(const uint64_t *ark, G1Affine *out, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t *src = ark + i * 13;  // 104 B = 13 u64
+    G1Affine p;
+    const bool inf = (src[12] & 0xff) != 0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        uint64_t a = inf ? 0 : src[k], b = inf ? 0 : src[6 + k];
+        p.x.l[2 * k] = (uint32_t)a;
+        p.x.l[2 * k + 1] = (uint32_t)(a >> 32);
+        p.y.l[2 * k] = (uint32_t)b;
+        p.y.l[2 * k + 1] = (uint32_t)(b >> 32);
+    }
+    out[i] = p;
+}
+
+// ------------------------------------------------------------------ digit recode
+struct Scalar256 {
+    uint32_t w[8];
+};
+DP_D Scalar256 load_scalar(const uint4 *scalars, uint64_t i) {
+    const uint4 a = scalars[2 * i], b = scalars[2 * i + 1];
+    Scalar256 s;
+    s.w[0] = a.x; s.w[1] = a.y; s.w[2] = a.z; s.w[3] = a.w;
+    s.w[4] = b.x; s.w[5] = b.y; s.w[6] = b.z; s.w[7] = b.w;
+    return s;
+}
+// c raw bits of the scalar starting at bit position `pos`
+DP_D uint32_t scalar_bits(const Scalar256 &s, uint32_t pos, uint32_t c) {
+    const uint32_t word = pos >> 5, sh = pos & 31;
+    if (word >= 8) return 0;
+    uint32_t v = s.w[word] >> sh;
+    if (sh && word + 1 < 8) v |= s.w[word + 1] << (32 - sh);
+    return v & ((1u << c) - 1);
+}
+
+// Calls f(window, key, negative) for every non-zero signed digit; returns the carry out of the top
+// window (non-zero only for scalars >= 2^255 or so: not canonical Fr, reported as DP_E_ARG).
+template <class F>
+DP_D uint32_t for_each_digit(const Scalar256 &s, const MsmGeom &g, F f) {
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < g.n_windows; w++) {
+        uint32_t raw = scalar_bits(s, w * g.c, g.c) + carry;
+        carry = 0;
+        if (raw > g.bpw) {  // digit = raw - 2^c  (negative)
+            const uint32_t mag = (1u << g.c) - raw;
+            carry = 1;
+            if (mag) f(w, w * g.bpw + (mag - 1), 1u);
+        } else if (raw) {
+            f(w, w * g.bpw + (raw - 1), 0u);
+        }
+    }
+    return carry;
+}
+
+__global__ void msm_count_kernel(const uint4 *scalars, uint64_t n, MsmGeom g, uint32_t *counts, uint32_t *err) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Scalar256 s = load_scalar(scalars, i);
+    const uint32_t carry = for_each_digit(s, g, [&](uint32_t, uint32_t key, uint32_t) { atomicAdd(&counts[key], 1u); });
+    if (carry) atomicOr(err, 1u);
+}
+
+__global__ void msm_scatter_kernel(const uint4 *scalars, uint64_t n, MsmGeom g, uint32_t *cursor, uint32_t *sorted) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Scalar256 s = load_scalar(scalars, i);
+    for_each_digit(s, g, [&](uint32_t, uint32_t key, uint32_t neg) {
+        const uint32_t pos = atomicAdd(&cursor[key], 1u);
+        sorted[pos] = (uint32_t)i | (neg << 31);
+    });
+}
+
+// ------------------------------------------------------------------ single-block exclusive scan
+// out[i] = sum_{k<i} t(in[k]) for i <= n (n+1 outputs);  t(x) = x  or  ceil(x / div) when div > 0
+__global__ void scan_exclusive_kernel(const uint32_t *in, uint32_t *out, uint32_t n, uint32_t div) {
+    __shared__ uint32_t part[1024];
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t chunk = (n + nt - 1) / nt;
+    const uint32_t lo = tid * chunk < n ? tid * chunk : n;
+    const uint32_t hi = lo + chunk < n ? lo + chunk : n;
+    uint32_t sum = 0;
+    for (uint32_t i = lo; i < hi; i++) {
+        uint32_t v = in[i];
+        sum += div ? (v + div - 1) / div : v;
+    }
+    part[tid] = sum;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over the per-thread sums
+    for (uint32_t off = 1; off < nt; off <<= 1) {
+        uint32_t add = tid >= off ? part[tid - off] : 0;
+        __syncthreads();
+        part[tid] += add;
+        __syncthreads();
+    }
+    uint32_t run = tid ? part[tid - 1] : 0;
+    for (uint32_t i = lo; i < hi; i++) {
+        out[i] = run;
+        uint32_t v = in[i];
+        run += div ? (v + div - 1) / div : v;
+    }
+    if (tid == nt - 1) out[n] = part[nt - 1];
+}
+
+// ------------------------------------------------------------------ tasks
+// tasks[t] = {first index into sorted[], number of points}; bucket `key` owns tasks
+// [task_off[key], task_off[key+1])
+__global__ void msm_tasks_kernel(const uint32_t *offsets, const uint32_t *task_off, uint32_t n_keys, uint2 *tasks) {
+    const uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
+    if (key >= n_keys) return;
+    const uint32_t start = offsets[key], cnt = offsets[key + 1] - start;
+    uint32_t t = task_off[key];
+    for (uint32_t done = 0; done < cnt; done += MSM_TSEG, t++) {
+        uint2 e;
+        e.x = start + done;
+        e.y = cnt - done < MSM_TSEG ? cnt - done : MSM_TSEG;
+        tasks[t] = e;
+    }
+}
+
+DP_D G1Affine load_affine(const G1Affine *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    G1Affine r;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        uint4 a = q[k], b = q[3 + k];
+        r.x.l[4 * k] = a.x; r.x.l[4 * k + 1] = a.y; r.x.l[4 * k + 2] = a.z; r.x.l[4 * k + 3] = a.w;
+        r.y.l[4 * k] = b.x; r.y.l[4 * k + 1] = b.y; r.y.l[4 * k + 2] = b.z; r.y.l[4 * k + 3] = b.w;
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(MSM_TPB) msm_accumulate_kernel(const uint2 *tasks, const uint32_t *n_tasks,
+                                                                  const uint32_t *sorted, const G1Affine *bases,
+                                                                  G1XYZZ *partials) {
+    // the grid is sized for the worst case; the real task count is only known on the device
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= *n_tasks) return;
+    const uint2 task = tasks[t];
+    G1XYZZ acc = G1XYZZ::inf();
+    for (uint32_t k = 0; k < task.y; k++) {
+        const uint32_t e = sorted[task.x + k];
+        G1Affine p = load_affine(bases + (e & 0x7fffffffu));
+        if (e >> 31) p = p.neg();
+        acc = acc.add_mixed(p);
+    }
+    partials[t] = acc;
+}
+
+// sum of the partial sums of one bucket
+DP_D G1XYZZ bucket_sum(const G1XYZZ *partials, const uint32_t *task_off, uint32_t key) {
+    G1XYZZ b = G1XYZZ::inf();
+    for (uint32_t t = task_off[key]; t < task_off[key + 1]; t++) b = b.add(partials[t]);
+    return b;
+}
+
+// k * P for a small non-negative integer k
+DP_D G1XYZZ small_mul(const G1XYZZ &p, uint32_t k) {
+    G1XYZZ acc = G1XYZZ::inf();
+    for (int b = 31 - __clz((int)(k | 1)); b >= 0; b--) {
+        acc = acc.dbl();
+        if ((k >> b) & 1) acc = acc.add(p);
+    }
+    return k ? acc : G1XYZZ::inf();
+}
+
+// one thread per (window, segment): sum_{k in segment} k * B_k with the running-sum trick
+__global__ void __launch_bounds__(MSM_TPB) msm_reduce_kernel(const G1XYZZ *partials, const uint32_t *task_off, MsmGeom g,
+                                                              G1XYZZ *seg_sums) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= g.n_windows * g.segs_per_window) return;
+    const uint32_t w = idx / g.segs_per_window, sgm = idx % g.segs_per_window;
+    const uint32_t lo = sgm * g.seg;  // buckets lo+1 .. lo+seg of this window (bucket k <-> digit k)
+    G1XYZZ running = G1XYZZ::inf(), acc = G1XYZZ::inf();
+    for (uint32_t k = g.seg; k >= 1; k--) {
+        running = running.add(bucket_sum(partials, task_off, w * g.bpw + lo + k - 1));
+        acc = acc.add(running);
+    }
+    if (lo) acc = acc.add(small_mul(running, lo));
+    seg_sums[idx] = acc;
+}
+
+// block per window: sum of the segment sums
+__global__ void __launch_bounds__(MSM_TPB) msm_window_sum_kernel(const G1XYZZ *seg_sums, MsmGeom g, G1XYZZ *win_sums) {
+    __shared__ G1XYZZ red[MSM_TPB];
+    const uint32_t w = blockIdx.x, tid = threadIdx.x;
+    G1XYZZ acc = G1XYZZ::inf();
+    for (uint32_t s = tid; s < g.segs_per_window; s += MSM_TPB) acc = acc.add(seg_sums[w * g.segs_per_window + s]);
+    red[tid] = acc;
+    __syncthreads();
+    for (uint32_t off = MSM_TPB / 2; off >= 1; off >>= 1) {
+        if (tid < off) red[tid] = red[tid].add(red[tid + off]);
+        __syncthreads();
+    }
+    if (tid == 0) win_sums[w] = red[0];
+}
+
+// Horner over the windows, optional extra term, normalise, write the raw 144-byte GroupProjective
+__global__ void msm_final_kernel(const G1XYZZ *win_sums, MsmGeom g, G1JacobianOut *out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    G1XYZZ total = win_sums[g.n_windows - 1];
+    for (int w = (int)g.n_windows - 2; w >= 0; w--) {
+        for (uint32_t k = 0; k < g.c; k++) total = total.dbl();
+        total = total.add(win_sums[w]);
+    }
+    *out = G1JacobianOut::from_affine(total.to_affine());
+}
+
+}  // namespace dp

@@ -1,0 +1,335 @@
+// NTT / iNTT over BLS12-381 Fr for sm_100a.
+//
+// Replaces ark-poly 0.3.0 Radix2EvaluationDomain::{fft,ifft}_in_place and the per-element
+// Fr::pow coset / twiddle loops around it in the reference worker:
+//   src/worker.rs:66-94   fft1_helper  (coset pre-scale, size-c (i)NTT, omega^(i*j) twiddle)
+//   src/worker.rs:96-115  fft2_helper  (size-r (i)NTT, inverse-coset post-scale)
+//   src/worker.rs:398     whole-domain ifft_in_place (round1)
+//   src/playground.rs:21-80 the 2-D decomposition these implement
+//
+// One kernel does all of it: `ntt_tile_kernel` runs a batch of K-point sub-DFTs (K = 2^log_k) for
+// G "lanes" at a time out of a (K x G)-element shared-memory tile (K*G = 2048 elements = 64 KiB),
+// radix-4 decimation-in-frequency butterflies in registers, natural-order in / natural-order out
+// (the bit reversal is done in the shared-memory read-out addressing), with fused
+//   * input scaling   v *= A[..] * B[..]        (forward coset  g^(i + j*r))
+//   * output twiddle  v *= omega_N^(+-e(o,lane,f))  from the per-domain half table
+//   * output scaling  v *= A[..] * B[..] * const  (inverse coset g^-(i+j*c), 1/size)
+// Every transform is a short list of such passes with explicit element strides (NttPass), so the
+// same kernel serves the worker's row phase, column phase, the four-step split of long rows and
+// the whole-domain transform.  The per-stage butterfly twiddles (omega_{2^(s+1)}^j, stage-major,
+// K entries) are staged into shared memory by a 1-D bulk TMA copy (cp.async.bulk + mbarrier)
+// that overlaps the tile load.
+//
+// HBM traffic per pass: 64 B per element (32 B read + 32 B written) + 32 B twiddle-table read
+// when a pass applies the omega_N twiddle; no tensor cores (modular arithmetic, not a contraction).
+#pragma once
+#include "rt.cuh"
+
+namespace dp {
+
+constexpr int NTT_TPB = 256;
+constexpr uint32_t NTT_TILE_LOG = 11;  // elements per tile (K * G)
+constexpr uint32_t NTT_WTAB_LOG = 11;  // largest K the level table covers
+constexpr uint32_t NTT_MAX_STRIDED_LOG_K = 9;   // keep G >= 4 lanes (128 B) when lanes are the contiguous axis
+
+// 2^32-th root of unity 7^((r-1)/2^32), Montgomery form (ark FrParameters::TWO_ADIC_ROOT_OF_UNITY)
+DP_HD Fr fr_two_adic_root() {
+    Fr w;
+    const uint32_t c[8] = {0x5f0e466au, 0xb9b58d8cu, 0x1819d7ecu, 0x5b1b4c80u,
+                           0x52a31e64u, 0x0af53ae3u, 0x19e9b27bu, 0x5bf3addau};
+    for (int i = 0; i < 8; i++) w.l[i] = c[i];
+    return w;
+}
+// Radix2EvaluationDomain::new(2^log_size).group_gen
+DP_HD Fr fr_domain_gen(uint32_t log_size) {
+    Fr w = fr_two_adic_root();
+    for (uint32_t i = log_size; i < 32; i++) w = w.sqr();
+    return w;
+}
+DP_HD Fr fr_from_u64(uint64_t v) {
+    Fr x = Fr::zero();
+    x.l[0] = (uint32_t)v;
+    x.l[1] = (uint32_t)(v >> 32);
+    return x.to_mont();
+}
+
+struct NttPass {
+    const Fr *in;
+    Fr *out;
+    uint32_t log_k, log_g;   // sub-DFT size, lanes per tile
+    uint32_t lane_tiles;     // n_lanes / G   (grid = n_outer * lane_tiles)
+    uint32_t n_outer;
+    uint64_t in_os, in_ls, in_ps;     // element strides: outer, lane, point
+    uint64_t out_os, out_ls, out_ps;
+    // output element address = out + o*out_os + lane*out_ls + S(lane*out_lc + f*out_ps) where S is the
+    // identity, or (exchange layout, W blocks of [rows][cols/W]) S(k) = (k >> split_log)*split_stride
+    // + (k & (2^split_log - 1)):  the pack step of worker.rs:327-330 fused into the store
+    uint64_t out_lc, split_stride;
+    uint32_t split_on, split_log;
+    const uint4 *w_lo, *w_hi;         // stage-major butterfly twiddles, plane-split, >= K entries
+    // output twiddle omega_N^(+-e),  e = (tw_la*lane + tw_oa*o + tw_c0) * (tw_fb*f + tw_lb*lane)
+    const Fr *tw_tab;                 // omega_N^e, e < N/2   (nullptr = no twiddle)
+    uint32_t tw_log_n, tw_inverse;
+    uint64_t tw_la, tw_oa, tw_c0, tw_fb, tw_lb;
+    // input scaling  v *= pre_a[pa_o*o + pa_l*lane] * pre_b[pb_m*m + pb_l*lane]   (nullptr = none)
+    const Fr *pre_a, *pre_b;
+    uint64_t pa_o, pa_l, pb_m, pb_l;
+    // output scaling v *= post_a[qa_o*o + qa_l*lane] * post_b[qb_o*o + qb_f*f + qb_l*lane] (nullptr = none)
+    const Fr *post_a, *post_b;
+    uint64_t qa_o, qa_l, qb_o, qb_f, qb_l;
+    uint32_t post_const_on;           // v *= post_const
+    Fr post_const;
+};
+
+// ------------------------------------------------------------------ shared-memory element access
+// An Fr is kept as two 16-byte halves in separate planes so that consecutive element indices are
+// conflict-free for LDS.128 / STS.128.
+DP_D Fr smem_ld(const uint4 *lo, const uint4 *hi, uint32_t e) {
+    Fr v;
+    uint4 a = lo[e], b = hi[e];
+    v.l[0] = a.x; v.l[1] = a.y; v.l[2] = a.z; v.l[3] = a.w;
+    v.l[4] = b.x; v.l[5] = b.y; v.l[6] = b.z; v.l[7] = b.w;
+    return v;
+}
+DP_D void smem_st(uint4 *lo, uint4 *hi, uint32_t e, const Fr &v) {
+    lo[e] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    hi[e] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+DP_D Fr gmem_ld(const Fr *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 a = q[0], b = q[1];
+    Fr v;
+    v.l[0] = a.x; v.l[1] = a.y; v.l[2] = a.z; v.l[3] = a.w;
+    v.l[4] = b.x; v.l[5] = b.y; v.l[6] = b.z; v.l[7] = b.w;
+    return v;
+}
+DP_D void gmem_st(Fr *p, const Fr &v) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+
+// omega_N^(+-e) from the half table H[e] = omega_N^e, e < N/2  (omega^(N/2) = -1)
+DP_D Fr tw_lookup(const Fr *H, uint64_t e, uint32_t log_n, uint32_t inverse) {
+    const uint64_t n = (uint64_t)1 << log_n, half = n >> 1;
+    e &= n - 1;
+    if (inverse) e = (n - e) & (n - 1);
+    const bool neg = e >= half;
+    if (neg) e -= half;
+    Fr w = gmem_ld(H + e);
+    return neg ? w.neg() : w;
+}
+
+// ------------------------------------------------------------------ TMA bulk copy of the level table
+#if !defined(DP_EMUL)
+DP_D uint32_t smem_addr_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+DP_D void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+DP_D void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+DP_D void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_addr_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_addr_u32(bar))
+        : "memory");
+}
+DP_D void mbar_wait(uint64_t *bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_addr_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+#endif
+
+// dynamic shared memory: [lo plane | hi plane] of G*(K+1) uint4 each, [w_lo | w_hi] of K uint4 each,
+// one 8-byte mbarrier
+DP_HD size_t ntt_pass_smem_bytes(uint32_t log_k, uint32_t log_g) {
+    size_t K = (size_t)1 << log_k, G = (size_t)1 << log_g;
+    return 2 * G * (K + 1) * 16 + 2 * K * 16 + 16;
+}
+
+__global__ void __launch_bounds__(NTT_TPB, 2) ntt_tile_kernel(NttPass p) {
+    DP_DYN_SMEM(smem_raw);
+    const uint32_t K = 1u << p.log_k, G = 1u << p.log_g, tile = K * G, pitch = K + 1;
+    uint4 *lo = reinterpret_cast<uint4 *>(smem_raw);
+    uint4 *hi = lo + (size_t)G * pitch;
+    uint4 *wlo = hi + (size_t)G * pitch;
+    uint4 *whi = wlo + K;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(whi + K);
+    const uint32_t tid = threadIdx.x;
+
+    const uint32_t o = blockIdx.x / p.lane_tiles;
+    const uint32_t lane0 = (blockIdx.x % p.lane_tiles) * G;
+
+    // ---- stage the butterfly twiddles (TMA bulk copy, overlaps the tile load below)
+#if defined(DP_EMUL)
+    if (tid == 0) {
+        memcpy(wlo, p.w_lo, (size_t)K * 16);
+        memcpy(whi, p.w_hi, (size_t)K * 16);
+    }
+#else
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, 2 * K * 16);
+        tma_bulk_g2s(wlo, p.w_lo, K * 16, bar);
+        tma_bulk_g2s(whi, p.w_hi, K * 16, bar);
+    }
+#endif
+
+    // ---- load the tile (natural point order), fused input scaling
+    {
+        const Fr *src = p.in + (uint64_t)o * p.in_os + (uint64_t)lane0 * p.in_ls;
+        const bool pts_contig = (p.in_ps == 1);
+        for (uint32_t idx = tid; idx < tile; idx += NTT_TPB) {
+            uint32_t m, g;
+            if (pts_contig) {
+                m = idx & (K - 1);
+                g = idx >> p.log_k;
+            } else {
+                g = idx & (G - 1);
+                m = idx >> p.log_g;
+            }
+            Fr v = gmem_ld(src + (uint64_t)g * p.in_ls + (uint64_t)m * p.in_ps);
+            if (p.pre_a) {
+                const uint64_t lane = lane0 + g;
+                v = v * gmem_ld(p.pre_a + p.pa_o * o + p.pa_l * lane);
+                v = v * gmem_ld(p.pre_b + p.pb_m * m + p.pb_l * lane);
+            }
+            smem_st(lo, hi, g * pitch + m, v);
+        }
+    }
+#if !defined(DP_EMUL)
+    mbar_wait(bar, 0);
+#endif
+    __syncthreads();
+
+    // ---- butterflies: decimation in frequency, stages log_k-1 .. 0
+    int s = (int)p.log_k - 1;
+    if (p.log_k & 1) {  // one radix-2 stage on top so that the rest pairs up
+        const uint32_t span = 1u << s, units = tile >> 1, upl = K >> 1;  // units per lane
+        for (uint32_t u = tid; u < units; u += NTT_TPB) {
+            const uint32_t g = u / upl, uu = u % upl;
+            const uint32_t j = uu & (span - 1);
+            const uint32_t m0 = ((uu >> s) << (s + 1)) | j;
+            const uint32_t e0 = g * pitch + m0, e1 = e0 + span;
+            Fr a = smem_ld(lo, hi, e0), b = smem_ld(lo, hi, e1);
+            Fr d = a - b;
+            a = a + b;
+            if (s > 0) d = d * smem_ld(wlo, whi, span + j);
+            smem_st(lo, hi, e0, a);
+            smem_st(lo, hi, e1, d);
+        }
+        __syncthreads();
+        s--;
+    }
+    for (; s >= 1; s -= 2) {  // radix-4: stages s and s-1
+        const int sl = s - 1;
+        const uint32_t q = 1u << sl, units = tile >> 2, upl = K >> 2;
+        for (uint32_t u = tid; u < units; u += NTT_TPB) {
+            const uint32_t g = u / upl, uu = u % upl;
+            const uint32_t j = uu & (q - 1);
+            const uint32_t m0 = ((uu >> sl) << (sl + 2)) | j;
+            const uint32_t e0 = g * pitch + m0;
+            Fr x0 = smem_ld(lo, hi, e0), x1 = smem_ld(lo, hi, e0 + q);
+            Fr x2 = smem_ld(lo, hi, e0 + 2 * q), x3 = smem_ld(lo, hi, e0 + 3 * q);
+            // stage s (span 2q): (x0,x2) with T_s[j], (x1,x3) with T_s[j+q]
+            Fr b0 = x0 + x2, b2 = (x0 - x2) * smem_ld(wlo, whi, 2 * q + j);
+            Fr b1 = x1 + x3, b3 = (x1 - x3) * smem_ld(wlo, whi, 2 * q + j + q);
+            // stage s-1 (span q): (b0,b1), (b2,b3) with T_{s-1}[j]
+            Fr c0 = b0 + b1, c1 = b0 - b1, c2 = b2 + b3, c3 = b2 - b3;
+            if (sl > 0) {
+                const Fr w = smem_ld(wlo, whi, q + j);
+                c1 = c1 * w;
+                c3 = c3 * w;
+            }
+            smem_st(lo, hi, e0, c0);
+            smem_st(lo, hi, e0 + q, c1);
+            smem_st(lo, hi, e0 + 2 * q, c2);
+            smem_st(lo, hi, e0 + 3 * q, c3);
+        }
+        __syncthreads();
+    }
+
+    // ---- write out (frequency f sits at bit-reversed position), fused twiddle / scaling
+    {
+        Fr *dst = p.out + (uint64_t)o * p.out_os;
+        const bool pts_contig = (p.out_ps == 1 && !p.out_lc);
+        for (uint32_t idx = tid; idx < tile; idx += NTT_TPB) {
+            uint32_t f, g;
+            if (pts_contig) {
+                f = idx & (K - 1);
+                g = idx >> p.log_k;
+            } else {
+                g = idx & (G - 1);
+                f = idx >> p.log_g;
+            }
+            const uint32_t pos = p.log_k ? (__brev(f) >> (32 - p.log_k)) : 0;
+            Fr v = smem_ld(lo, hi, g * pitch + pos);
+            const uint64_t lane = lane0 + g;
+            if (p.tw_tab) {
+                const uint64_t e = (p.tw_la * lane + p.tw_oa * o + p.tw_c0) * (p.tw_fb * f + p.tw_lb * lane);
+                v = v * tw_lookup(p.tw_tab, e, p.tw_log_n, p.tw_inverse);
+            }
+            if (p.post_a) {
+                v = v * gmem_ld(p.post_a + p.qa_o * o + p.qa_l * lane);
+                v = v * gmem_ld(p.post_b + p.qb_o * o + p.qb_f * f + p.qb_l * lane);
+            }
+            if (p.post_const_on) v = v * p.post_const;
+            uint64_t col = lane * p.out_lc + (uint64_t)f * p.out_ps;
+            if (p.split_on) col = (col >> p.split_log) * p.split_stride + (col & (((uint64_t)1 << p.split_log) - 1));
+            gmem_st(dst + lane * p.out_ls + col, v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ table generation (init time)
+// stage-major butterfly twiddles: W[2^s + j] = omega_{2^(s+1)}^(+-j), j < 2^s, s < NTT_WTAB_LOG;
+// W[0] unused (= 1).  Plane-split (low / high 16 bytes) so one bulk copy per plane stages a prefix.
+__global__ void ntt_gen_level_table_kernel(uint4 *w_lo, uint4 *w_hi, uint32_t inverse) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (1u << NTT_WTAB_LOG)) return;
+    Fr v = Fr::one();
+    if (idx >= 1) {
+        const uint32_t s = 31 - __clz((int)idx), j = idx - (1u << s);
+        Fr g = fr_domain_gen(s + 1);
+        if (inverse) g = g.inverse();
+        v = g.pow(j);
+    }
+    w_lo[idx] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    w_hi[idx] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+
+// out[i] = mulc * base^(first + i*step) for i < n   (half twiddle tables, coset power tables)
+__global__ void fr_gen_powers_kernel(Fr *out, uint64_t n, Fr base, uint64_t first, uint64_t step, Fr mulc) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    gmem_st(out + i, base.pow(first + i * step) * mulc);
+}
+
+// x[i] *= base^(i) * c   elementwise (whole-domain coset scaling: distribute_powers)
+__global__ void fr_scale_powers_kernel(Fr *x, uint64_t n, Fr base, Fr c) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    gmem_st(x + i, gmem_ld(x + i) * (base.pow(i) * c));
+}
+
+// Montgomery -> canonical (Fr::into_repr, worker.rs:118), optionally zero-padding up to n_out
+__global__ void fr_into_repr_kernel(const Fr *in, Fr *out, uint64_t n_in, uint64_t n_out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    gmem_st(out + i, i < n_in ? gmem_ld(in + i).from_mont() : Fr::zero());
+}
+
+}  // namespace dp

@@ -1,0 +1,58 @@
+"""One process per GPU: the exchange step of the distributed 2-D NTT as a single all-to-all.
+
+The reference moves every (rows_p x cols_q) block with a hand-rolled all-to-all over fresh TCP
+connections (PlonkSlave.fft2Prepare -> PlonkPeer.fftExchange, src/worker.rs:280-345, 412-438).
+Here the row-phase kernel already stores its output in exchange layout (W contiguous blocks), so
+the whole step is ONE `all_to_all_single` over NVLink (NCCL) on the library's device buffers, and
+the column-phase kernel reads the received [r][cols] matrix with strided loads: no pack, unpack or
+transpose kernels.  This is the only collective on the path; MSM shards need none.
+
+The same code runs on CPU under the `gloo` backend against the kernel-logic emulator (tests only).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class _CudaBuffer:
+    """Expose a raw device pointer through __cuda_array_interface__ (no copy)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {
+            "shape": (nbytes // 8,), "typestr": "<i8", "data": (ptr, False), "version": 3, "strides": None,
+        }
+
+
+def as_tensor(ptr: int, nbytes: int, cuda: bool) -> torch.Tensor:
+    """int64 view of `nbytes` at `ptr` (device memory when cuda, host memory otherwise)."""
+    if cuda:
+        return torch.as_tensor(_CudaBuffer(ptr, nbytes), device="cuda")
+    arr = np.ctypeslib.as_array((C.c_int64 * (nbytes // 8)).from_address(ptr))
+    return torch.from_numpy(arr)
+
+
+def make_exchange(group=None, cuda: bool | None = None):
+    """Returns exchange(send_ptr, recv_ptr, block_elems) for PlonkSlave.fft2_prepare: block q of my
+    send buffer goes to rank q, landing as block `rank` of its recv buffer."""
+    world = dist.get_world_size(group)
+    if cuda is None:
+        cuda = dist.get_backend(group) == "nccl"
+
+    def exchange(send_ptr: int, recv_ptr: int, block_elems: int):
+        nbytes = block_elems * 32 * world
+        send = as_tensor(send_ptr, nbytes, cuda)
+        recv = as_tensor(recv_ptr, nbytes, cuda)
+        dist.all_to_all_single(recv, send, group=group)
+        if cuda:
+            torch.cuda.current_stream().synchronize()
+
+    return exchange
+
+
+def msm_shard(n_bases: int, rank: int, world: int):
+    """MsmWorkload of `rank`: the global index range of dispatcher2.rs:870-881."""
+    return rank * n_bases // world, (rank + 1) * n_bases // world

@@ -1,0 +1,156 @@
+/*
+ * dplonk.h - C ABI of the B200-native worker hot path of MengLing-L/distributed_plonk.
+ *
+ * The reference worker (Rust) has no FFI today: its RPC method bodies call arkworks directly
+ * (SURVEY.md §8b).  Each entry point below is what the body of one `PlonkSlave` / `PlonkPeer`
+ * method (src/hello_world.capnp:15-52, implemented in src/worker.rs:125-439) binds instead of the
+ * arkworks call it makes today; INTEGRATION.md shows the Rust `extern "C"` block and the patched
+ * method bodies.  Wire formats are exactly what the reference puts in its `Data` blobs
+ * (src/utils.rs:27-43 = raw in-memory Rust structs):
+ *
+ *   Fr            32 B  ark-ff Fp256, Montgomery form (R = 2^256), 4 x u64 little-endian
+ *   BigInteger256 32 B  canonical scalar (Fr::into_repr), 4 x u64 little-endian
+ *   G1Affine     104 B  x (48 B Fq Montgomery) | y (48 B) | infinity flag (1 B) | 7 B padding
+ *   G1Projective 144 B  Jacobian X | Y | Z, each 48 B Fq Montgomery; identity has Z = 0
+ *
+ * Conventions: every function returns DP_OK (0) or a negative DP_E_* code and never throws or
+ * aborts across the boundary; dp_last_error() gives the text.  All buffers are caller-owned,
+ * borrowed only for the duration of the call, may be unaligned, and are HOST memory unless a
+ * parameter says "dev".  A context is bound to one CUDA device and must be used from one thread
+ * at a time (the reference worker is single-threaded: worker.rs:441,453).  There is no CPU
+ * fallback: dp_create fails with DP_E_CUDA when no sm_100 device is usable.
+ */
+#ifndef DPLONK_H
+#define DPLONK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DP_OK 0
+#define DP_E_ARG (-1)   /* bad argument (size mismatch, non-canonical scalar, unknown id ...) */
+#define DP_E_STATE (-2) /* call out of order (fft2 before fft2_prepare, rows missing ...)      */
+#define DP_E_OOM (-3)   /* device or host allocation failed                                   */
+#define DP_E_CUDA (-4)  /* CUDA runtime / kernel error                                        */
+#define DP_E_COMM (-5)  /* exchange needed but no peer transport attached                     */
+
+#define DP_FR_BYTES 32
+#define DP_G1_AFFINE_BYTES 104
+#define DP_G1_PROJECTIVE_BYTES 144
+
+typedef struct dp_ctx dp_ctx;
+
+/* src/utils.rs:3-19 FftWorkload (src/hello_world.capnp:8-13) */
+typedef struct dp_fft_workload {
+    uint64_t row_start, row_end, col_start, col_end;
+} dp_fft_workload;
+
+/* ---- lifetime -------------------------------------------------------------------------------
+ * Replaces the `State` construction in worker main (src/worker.rs:455-472).  `me` is the worker
+ * index (argv[1], worker.rs:443-449), `n_workers` the number of workers sharing distributed NTTs. */
+int dp_create(int cuda_device, uint64_t me, uint64_t n_workers, dp_ctx **out);
+int dp_destroy(dp_ctx *ctx);
+const char *dp_last_error(const dp_ctx *ctx); /* valid until the next call on ctx; ctx may be NULL */
+const char *dp_version(void);
+
+/* ---- PlonkSlave.init (src/worker.rs:126-157) -------------------------------------------------
+ * Stores the SRS bases on the device and builds the (r, c) split domains for `domain_size` and
+ * `quot_domain_size` (Radix2EvaluationDomain::new rounds both up to powers of two).
+ * bases: n_bases raw G1Affine (104 B each), the concatenation of the `bases` Data chunks. */
+int dp_init(dp_ctx *ctx, const void *bases, size_t n_bases, uint64_t domain_size, uint64_t quot_domain_size);
+
+/* ---- PlonkSlave.varMsm (src/worker.rs:159-185) -----------------------------------------------
+ * out = sum_{k < min(end-start, n_scalars)} scalars[k] * bases[start + k]
+ * (VariableBaseMSM::multi_scalar_mul(&bases[start..end], &scalars) truncates to the shorter).
+ * scalars: canonical BigInteger256.  out: 144 B raw G1Projective, normalised (Z = 1) or identity. */
+int dp_msm(dp_ctx *ctx, uint64_t start, uint64_t end, const void *scalars, size_t n_scalars, void *out);
+
+/* ---- commit_polynomial (src/worker.rs:117-123) -----------------------------------------------
+ * Fr::into_repr on every coefficient, zero-pad to bases.len(), MSM over all bases.
+ * coeffs: n raw Fr (Montgomery), n <= n_bases. */
+int dp_commit(dp_ctx *ctx, const void *coeffs, size_t n, void *out);
+
+/* ---- PlonkSlave.fftInit (src/worker.rs:187-233) ----------------------------------------------
+ * Opens task `id`.  workloads[w] is worker w's row / column range; n_workloads must equal
+ * n_workers and the ranges must tile [0,r) x [0,c) in equal power-of-two blocks. */
+int dp_fft_init(dp_ctx *ctx, uint64_t id, const dp_fft_workload *workloads, size_t n_workloads, int is_quot,
+                int is_inv, int is_coset);
+
+/* ---- PlonkSlave.fft1 (src/worker.rs:235-278) -------------------------------------------------
+ * Hands in local row `i` (global row i + row_start): len must be c.  The row transform
+ * (fft1_helper, worker.rs:66-94) runs on the device, at the latest in dp_fft2_prepare. */
+int dp_fft1(dp_ctx *ctx, uint64_t id, uint64_t i, const void *row, size_t len);
+/* n_rows consecutive local rows in one call (rows = n_rows * c Fr, row-major) */
+int dp_fft1_rows(dp_ctx *ctx, uint64_t id, uint64_t i_first, uint64_t n_rows, const void *rows);
+
+/* ---- PlonkSlave.fft2Prepare + PlonkPeer.fftExchange (src/worker.rs:280-345, 412-438) ---------
+ * Finishes the row phase and moves every (rows_p x cols_q) block to its owner.  n_workers == 1:
+ * purely local.  n_workers > 1: either peers were attached with dp_peer_attach (the blocks are
+ * written straight into the owners' memory over NVLink by the row kernel), or the caller drives
+ * the split API below around its own all-to-all (NCCL / torch.distributed). */
+int dp_fft2_prepare(dp_ctx *ctx, uint64_t id);
+
+/* split exchange: after _begin, *send_dev / *recv_dev are DEVICE pointers to n_workers blocks of
+ * *block_elems Fr each (block q of send = my rows x q's columns, row-major = the payload of
+ * fftExchange, worker.rs:327-330; block p of recv = p's rows x my columns).  The caller performs
+ * the all-to-all (block q of send -> rank q, into block `me` of its recv) and calls _end. */
+int dp_fft_exchange_begin(dp_ctx *ctx, uint64_t id, void **send_dev, void **recv_dev, uint64_t *block_elems);
+int dp_fft_exchange_end(dp_ctx *ctx, uint64_t id);
+
+/* ---- PlonkSlave.fft2 (src/worker.rs:347-381) -------------------------------------------------
+ * Column transforms (fft2_helper, worker.rs:96-115); writes the local columns back to back
+ * (n_cols * r Fr, column k at out + k*r*32 = the k-th `Data` of the reply) and drops the task. */
+int dp_fft2(dp_ctx *ctx, uint64_t id, void *out, size_t out_bytes);
+
+/* ---- whole-domain transform ------------------------------------------------------------------
+ * Radix2EvaluationDomain::{fft,ifft,coset_fft,coset_ifft} on one device (round1's
+ * ifft_in_place, worker.rs:398; the dispatcher-local coset_ifft, dispatcher2.rs:507).
+ * data: n Fr in, 2^log_n Fr out (n <= 2^log_n, zero-padded like ark's resize); capacity of the
+ * buffer must be 2^log_n elements. */
+int dp_ntt(dp_ctx *ctx, void *data, size_t n, uint32_t log_n, int is_inv, int is_coset);
+
+/* ---- PlonkSlave.round1 (src/worker.rs:383-408) -----------------------------------------------
+ * evals (n Fr) -> ifft -> wire = (b0 + b1*X) * (X^n - 1) + poly -> commitment.  The reference
+ * draws b0,b1 from the worker's ThreadRng; pass them in `blind` (2 raw Fr) to make the call
+ * reproducible, or NULL for an internally generated pair.  The blinded polynomial stays resident
+ * (state.wire, worker.rs:58) and can be read back with dp_get_wire. */
+int dp_round1(dp_ctx *ctx, const void *evals, size_t n, const void *blind, void *out);
+int dp_get_wire(dp_ctx *ctx, void *out, size_t out_bytes, size_t *n_coeffs);
+
+/* ---- peer transport for n_workers > 1 ---------------------------------------------------------
+ * Exchange arena shared between the GPUs of one box through CUDA IPC: every rank exports a
+ * handle, the ranks swap them out of band (torch.distributed / the capnp control plane) and attach
+ * the others'.  Afterwards dp_fft2_prepare writes over NVLink and needs only dp_peer_barrier-style
+ * ordering from the caller (any barrier across ranks between fft2Prepare and fft2). */
+#define DP_IPC_HANDLE_BYTES 64
+int dp_peer_arena_create(dp_ctx *ctx, uint64_t arena_bytes, void *handle_out /* DP_IPC_HANDLE_BYTES */);
+int dp_peer_attach(dp_ctx *ctx, uint64_t peer, const void *handle /* DP_IPC_HANDLE_BYTES */);
+
+/* ---- instrumentation --------------------------------------------------------------------------*/
+/* device-side time (ms, CUDA events on the context stream) and kernel launches of the last call */
+int dp_last_timing(const dp_ctx *ctx, float *kernel_ms, uint64_t *launches);
+/* total kernel launches since dp_create */
+uint64_t dp_launch_count(const dp_ctx *ctx);
+/* block until everything queued on the context stream has finished */
+int dp_sync(dp_ctx *ctx);
+
+/* test hook: lower the pass-planning limits (sub-transform sizes 2^k handled by one kernel pass;
+ * defaults 11 / 9) and/or force the MSM window width (0 = automatic) so that small inputs
+ * exercise the multi-pass NTT plans and every MSM geometry. */
+int dp_debug_set_limits(dp_ctx *ctx, uint32_t max_contig_log_k, uint32_t max_strided_log_k, int msm_window_bits);
+
+/* device-resident variants used by bench.py to time the kernels with inputs already in HBM.
+ * All pointers are DEVICE pointers owned by the caller (e.g. torch tensors). */
+int dp_msm_dev(dp_ctx *ctx, uint64_t start, uint64_t end, const void *scalars_dev, size_t n_scalars, void *out_dev);
+int dp_ntt_dev(dp_ctx *ctx, void *data_dev, uint32_t log_n, int is_inv, int is_coset);
+/* full 2-D pipeline of one worker on device-resident rows: rows_dev = my rows (n_rows*c Fr),
+ * cols_dev receives my columns (n_cols*r Fr); n_workers must be 1 or peers attached. */
+int dp_fft_dev(dp_ctx *ctx, const void *rows_dev, void *cols_dev, int is_quot, int is_inv, int is_coset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPLONK_H */

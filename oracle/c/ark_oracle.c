@@ -417,6 +417,37 @@ void orc_distributed_fft(const u64 *in, u64 *out, u64 domain_size, int is_inv, i
     free(cols);
 }
 
+/* p(z) for p = sum x[j] z^j by Horner, z = omega_n^(+-k) (and optionally the coset shift g): one
+ * output element X[k] of an n-point (coset) (i)NTT in O(n) - the size-independent spot check used
+ * by the full-size parity tests.  inverse also multiplies by 1/n (and g^-k for coset). */
+void orc_ntt_output_at(const u64 *data, u64 n, u64 k, int inverse, int coset, u64 *out) {
+    const fr_t *x = (const fr_t *)data;
+    int log_n = log2_ceil(n);
+    fr_t w, z, g, acc;
+    domain_gen(&w, log_n, inverse);
+    fr_pow_u64(&z, &w, k);
+    fr_from_u64(&g, 7);
+    if (coset && !inverse) fr_mul(&z, &z, &g);
+    memset(&acc, 0, sizeof acc);
+    for (u64 j = n; j-- > 0;) {
+        fr_mul(&acc, &acc, &z);
+        fr_add(&acc, &acc, &x[j]);
+    }
+    if (inverse) {
+        fr_t nn, ninv;
+        fr_from_u64(&nn, n);
+        fr_inv(&ninv, &nn);
+        fr_mul(&acc, &acc, &ninv);
+        if (coset) {
+            fr_t gi, gk;
+            fr_inv(&gi, &g);
+            fr_pow_u64(&gk, &gi, k);
+            fr_mul(&acc, &acc, &gk);
+        }
+    }
+    memcpy(out, &acc, 32);
+}
+
 /* ------------------------------------------------------------------ raw Fr utilities for tests */
 void orc_fr_mul(const u64 *a, const u64 *b, u64 *out) { fr_mul((fr_t *)out, (const fr_t *)a, (const fr_t *)b); }
 void orc_fr_add(const u64 *a, const u64 *b, u64 *out) { fr_add((fr_t *)out, (const fr_t *)a, (const fr_t *)b); }

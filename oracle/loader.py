@@ -68,6 +68,7 @@ def lib():
             "orc_msm": (None, [p, p, u64, p]),
             "orc_commit": (None, [p, u64, p, u64, p]),
             "orc_num_threads": (i, []),
+            "orc_ntt_output_at": (None, [p, u64, u64, i, i, p]),
         }
         for name, (res, args) in sig.items():
             f = getattr(L, name)
@@ -119,6 +120,14 @@ def distributed_fft(x, domain_size, is_inv, is_coset, n_workers=1, as_written=Fa
     xin[: x.shape[0]] = x
     out = np.empty_like(xin)
     lib().orc_distributed_fft(_ptr(xin), _ptr(out), domain_size, int(is_inv), int(is_coset), n_workers, int(as_written))
+    return out
+
+
+def ntt_output_at(x: np.ndarray, k: int, inverse: bool, coset: bool) -> np.ndarray:
+    """element k of the (coset) (i)NTT of x, in O(n) (Horner)"""
+    x = np.ascontiguousarray(x, dtype=np.uint64)
+    out = np.zeros(4, dtype=np.uint64)
+    lib().orc_ntt_output_at(_ptr(x), x.shape[0], k, int(inverse), int(coset), _ptr(out))
     return out
 
 

@@ -1,0 +1,125 @@
+"""Parity checks shared by the emulator (CPU) and the GPU test files: every check drives the C ABI
+exactly like the reference's own tests drive the workers (dispatcher.rs:177-350, dispatcher2.rs:
+1088-1216) and compares with the oracle."""
+import ctypes as C
+
+import numpy as np
+
+from distributed_plonk_b200 import dispatcher as disp
+from distributed_plonk_b200._binding import Context, DpError
+from distributed_plonk_b200.worker import PlonkSlave, chunks
+
+R_MOD = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+FLAG_COMBOS = [(inv, cos) for inv in (False, True) for cos in (False, True)]
+
+
+def u256(v: int) -> np.ndarray:
+    return np.frombuffer(int(v).to_bytes(32, "little"), dtype=np.uint64).copy()
+
+
+def check_whole_ntt(orc, ctx: Context, log_n: int, seed: int, n_in=None):
+    N = 1 << log_n
+    n_in = N if n_in is None else n_in
+    x = orc.gen_fr(seed, n_in)
+    padded = np.zeros((N, 4), dtype=np.uint64)
+    padded[:n_in] = x
+    for inv, cos in FLAG_COMBOS:
+        got = ctx.ntt(x, log_n, inv, cos)
+        ref = orc.fft(padded, inv, cos)
+        assert np.array_equal(got, ref), f"dp_ntt log_n={log_n} inv={inv} coset={cos}"
+
+
+def local_exchange(ctxs, tid):
+    """in-process all-to-all over the split API (single process holding every worker)"""
+    W = len(ctxs)
+    bufs = [c.fft_exchange_begin(tid) for c in ctxs]
+    import_cuda = None
+    for p in range(W):
+        for q in range(W):
+            n = bufs[p][2] * 32
+            yield bufs[q][1] + p * n, bufs[p][0] + q * n, n
+    for c in ctxs:
+        c.fft_exchange_end(tid)
+
+
+def check_distributed_fft(orc, workers, domain_log, is_quot, seed, copy_fn, n_in=None):
+    """test_fft (dispatcher.rs:246-350): all flag combos through fft_init / fft1 / fft2_prepare /
+    fft2 must equal Radix2EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}."""
+    N = 1 << domain_log
+    n_in = N if n_in is None else n_in
+    W = len(workers)
+    for k, (inv, cos) in enumerate(FLAG_COMBOS):
+        x = orc.gen_fr(seed + k, n_in)
+        padded = np.zeros((N, 4), dtype=np.uint64)
+        padded[:n_in] = x
+        tid = 0xF00D0000 + seed * 16 + k
+
+        def exchange(send, recv, n, _tid=tid):
+            raise AssertionError("single-process test drives the split API directly")
+
+        if W == 1:
+            got = disp.fft(workers, domain_log, x, is_quot, inv, cos, tid)
+        else:
+            # drive the stubs by hand so the exchange can be done in-process
+            wl = disp.fft_workloads(domain_log, W)
+            rows = disp.dispatcher_rows(x, domain_log)
+            for w in workers:
+                w.fft_init(tid, wl, is_quot, inv, cos)
+            for p, w in enumerate(workers):
+                for j in range(wl[p][1] - wl[p][0]):
+                    w.fft1(tid, j, chunks(rows[wl[p][0] + j]))
+            for dst, src, n in local_exchange([w.ctx for w in workers], tid):
+                copy_fn(dst, src, n)
+            cols = np.concatenate([w.fft2_array(tid) for w in workers], axis=0)
+            got = disp.assemble(cols)
+        ref = orc.fft(padded, inv, cos)
+        assert np.array_equal(got, ref), f"distributed fft L={domain_log} W={W} inv={inv} coset={cos}"
+
+
+def scalar_sets(orc, n, seed):
+    """input distributions of SURVEY §8d: (A) uniform, (B) witness-like, (C) all r-1, plus edges"""
+    a = orc.gen_fr(seed, n, False)
+    b = orc.gen_fr(seed + 1, n, False)
+    b[::2] = 0
+    b[1::10] = u256(1)
+    if n > 7:
+        b[5] = u256(R_MOD - 1)
+        b[7] = u256(2)
+    c = np.tile(u256(R_MOD - 1), (n, 1))
+    z = np.zeros((n, 4), dtype=np.uint64)
+    o = np.tile(u256(1), (n, 1))
+    return {"uniform": a, "witness-like": b, "all r-1": c, "all zero": z, "all one": o}
+
+
+def assert_point_eq(orc, got144, ref144, what):
+    g, r = orc.normalize(got144), orc.normalize(ref144)
+    assert np.array_equal(g, r), f"{what}: affine mismatch"
+    # the library promises a normalised representative: identical raw bytes after normalisation
+    norm = np.zeros(144, dtype=np.uint8)
+    norm[:96] = g[:96]
+    if g[96]:
+        norm[96:144] = 0
+    else:
+        from oracle.py import bls12_381 as B
+        norm[96:144] = np.frombuffer(B.fq_to_mont_bytes(1), dtype=np.uint8)
+    assert np.array_equal(np.asarray(got144, dtype=np.uint8), norm), f"{what}: output is not the normalised Jacobian"
+
+
+def check_msm(orc, ctx: Context, bases, n, seed, which=None):
+    for name, sc in scalar_sets(orc, n, seed).items():
+        if which and name not in which:
+            continue
+        got = ctx.msm(0, n, sc)
+        ref = orc.msm(bases[:n], sc)
+        assert_point_eq(orc, got, ref, f"msm n={n} {name}")
+
+
+def check_sharded_msm(orc, workers, bases, n, seed):
+    """test_msm (dispatcher.rs:177-244): sum of the workers' partials == one multi_scalar_mul"""
+    sc = orc.gen_fr(seed, n, False)
+    parts = disp.commit_polynomial(workers, n, sc)
+    acc = np.frombuffer(parts[0], dtype=np.uint8)
+    for p in parts[1:]:
+        acc = orc.g1_add(acc, np.frombuffer(p, dtype=np.uint8))
+    ref = orc.msm(bases[:n], sc)
+    assert np.array_equal(orc.normalize(acc), orc.normalize(ref))

@@ -1,0 +1,36 @@
+import ctypes
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run by `pytest -m gpu` on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def orc():
+    """tier-1 C oracle (oracle/c/ark_oracle.c) behind numpy helpers"""
+    from oracle import loader
+    loader.lib()
+    return loader
+
+
+@pytest.fixture(scope="session")
+def emul_lib():
+    """CPU kernel-logic emulator build of the library (tests/emul; NOT a product backend)"""
+    from tests.emul import build as emul_build
+    from distributed_plonk_b200._binding import bind
+    return bind(ctypes.CDLL(emul_build.build()))
+
+
+@pytest.fixture(scope="session")
+def gpu_lib():
+    """the real nvcc-built library; GPU tests fail (not skip) if it is missing"""
+    import distributed_plonk_b200 as dp
+    return dp.load()

@@ -1,0 +1,30 @@
+"""Build the CPU kernel-logic emulator of the library (TEST INFRASTRUCTURE ONLY; see cuda_emul.h).
+
+Compiles distributed_plonk_b200/csrc/dplonk.cu with g++ -DDP_EMUL into
+tests/emul/_build/libdplonk_emul.so.  Never loaded by the package itself.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+SRC = os.path.join(ROOT, "distributed_plonk_b200", "csrc")
+OUT = os.path.join(HERE, "_build", "libdplonk_emul.so")
+CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+
+
+def build(force=False):
+    deps = [os.path.join(SRC, f) for f in os.listdir(SRC)] + [os.path.join(HERE, "cuda_emul.h"),
+                                                             os.path.join(ROOT, "include", "dplonk.h")]
+    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
+        return OUT
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    cmd = [CXX, "-O2", "-g", "-std=c++20", "-fPIC", "-shared", "-pthread", "-DDP_EMUL", "-Wall", "-Wno-unknown-pragmas",
+           "-x", "c++", os.path.join(SRC, "dplonk.cu"), "-o", OUT]
+    subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="-f" in sys.argv))

@@ -23,3 +23,28 @@ void emu_fr_pow(const void *a, uint64_t e, void *o) { *(Fr *)o = ((const Fr *)a)
 void emu_fr_to_mont(const void *a, void *o) { *(Fr *)o = ((const Fr *)a)->to_mont(); }
 void emu_fr_from_mont(const void *a, void *o) { *(Fr *)o = ((const Fr *)a)->from_mont(); }
 }
+
+#include "../../distributed_plonk_b200/csrc/g1.cuh"
+extern "C" {
+// k*P with XYZZ double-and-add (exercises dbl + add_mixed incl. the special cases)
+void emu_g1_mul(const void *aff96, const uint64_t *k, void *out96) {
+    G1Affine p = *(const G1Affine *)aff96;
+    G1XYZZ acc = G1XYZZ::inf();
+    for (int i = 255; i >= 0; i--) {
+        acc = acc.dbl();
+        if ((k[i / 64] >> (i % 64)) & 1) acc = acc.add_mixed(p);
+    }
+    *(G1Affine *)out96 = acc.to_affine();
+}
+// sum of n affine points: two halves accumulated with add_mixed, merged with the full add
+void emu_g1_sum(const void *pts96, uint64_t n, void *out96) {
+    const G1Affine *p = (const G1Affine *)pts96;
+    G1XYZZ a = G1XYZZ::inf(), b = G1XYZZ::inf();
+    for (uint64_t i = 0; i < n; i++) (i & 1 ? b : a) = (i & 1 ? b : a).add_mixed(p[i]);
+    *(G1Affine *)out96 = a.add(b).to_affine();
+}
+void emu_g1_add_xyzz_self(const void *aff96, void *out96) {  // P + P through the full add
+    G1XYZZ a = G1XYZZ::from_affine(*(const G1Affine *)aff96);
+    *(G1Affine *)out96 = a.add(a).to_affine();
+}
+}

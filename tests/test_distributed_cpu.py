@@ -1,0 +1,82 @@
+"""N > 1 path on CPU: world_size-2 `gloo` processes, each owning one emulated worker, run the
+distributed 2-D NTT with the exchange as ONE all_to_all_single (distributed_plonk_b200/parallel.py)
+and the sharded MSM (no collective).  Same code path as the NCCL run on GPUs; only the backend and
+the (emulated) library differ."""
+import ctypes
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, emul_path, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from distributed_plonk_b200 import dispatcher as disp
+    from distributed_plonk_b200 import parallel
+    from distributed_plonk_b200._binding import bind
+    from distributed_plonk_b200.worker import PlonkSlave, chunks
+    from oracle import loader as orc
+
+    lib = bind(ctypes.CDLL(emul_path))
+    w = PlonkSlave(lib, rank, world)
+    n_bases = 256
+    bases = orc.gen_bases(5, n_bases, 32, True)
+    w.init(chunks(bases), 1 << 6, 1 << 9)
+    exchange = parallel.make_exchange()
+    ok = True
+    for is_quot, L in ((False, 6), (True, 9)):
+        wl = disp.fft_workloads(L, world)
+        for k, (inv, cos) in enumerate([(False, False), (True, False), (False, True), (True, True)]):
+            x = orc.gen_fr(100 + L + k, 1 << L)
+            rows = disp.dispatcher_rows(x, L)
+            tid = 500 + 10 * L + k
+            w.fft_init(tid, wl, is_quot, inv, cos)
+            for j in range(wl[rank][1] - wl[rank][0]):
+                w.fft1(tid, j, chunks(rows[wl[rank][0] + j]))
+            w.fft2_prepare(tid, exchange)
+            mine = torch.from_numpy(w.fft2_array(tid).view(np.int64))
+            gathered = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(gathered, mine)
+            cols = torch.cat(gathered).numpy().view(np.uint64)
+            got = disp.assemble(cols)
+            ok &= bool(np.array_equal(got, orc.fft(x, inv, cos)))
+    # sharded MSM: index-range split, partials summed by the dispatcher (rank 0 here)
+    sc = orc.gen_fr(77, n_bases, False)
+    lo, hi = parallel.msm_shard(n_bases, rank, world)
+    part = torch.from_numpy(np.frombuffer(w.var_msm((lo, hi), chunks(sc[lo:hi])), dtype=np.uint8).copy())
+    parts = [torch.empty_like(part) for _ in range(world)]
+    dist.all_gather(parts, part)
+    acc = parts[0].numpy()
+    for p in parts[1:]:
+        acc = orc.g1_add(acc, p.numpy())
+    ok &= bool(np.array_equal(orc.normalize(acc), orc.normalize(orc.msm(bases, sc))))
+    with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as f:
+        f.write("ok" if ok else "FAIL")
+    w.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_rank_gloo_fft_and_msm(tmp_path):
+    from tests.emul import build as emul_build
+    from oracle import loader
+    loader.build()
+    path = emul_build.build()
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), path, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert (tmp_path / f"rank{r}.txt").read_text() == "ok"

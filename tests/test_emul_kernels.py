@@ -1,0 +1,128 @@
+"""Kernel-LOGIC tests on a CPU-only box: the library's .cu sources compiled against the CUDA
+execution-model emulator in tests/emul (barriers, shared memory, atomics and carry flags emulated;
+the real PTX paths are exercised by the `-m gpu` tests).  Same checks as tests/test_gpu_parity.py,
+at sizes the emulator finishes in seconds."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from distributed_plonk_b200._binding import Context, DpError
+from distributed_plonk_b200.worker import PlonkSlave
+from tests import common
+
+
+def host_copy(dst, src, n):
+    C.memmove(dst, src, n)
+
+
+@pytest.fixture(scope="module")
+def ctx(emul_lib, orc):
+    c = Context(emul_lib, 0, 0, 1)
+    c.init(orc.gen_bases(5, 600, 64, True), 1 << 6, 1 << 9)
+    yield c
+    c.close()
+
+
+def test_whole_ntt_single_pass(orc, ctx):
+    ctx.debug_set_limits(11, 9, 0)
+    for log_n in (0, 1, 2, 3, 6, 9, 11):
+        common.check_whole_ntt(orc, ctx, log_n, 40 + log_n)
+    common.check_whole_ntt(orc, ctx, 8, 77, n_in=100)          # zero-padded short input
+
+
+@pytest.mark.parametrize("limits,logs", [((3, 2), (4, 5, 6)), ((4, 3), (7, 9)), ((11, 9), (12,))])
+def test_whole_ntt_multi_pass_plans(orc, ctx, limits, logs):
+    ctx.debug_set_limits(limits[0], limits[1], 0)
+    for log_n in logs:
+        common.check_whole_ntt(orc, ctx, log_n, 50 + log_n)
+    ctx.debug_set_limits(11, 9, 0)
+
+
+@pytest.mark.parametrize("W,logn,logq,limits", [(1, 6, 9, (11, 9)), (1, 6, 9, (2, 2)), (2, 6, 9, (11, 9)),
+                                                (4, 6, 9, (2, 2)), (2, 8, 7, (3, 2))])
+def test_distributed_fft_like_reference_test_fft(orc, emul_lib, W, logn, logq, limits):
+    workers = [PlonkSlave(emul_lib, p, W) for p in range(W)]
+    for w in workers:
+        w.init([b""], 1 << logn, 1 << logq)
+        w.ctx.debug_set_limits(limits[0], limits[1], 0)
+    common.check_distributed_fft(orc, workers, logn, False, 3, host_copy)
+    common.check_distributed_fft(orc, workers, logq, True, 4, host_copy)
+    common.check_distributed_fft(orc, workers, logq, True, 5, host_copy, n_in=(1 << logq) // 8)  # n coeffs on the 8n domain
+    for w in workers:
+        w.close()
+
+
+def test_msm_distributions_and_geometries(orc, ctx):
+    bases = orc.gen_bases(5, 600, 64, True)
+    ctx.debug_set_limits(11, 9, 0)
+    common.check_msm(orc, ctx, bases, 600, 21)
+    for c in (4, 7, 13):
+        ctx.debug_set_limits(11, 9, c)
+        common.check_msm(orc, ctx, bases, 300, 30 + c, which=("uniform", "witness-like"))
+    ctx.debug_set_limits(11, 9, 0)
+
+
+def test_msm_edges(orc, ctx):
+    bases = orc.gen_bases(5, 600, 64, True)
+    sc = orc.gen_fr(9, 600, False)
+    ident = orc.normalize(ctx.msm(10, 10, sc[:0]))
+    assert ident[96] == 1                                                       # empty range -> identity
+    common.assert_point_eq(orc, ctx.msm(100, 333, sc[:233]), orc.msm(bases[100:333], sc[:233]), "sub-range")
+    common.assert_point_eq(orc, ctx.msm(0, 600, sc[:50]), orc.msm(bases[:50], sc[:50]), "truncate to scalars")
+    common.assert_point_eq(orc, ctx.msm(0, 40, sc), orc.msm(bases[:40], sc[:40]), "truncate to bases")
+    common.assert_point_eq(orc, ctx.msm(3, 4, sc[:1]), orc.msm(bases[3:4], sc[:1]), "infinity base")
+    with pytest.raises(DpError) as e:
+        ctx.msm(0, 601, sc)
+    assert e.value.code == -1
+    # P + (-P) and repeated points (doubling path): bases 0 and 64 are the same point
+    s2 = np.zeros((65, 4), dtype=np.uint64)
+    s2[0] = common.u256(5)
+    s2[64] = common.u256(common.R_MOD - 5)
+    assert orc.normalize(ctx.msm(0, 65, s2))[96] == 1
+    s2[64] = common.u256(5)
+    common.assert_point_eq(orc, ctx.msm(0, 65, s2), orc.msm(bases[:65], s2), "same point twice")
+
+
+def test_commit_and_round1(orc, ctx):
+    bases = orc.gen_bases(5, 600, 64, True)
+    co = orc.gen_fr(21, 300, True)
+    common.assert_point_eq(orc, ctx.commit(co), orc.commit(bases, co), "commit_polynomial")
+    # round1 (worker.rs:383-408) with injected blinders
+    n = 1 << 6
+    evals = orc.gen_fr(22, n, True)
+    blind = orc.gen_fr(23, 2, True)
+    got = ctx.round1(evals, blind)
+    poly = orc.fft(evals, True, False)
+    L = orc.lib()
+    wire = np.zeros((n + 2, 4), dtype=np.uint64)
+    wire[:n] = poly
+    for k in range(2):
+        L.orc_fr_sub(wire[k].ctypes.data, blind[k].ctypes.data, wire[k].ctypes.data)
+        wire[n + k] = blind[k]
+    assert np.array_equal(ctx.get_wire(), wire)
+    common.assert_point_eq(orc, got, orc.commit(bases, wire), "round1 commitment")
+
+
+def test_error_behaviour(orc, emul_lib):
+    c = Context(emul_lib, 0, 0, 1)
+    with pytest.raises(DpError) as e:
+        c.msm(0, 0, np.zeros((0, 4), dtype=np.uint64))
+    assert e.value.code == -2                      # before init
+    c.init(np.zeros(0, dtype=np.uint8), 1 << 4, 1 << 7)
+    wl = [(0, 4, 0, 4)]
+    c.fft_init(1, wl, False, False, False)
+    with pytest.raises(DpError):
+        c.fft_init(1, wl, False, False, False)     # duplicate id
+    with pytest.raises(DpError):
+        c.fft1(1, 0, np.zeros((3, 4), dtype=np.uint64))   # wrong row length
+    with pytest.raises(DpError) as e:
+        c.fft2_prepare(1)                          # rows missing
+    assert e.value.code == -2
+    with pytest.raises(DpError):
+        c.fft2(7, 4, 4)                            # unknown task
+    with pytest.raises(DpError):
+        c.fft_init(2, [(0, 3, 0, 4)], False, False, False)   # not the equal split
+    c.close()
+    with pytest.raises(DpError):
+        Context(emul_lib, 0, 2, 2)                 # me >= n_workers

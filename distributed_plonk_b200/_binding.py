@@ -13,6 +13,7 @@ EXPORTS = [
     "dp_fft1", "dp_fft1_rows", "dp_fft2_prepare", "dp_fft_exchange_begin", "dp_fft_exchange_end", "dp_fft2",
     "dp_ntt", "dp_round1", "dp_get_wire", "dp_peer_arena_create", "dp_peer_attach", "dp_last_timing",
     "dp_launch_count", "dp_sync", "dp_msm_dev", "dp_ntt_dev", "dp_fft_dev", "dp_debug_set_limits",
+    "dp_last_msm_breakdown", "dp_debug_gen_bases", "dp_fft_dev_rows", "dp_fft_dev_cols",
 ]
 
 
@@ -56,6 +57,10 @@ def bind(cdll: C.CDLL) -> C.CDLL:
         "dp_ntt_dev": (i, [vp, vp, u32, i, i]),
         "dp_fft_dev": (i, [vp, vp, vp, i, i, i]),
         "dp_debug_set_limits": (i, [vp, u32, u32, i]),
+        "dp_last_msm_breakdown": (i, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+        "dp_debug_gen_bases": (i, [vp, u64, sz, vp]),
+        "dp_fft_dev_rows": (i, [vp, vp, i, i, i, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]),
+        "dp_fft_dev_cols": (i, [vp, vp]),
     }
     assert set(sig) == set(EXPORTS)
     for name, (res, args) in sig.items():
@@ -181,8 +186,27 @@ class Context:
     def fft_dev(self, rows_ptr: int, cols_ptr: int, is_quot: bool, is_inv: bool, is_coset: bool):
         self._ck(self.lib.dp_fft_dev(self.h, rows_ptr, cols_ptr, int(is_quot), int(is_inv), int(is_coset)))
 
+    def fft_dev_rows(self, rows_ptr: int, is_quot: bool, is_inv: bool, is_coset: bool):
+        s, r, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        self._ck(self.lib.dp_fft_dev_rows(self.h, rows_ptr, int(is_quot), int(is_inv), int(is_coset),
+                                          C.byref(s), C.byref(r), C.byref(n)))
+        return s.value, r.value, n.value
+
+    def fft_dev_cols(self, cols_ptr: int):
+        self._ck(self.lib.dp_fft_dev_cols(self.h, cols_ptr))
+
     def debug_set_limits(self, max_contig_log_k=11, max_strided_log_k=9, msm_window_bits=0):
         self._ck(self.lib.dp_debug_set_limits(self.h, max_contig_log_k, max_strided_log_k, msm_window_bits))
+
+    def msm_breakdown(self):
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        self.lib.dp_last_msm_breakdown(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
+
+    def gen_bases(self, seed: int, n: int) -> np.ndarray:
+        out = np.zeros((n, G1_AFFINE_BYTES), dtype=np.uint8)
+        self._ck(self.lib.dp_debug_gen_bases(self.h, seed, n, _addr(out) if n else None))
+        return out
 
     def sync(self):
         self._ck(self.lib.dp_sync(self.h))

@@ -97,6 +97,8 @@ struct dp_ctx {
     uint64_t me = 0, W = 1;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_msm[4] = {nullptr, nullptr, nullptr, nullptr};  // sort done | accumulate done | tail done
+    float msm_ms[3] = {0.f, 0.f, 0.f};
     std::string err;
     uint64_t launches = 0, launches_at_call = 0;
     float last_ms = 0.f;
@@ -110,6 +112,8 @@ struct dp_ctx {
     Fr *wire = nullptr;
     uint64_t wire_len = 0;
     uint64_t rng_state = 0x9E3779B97F4A7C15ull;
+    Fr *dev_send = nullptr, *dev_recv = nullptr;  // dp_fft_dev_rows / _cols staging (one transform in flight)
+    int dev_flags = -1;
     // pass-planning limits (dp_debug_set_limits lowers them so small tests reach the multi-pass plans)
     uint32_t max_contig_log_k = NTT_WTAB_LOG, max_strided_log_k = NTT_MAX_STRIDED_LOG_K;
     int msm_force_c = 0;
@@ -553,6 +557,7 @@ int msm_device(dp_ctx *ctx, const G1Affine *bases, const uint4 *scalars_dev, uin
         return fail(ctx, DP_E_OOM, "msm scratch for %llu points", (unsigned long long)n);
     }
     cudaStream_t st = ctx->stream;
+    cudaEventRecord(ctx->ev_msm[0], st);
     cudaMemsetAsync(counts, 0, (g.n_keys + 1) * 4ull, st);
     cudaMemsetAsync(err, 0, 4, st);
     DP_LAUNCH(msm_count_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, scalars_dev, n, g, counts, err);
@@ -561,11 +566,14 @@ int msm_device(dp_ctx *ctx, const G1Affine *bases, const uint4 *scalars_dev, uin
     cudaMemcpyAsync(cursor, offsets, (g.n_keys + 1) * 4ull, cudaMemcpyDeviceToDevice, st);
     DP_LAUNCH(msm_scatter_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, scalars_dev, n, g, cursor, sorted);
     DP_LAUNCH(msm_tasks_kernel, dim3(blocks_for(g.n_keys, 256)), dim3(256), 0, st, offsets, task_off, g.n_keys, tasks);
+    cudaEventRecord(ctx->ev_msm[1], st);
     DP_LAUNCH(msm_accumulate_kernel, dim3(blocks_for(max_tasks, MSM_TPB)), dim3(MSM_TPB), 0, st, tasks,
               task_off + g.n_keys, sorted, bases, partials);
+    cudaEventRecord(ctx->ev_msm[2], st);
     DP_LAUNCH(msm_reduce_kernel, dim3(blocks_for(n_segs, MSM_TPB)), dim3(MSM_TPB), 0, st, partials, task_off, g, seg_sums);
     DP_LAUNCH(msm_window_sum_kernel, dim3(g.n_windows), dim3(MSM_TPB), 0, st, seg_sums, g, win_sums);
     DP_LAUNCH(msm_final_kernel, dim3(1), dim3(32), 0, st, win_sums, g, out_dev);
+    cudaEventRecord(ctx->ev_msm[3], st);
     ctx->launches += 9;
     uint32_t err_host = 0;
     cudaError_t e = cudaMemcpyAsync(&err_host, err, 4, cudaMemcpyDeviceToHost, st);
@@ -573,6 +581,7 @@ int msm_device(dp_ctx *ctx, const G1Affine *bases, const uint4 *scalars_dev, uin
     if (e == cudaSuccess) e = cudaGetLastError();
     cleanup();
     if (e != cudaSuccess) return fail(ctx, DP_E_CUDA, "msm kernels: %s", cudaGetErrorString(e));
+    for (int k = 0; k < 3; k++) cudaEventElapsedTime(&ctx->msm_ms[k], ctx->ev_msm[k], ctx->ev_msm[k + 1]);
     if (err_host_out) *err_host_out = err_host;
     if (err_host) return fail(ctx, DP_E_ARG, "msm: a scalar is not a canonical Fr integer (>= 2^255)");
     return DP_OK;
@@ -636,6 +645,7 @@ int dp_create(int cuda_device, uint64_t me, uint64_t n_workers, dp_ctx **out) {
         if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = DP_E_CUDA; break; }
         cudaEventCreate(&ctx->ev0);
         cudaEventCreate(&ctx->ev1);
+        for (int k = 0; k < 4; k++) cudaEventCreate(&ctx->ev_msm[k]);
         if (cudaFuncSetAttribute(ntt_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)ntt_pass_smem_bytes(NTT_WTAB_LOG, 0)) != cudaSuccess) { rc = DP_E_CUDA; break; }
         const size_t wb = ((size_t)1 << NTT_WTAB_LOG) * sizeof(uint4);
@@ -667,6 +677,8 @@ int dp_destroy(dp_ctx *ctx) {
     ctx->pool.destroy();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (int k = 0; k < 4; k++)
+        if (ctx->ev_msm[k]) cudaEventDestroy(ctx->ev_msm[k]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return DP_OK;
@@ -946,6 +958,46 @@ int dp_fft_dev(dp_ctx *ctx, const void *rows_dev, void *cols_dev, int is_quot, i
     return call_end(ctx, true);
 }
 
+int dp_fft_dev_rows(dp_ctx *ctx, const void *rows_dev, int is_quot, int is_inv, int is_coset, void **send_dev,
+                    void **recv_dev, uint64_t *block_elems) {
+    if (!ctx || !rows_dev || !send_dev || !recv_dev || !block_elems) return fail(ctx, DP_E_ARG, "dp_fft_dev_rows: NULL argument");
+    if (!ctx->inited) return fail(ctx, DP_E_STATE, "dp_fft_dev_rows before dp_init");
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const DomainDev &d = ctx->dom[is_quot ? 1 : 0];
+    const uint64_t W = ctx->W, n_rows = d.r() / W, n_cols = d.c() / W, c = d.c();
+    call_begin(ctx);
+    ctx->pool.release(ctx->dev_send);
+    ctx->pool.release(ctx->dev_recv);
+    ctx->dev_send = (Fr *)ctx->pool.alloc(n_rows * c * sizeof(Fr));
+    ctx->dev_recv = W > 1 ? (Fr *)ctx->pool.alloc(d.r() * n_cols * sizeof(Fr)) : nullptr;
+    const bool need_scratch = d.log_c > ctx->max_contig_log_k;
+    Fr *scratch = need_scratch ? (Fr *)ctx->pool.alloc(n_rows * c * sizeof(Fr)) : nullptr;
+    if (!ctx->dev_send || (W > 1 && !ctx->dev_recv) || (need_scratch && !scratch)) return fail(ctx, DP_E_OOM, "dp_fft_dev_rows buffers");
+    int rc = plan_row_phase(ctx, d, (const Fr *)rows_dev, ctx->dev_send, scratch, n_rows, ctx->me * n_rows, is_inv != 0, is_coset != 0, W);
+    ctx->pool.release(scratch);
+    if (rc != DP_OK) return rc;
+    DP_TRY(call_end(ctx, true));
+    ctx->dev_flags = (is_quot ? 4 : 0) | (is_inv ? 2 : 0) | (is_coset ? 1 : 0);
+    *send_dev = ctx->dev_send;
+    *recv_dev = W > 1 ? ctx->dev_recv : ctx->dev_send;
+    *block_elems = n_rows * n_cols;
+    return DP_OK;
+}
+
+int dp_fft_dev_cols(dp_ctx *ctx, void *cols_dev) {
+    if (!ctx || !cols_dev) return fail(ctx, DP_E_ARG, "dp_fft_dev_cols: NULL argument");
+    if (ctx->dev_flags < 0) return fail(ctx, DP_E_STATE, "dp_fft_dev_cols before dp_fft_dev_rows");
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int f = ctx->dev_flags;
+    const DomainDev &d = ctx->dom[(f & 4) ? 1 : 0];
+    const uint64_t n_cols = d.c() / ctx->W;
+    call_begin(ctx);
+    Fr *src = ctx->W > 1 ? ctx->dev_recv : ctx->dev_send;
+    DP_TRY(plan_col_phase(ctx, d, src, (Fr *)cols_dev, n_cols, ctx->me * n_cols, (f & 2) != 0, (f & 1) != 0));
+    ctx->dev_flags = -1;
+    return call_end(ctx, true);
+}
+
 static int ntt_device(dp_ctx *ctx, Fr *x, uint32_t log_n, bool is_inv, bool is_coset) {
     // twiddles: reuse a resident domain table when it is at least as large, else build one
     const DomainDev *d = nullptr;
@@ -1073,6 +1125,29 @@ int dp_get_wire(dp_ctx *ctx, void *out, size_t out_bytes, size_t *n_coeffs) {
     DP_CUDA(ctx, cudaSetDevice(ctx->device));
     DP_CUDA(ctx, cudaMemcpyAsync(out, ctx->wire, ctx->wire_len * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
     DP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DP_OK;
+}
+
+int dp_last_msm_breakdown(const dp_ctx *ctx, float *sort_ms, float *accumulate_ms, float *reduce_ms) {
+    if (!ctx) return DP_E_ARG;
+    if (sort_ms) *sort_ms = ctx->msm_ms[0];
+    if (accumulate_ms) *accumulate_ms = ctx->msm_ms[1];
+    if (reduce_ms) *reduce_ms = ctx->msm_ms[2];
+    return DP_OK;
+}
+
+int dp_debug_gen_bases(dp_ctx *ctx, uint64_t seed, size_t n, void *out) {
+    if (!ctx || (n && !out)) return fail(ctx, DP_E_ARG, "dp_debug_gen_bases: NULL argument");
+    if (n == 0) return DP_OK;
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint64_t *dev = (uint64_t *)ctx->pool.alloc(n * (size_t)DP_G1_AFFINE_BYTES);
+    if (!dev) return fail(ctx, DP_E_OOM, "dp_debug_gen_bases");
+    DP_LAUNCH(g1_gen_bases_kernel, dim3(blocks_for(n, 128)), dim3(128), 0, ctx->stream, dev, (uint64_t)n, seed);
+    ctx->launches++;
+    cudaError_t e = cudaMemcpyAsync(out, dev, n * (size_t)DP_G1_AFFINE_BYTES, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    ctx->pool.release(dev);
+    if (e != cudaSuccess) return fail(ctx, DP_E_CUDA, "dp_debug_gen_bases: %s", cudaGetErrorString(e));
     return DP_OK;
 }
 

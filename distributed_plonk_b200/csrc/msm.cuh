@@ -85,6 +85,43 @@ __global__ void g1_import_ark_kernel(const uint64_t *ark, G1Affine *out, uint64_
     out[i] = p;
 }
 
+// Synthetic SRS for benchmarks / tests: out[i] = k_i * G with k_i = SplitMix64(seed, i) (64-bit,
+// distinct points), written in the raw ark GroupAffine layout (104 B) that dp_init ingests.
+DP_HD G1Affine g1_generator() {
+    const uint32_t gx[12] = {0xfd530c16u, 0x5cb38790u, 0x9976fff5u, 0x7817fc67u, 0x143ba1c1u, 0x154f95c7u,
+                             0xf3d0e747u, 0xf0ae6acdu, 0x21dbf440u, 0xedce6eccu, 0x9e0bfb75u, 0x12017741u};
+    const uint32_t gy[12] = {0x0ce72271u, 0xbaac93d5u, 0x7918fd8eu, 0x8c22631au, 0x570725ceu, 0xdd595f13u,
+                             0x50405194u, 0x51ac5829u, 0xad0059c0u, 0x0e1c8c3fu, 0x5008a26au, 0x0bbc3efcu};
+    G1Affine g;
+    for (int i = 0; i < 12; i++) {
+        g.x.l[i] = gx[i];
+        g.y.l[i] = gy[i];
+    }
+    return g;
+}
+__global__ void g1_gen_bases_kernel(uint64_t *ark_out, uint64_t n, uint64_t seed) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t z = seed + (i + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    z |= 1;
+    const G1Affine g = g1_generator();
+    G1XYZZ acc = G1XYZZ::inf();
+    for (int b = 63; b >= 0; b--) {
+        acc = acc.dbl();
+        if ((z >> b) & 1) acc = acc.add_mixed(g);
+    }
+    const G1Affine a = acc.to_affine();
+    uint64_t *dst = ark_out + i * 13;
+    for (int k = 0; k < 6; k++) {
+        dst[k] = (uint64_t)a.x.l[2 * k] | ((uint64_t)a.x.l[2 * k + 1] << 32);
+        dst[6 + k] = (uint64_t)a.y.l[2 * k] | ((uint64_t)a.y.l[2 * k + 1] << 32);
+    }
+    dst[12] = 0;  // infinity flag + padding
+}
+
 // ------------------------------------------------------------------ digit recode
 struct Scalar256 {
     uint32_t w[8];

@@ -137,6 +137,14 @@ uint64_t dp_launch_count(const dp_ctx *ctx);
 /* block until everything queued on the context stream has finished */
 int dp_sync(dp_ctx *ctx);
 
+/* device-side ms of the three phases of the last MSM on ctx: digit sort (count/scan/scatter/tasks),
+ * bucket accumulation (the dominant kernel), bucket reduction + window combine + normalise */
+int dp_last_msm_breakdown(const dp_ctx *ctx, float *sort_ms, float *accumulate_ms, float *reduce_ms);
+
+/* synthetic SRS: n distinct points k_i*G (k_i = SplitMix64(seed, i)), raw 104-byte G1Affine each,
+ * computed on the device and written to HOST memory `out` (feeds dp_init in benches and tests) */
+int dp_debug_gen_bases(dp_ctx *ctx, uint64_t seed, size_t n, void *out);
+
 /* test hook: lower the pass-planning limits (sub-transform sizes 2^k handled by one kernel pass;
  * defaults 11 / 9) and/or force the MSM window width (0 = automatic) so that small inputs
  * exercise the multi-pass NTT plans and every MSM geometry. */
@@ -149,6 +157,13 @@ int dp_ntt_dev(dp_ctx *ctx, void *data_dev, uint32_t log_n, int is_inv, int is_c
 /* full 2-D pipeline of one worker on device-resident rows: rows_dev = my rows (n_rows*c Fr),
  * cols_dev receives my columns (n_cols*r Fr); n_workers must be 1 or peers attached. */
 int dp_fft_dev(dp_ctx *ctx, const void *rows_dev, void *cols_dev, int is_quot, int is_inv, int is_coset);
+/* the same split around the caller's all-to-all for n_workers > 1 (one transform in flight per ctx):
+ * _rows runs the row phase on my row block (rows_dev: r/W x c Fr) and returns the exchange buffers
+ * exactly like dp_fft_exchange_begin; after the all-to-all _cols runs the column phase into
+ * cols_dev (c/W x r Fr).  With n_workers == 1 recv == send and no exchange is needed. */
+int dp_fft_dev_rows(dp_ctx *ctx, const void *rows_dev, int is_quot, int is_inv, int is_coset, void **send_dev,
+                    void **recv_dev, uint64_t *block_elems);
+int dp_fft_dev_cols(dp_ctx *ctx, void *cols_dev);
 
 #ifdef __cplusplus
 }

@@ -54,7 +54,7 @@ def test_whole_ntt(orc, ctx, log_n):
         common.check_whole_ntt(orc, ctx, log_n, 90 + log_n, n_in=(1 << log_n) // 8 + 3)
 
 
-@pytest.mark.parametrize("limits,logs", [((3, 2), (4, 5, 6)), ((4, 3), (7, 9, 12)), ((6, 5), (15,))])
+@pytest.mark.parametrize("limits,logs", [((3, 2), (4, 5, 6)), ((4, 3), (7, 9)), ((6, 5), (12, 15))])
 def test_whole_ntt_forced_multi_pass(orc, ctx, limits, logs):
     ctx.debug_set_limits(limits[0], limits[1], 0)
     try:

@@ -10,9 +10,9 @@ lib = dp.load()
 logn = int(sys.argv[1]) if len(sys.argv) > 1 else 22
 n = (1 << logn) + 32
 t0 = time.time()
-bases = orc.gen_bases(5, n, 2048, True)
-print("gen bases", round(time.time() - t0, 2), flush=True)
 ctx = dp.Context(lib, 0, 0, 1)
+bases = ctx.gen_bases(5, n)
+print("gen bases (gpu, distinct)", round(time.time() - t0, 2), flush=True)
 t0 = time.time()
 ctx.init(bases, 1 << logn, 1 << (logn + 3))
 print("init ms", round((time.time() - t0) * 1e3, 1), ctx.last_timing(), flush=True)
@@ -46,6 +46,6 @@ for kind in ("uniform", "witness"):
         for rep in range(3):
             ctx.msm_dev(0, m, scd.data_ptr(), m, out.data_ptr())
         ms, nl = ctx.last_timing()
-        print(f"msm_dev {kind} n={m}: {ms:.3f} ms, {nl} launches", flush=True)
+        print(f"msm_dev {kind} n={m}: {ms:.3f} ms, {nl} launches, sort/accumulate/reduce ms = {[round(v,3) for v in ctx.msm_breakdown()]}", flush=True)
 torch.cuda.synchronize()
 print("done")

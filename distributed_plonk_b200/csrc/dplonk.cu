@@ -548,11 +548,14 @@ int msm_device(dp_ctx *ctx, const G1Affine *bases, const uint4 *scalars_dev, uin
     G1XYZZ *seg_sums = (G1XYZZ *)P.alloc((uint64_t)n_segs * sizeof(G1XYZZ));
     G1XYZZ *win_sums = (G1XYZZ *)P.alloc((uint64_t)g.n_windows * sizeof(G1XYZZ));
     uint32_t *err = (uint32_t *)P.alloc(4);
+    const uint32_t n_scan_blocks = (g.n_keys + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    uint2 *block_sums = (uint2 *)P.alloc((size_t)n_scan_blocks * sizeof(uint2));
     auto cleanup = [&]() {
+        P.release(block_sums);
         P.release(counts); P.release(offsets); P.release(cursor); P.release(task_off); P.release(sorted);
         P.release(tasks); P.release(partials); P.release(seg_sums); P.release(win_sums); P.release(err);
     };
-    if (!counts || !offsets || !cursor || !task_off || !sorted || !tasks || !partials || !seg_sums || !win_sums || !err) {
+    if (!counts || !offsets || !cursor || !task_off || !sorted || !tasks || !partials || !seg_sums || !win_sums || !err || !block_sums) {
         cleanup();
         return fail(ctx, DP_E_OOM, "msm scratch for %llu points", (unsigned long long)n);
     }
@@ -561,8 +564,9 @@ int msm_device(dp_ctx *ctx, const G1Affine *bases, const uint4 *scalars_dev, uin
     cudaMemsetAsync(counts, 0, (g.n_keys + 1) * 4ull, st);
     cudaMemsetAsync(err, 0, 4, st);
     DP_LAUNCH(msm_count_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, scalars_dev, n, g, counts, err);
-    DP_LAUNCH(scan_exclusive_kernel, dim3(1), dim3(1024), 0, st, counts, offsets, g.n_keys, 0u);
-    DP_LAUNCH(scan_exclusive_kernel, dim3(1), dim3(1024), 0, st, counts, task_off, g.n_keys, MSM_TSEG);
+    DP_LAUNCH(scan_block_sums_kernel, dim3(n_scan_blocks), dim3(SCAN_TPB), 0, st, counts, g.n_keys, block_sums);
+    DP_LAUNCH(scan_block_offsets_kernel, dim3(1), dim3(SCAN_TPB), 0, st, block_sums, n_scan_blocks, offsets, task_off, g.n_keys);
+    DP_LAUNCH(scan_write_kernel, dim3(n_scan_blocks), dim3(SCAN_TPB), 0, st, counts, g.n_keys, block_sums, offsets, task_off);
     cudaMemcpyAsync(cursor, offsets, (g.n_keys + 1) * 4ull, cudaMemcpyDeviceToDevice, st);
     DP_LAUNCH(msm_scatter_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, scalars_dev, n, g, cursor, sorted);
     DP_LAUNCH(msm_tasks_kernel, dim3(blocks_for(g.n_keys, 256)), dim3(256), 0, st, offsets, task_off, g.n_keys, tasks);
@@ -574,7 +578,7 @@ int msm_device(dp_ctx *ctx, const G1Affine *bases, const uint4 *scalars_dev, uin
     DP_LAUNCH(msm_window_sum_kernel, dim3(g.n_windows), dim3(MSM_TPB), 0, st, seg_sums, g, win_sums);
     DP_LAUNCH(msm_final_kernel, dim3(1), dim3(32), 0, st, win_sums, g, out_dev);
     cudaEventRecord(ctx->ev_msm[3], st);
-    ctx->launches += 9;
+    ctx->launches += 10;
     uint32_t err_host = 0;
     cudaError_t e = cudaMemcpyAsync(&err_host, err, 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);

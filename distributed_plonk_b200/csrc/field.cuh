@@ -40,6 +40,7 @@ struct FrParams {
         return m[i];
     }
     static constexpr uint32_t INV = 0xffffffffu;  // -r^-1 mod 2^32
+    static constexpr bool OUTLINE_MUL = false;    // NTT butterflies: a handful of call sites, keep inline
 };
 
 struct FqParams {
@@ -63,6 +64,11 @@ struct FqParams {
         return m[i];
     }
     static constexpr uint32_t INV = 0xfffcfffdu;  // -p^-1 mod 2^32
+    // One Fq product is ~380 SASS instructions (6 KB).  The curve formulas use 10-16 of them per
+    // point operation; inlining every site made the MSM kernels 60-400 KB of straight-line code that
+    // thrashed the instruction cache (ncu: 14% "no instruction" stalls in msm_accumulate, 30x
+    // slowdown of msm_reduce).  A real call costs ~30 register moves (args travel in registers).
+    static constexpr bool OUTLINE_MUL = true;
 };
 
 // ------------------------------------------------------------------------------ field
@@ -183,7 +189,16 @@ struct Field : Limbs<P::N> {
         hi[N - 1] = ptx::addc(hi[N - 1], 0u);
     }
 
+#if defined(__CUDACC__)
+    __device__ __noinline__ static Field mul_outlined(Field a, Field b) { return mul_inline(a, b); }
+#endif
     DP_HD friend Field operator*(const Field &a, const Field &b) {
+#if defined(__CUDA_ARCH__)
+        if (P::OUTLINE_MUL) return mul_outlined(a, b);
+#endif
+        return mul_inline(a, b);
+    }
+    DP_HD static Field mul_inline(const Field &a, const Field &b) {
         uint32_t even[N], odd[N];
 #pragma unroll
         for (int i = 0; i < N; i += 2) {

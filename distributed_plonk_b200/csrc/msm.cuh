@@ -9,7 +9,7 @@
 //
 //   1. msm_count      signed-digit recode (digits in [-2^(c-1), 2^(c-1)]), histogram of
 //                     (window, |digit|) keys with L2 atomics; 128-bit coalesced scalar loads
-//   2. scan           exclusive prefix sums -> bucket offsets and task offsets
+//   2. scan (3 kernels) exclusive prefix sums -> bucket offsets and task offsets
 //   3. msm_scatter    counting-sort the point indices by key (sign kept in bit 31)
 //   4. msm_tasks      cut every bucket into tasks of <= TSEG points (load balance for skewed
 //                     scalars: witness vectors are full of 0/1/small values)
@@ -49,7 +49,8 @@ inline MsmGeom msm_geometry(uint64_t n, int force_c = 0) {
     double best = 1e300;
     for (uint32_t c = 4; c <= 18; c++) {
         double w = (double)((256 + c - 1) / c);
-        double cost = (double)n * w * 10.0 + 2.0 * w * (double)(1u << (c - 1)) * 14.0;
+        // (the reduce phase runs with far fewer threads than the accumulate phase: weight it x2)
+        double cost = (double)n * w * 10.0 + 2.0 * 2.0 * w * (double)(1u << (c - 1)) * 14.0;
         if (cost < best) {
             best = cost;
             best_c = c;
@@ -179,35 +180,103 @@ __global__ void msm_scatter_kernel(const uint4 *scalars, uint64_t n, MsmGeom g, 
     });
 }
 
-// ------------------------------------------------------------------ single-block exclusive scan
-// out[i] = sum_{k<i} t(in[k]) for i <= n (n+1 outputs);  t(x) = x  or  ceil(x / div) when div > 0
-__global__ void scan_exclusive_kernel(const uint32_t *in, uint32_t *out, uint32_t n, uint32_t div) {
-    __shared__ uint32_t part[1024];
+// ------------------------------------------------------------------ exclusive scans (3 phases)
+// offsets[i]  = sum_{k<i} counts[k]                  (bucket start in sorted[])
+// task_off[i] = sum_{k<i} ceil(counts[k] / TSEG)     (first task of bucket i)     for i <= n
+constexpr int SCAN_TPB = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_BLOCK = SCAN_TPB * SCAN_ITEMS;
+
+DP_D uint32_t tasks_of(uint32_t cnt) { return (cnt + MSM_TSEG - 1) / MSM_TSEG; }
+
+// block-wide exclusive scan of one value per thread (Hillis-Steele in shared memory); returns the
+// exclusive prefix of this thread and the block total
+DP_D uint32_t block_exclusive_scan(uint32_t v, uint32_t *sh, uint32_t &total) {
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
-    const uint32_t chunk = (n + nt - 1) / nt;
-    const uint32_t lo = tid * chunk < n ? tid * chunk : n;
-    const uint32_t hi = lo + chunk < n ? lo + chunk : n;
-    uint32_t sum = 0;
-    for (uint32_t i = lo; i < hi; i++) {
-        uint32_t v = in[i];
-        sum += div ? (v + div - 1) / div : v;
-    }
-    part[tid] = sum;
+    sh[tid] = v;
     __syncthreads();
-    // Hillis-Steele inclusive scan over the per-thread sums
     for (uint32_t off = 1; off < nt; off <<= 1) {
-        uint32_t add = tid >= off ? part[tid - off] : 0;
+        uint32_t add = tid >= off ? sh[tid - off] : 0;
         __syncthreads();
-        part[tid] += add;
+        sh[tid] += add;
         __syncthreads();
     }
-    uint32_t run = tid ? part[tid - 1] : 0;
-    for (uint32_t i = lo; i < hi; i++) {
-        out[i] = run;
-        uint32_t v = in[i];
-        run += div ? (v + div - 1) / div : v;
+    total = sh[nt - 1];
+    const uint32_t excl = tid ? sh[tid - 1] : 0;
+    __syncthreads();
+    return excl;
+}
+
+__global__ void __launch_bounds__(SCAN_TPB) scan_block_sums_kernel(const uint32_t *counts, uint32_t n, uint2 *block_sums) {
+    __shared__ uint32_t sh[SCAN_TPB];
+    const uint32_t base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
+    uint32_t a = 0, t = 0;
+    for (int k = 0; k < SCAN_ITEMS; k++)
+        if (base + k < n) {
+            const uint32_t c = counts[base + k];
+            a += c;
+            t += tasks_of(c);
+        }
+    uint32_t ta, tt;
+    block_exclusive_scan(a, sh, ta);
+    block_exclusive_scan(t, sh, tt);
+    if (threadIdx.x == 0) {
+        uint2 r;
+        r.x = ta;
+        r.y = tt;
+        block_sums[blockIdx.x] = r;
     }
-    if (tid == nt - 1) out[n] = part[nt - 1];
+}
+
+// single block: exclusive scan of the per-block sums in place; grand totals -> offsets[n], task_off[n]
+__global__ void __launch_bounds__(SCAN_TPB) scan_block_offsets_kernel(uint2 *block_sums, uint32_t n_blocks, uint32_t *offsets,
+                                                                       uint32_t *task_off, uint32_t n) {
+    __shared__ uint32_t sh[SCAN_TPB];
+    uint32_t run_a = 0, run_t = 0;
+    for (uint32_t base = 0; base < n_blocks; base += SCAN_TPB) {
+        const uint32_t i = base + threadIdx.x;
+        uint2 v;
+        v.x = v.y = 0;
+        if (i < n_blocks) v = block_sums[i];
+        uint32_t ta, tt;
+        const uint32_t ea = block_exclusive_scan(v.x, sh, ta);
+        const uint32_t et = block_exclusive_scan(v.y, sh, tt);
+        if (i < n_blocks) {
+            uint2 o;
+            o.x = run_a + ea;
+            o.y = run_t + et;
+            block_sums[i] = o;
+        }
+        run_a += ta;
+        run_t += tt;
+    }
+    if (threadIdx.x == 0) {
+        offsets[n] = run_a;
+        task_off[n] = run_t;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_TPB) scan_write_kernel(const uint32_t *counts, uint32_t n, const uint2 *block_sums,
+                                                               uint32_t *offsets, uint32_t *task_off) {
+    __shared__ uint32_t sh[SCAN_TPB];
+    const uint32_t base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
+    uint32_t c[SCAN_ITEMS];
+    uint32_t a = 0, t = 0;
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        c[k] = base + k < n ? counts[base + k] : 0;
+        a += c[k];
+        t += tasks_of(c[k]);
+    }
+    uint32_t ta, tt;
+    uint32_t ea = block_exclusive_scan(a, sh, ta) + block_sums[blockIdx.x].x;
+    uint32_t et = block_exclusive_scan(t, sh, tt) + block_sums[blockIdx.x].y;
+    for (int k = 0; k < SCAN_ITEMS; k++)
+        if (base + k < n) {
+            offsets[base + k] = ea;
+            task_off[base + k] = et;
+            ea += c[k];
+            et += tasks_of(c[k]);
+        }
 }
 
 // ------------------------------------------------------------------ tasks

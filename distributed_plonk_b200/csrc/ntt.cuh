@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(NTT_TPB, 2) ntt_tile_kernel(NttPass p) {
     if (p.log_k & 1) {  // one radix-2 stage on top so that the rest pairs up
         const uint32_t span = 1u << s, units = tile >> 1, upl = K >> 1;  // units per lane
         for (uint32_t u = tid; u < units; u += NTT_TPB) {
-            const uint32_t g = u / upl, uu = u % upl;
+            const uint32_t g = u >> (p.log_k - 1), uu = u & (upl - 1);
             const uint32_t j = uu & (span - 1);
             const uint32_t m0 = ((uu >> s) << (s + 1)) | j;
             const uint32_t e0 = g * pitch + m0, e1 = e0 + span;
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(NTT_TPB, 2) ntt_tile_kernel(NttPass p) {
         const int sl = s - 1;
         const uint32_t q = 1u << sl, units = tile >> 2, upl = K >> 2;
         for (uint32_t u = tid; u < units; u += NTT_TPB) {
-            const uint32_t g = u / upl, uu = u % upl;
+            const uint32_t g = u >> (p.log_k - 2), uu = u & (upl - 1);
             const uint32_t j = uu & (q - 1);
             const uint32_t m0 = ((uu >> sl) << (sl + 2)) | j;
             const uint32_t e0 = g * pitch + m0;

@@ -550,12 +550,15 @@ int msm_device(dp_ctx *ctx, const G1Affine *bases, const uint4 *scalars_dev, uin
     uint32_t *err = (uint32_t *)P.alloc(4);
     const uint32_t n_scan_blocks = (g.n_keys + SCAN_BLOCK - 1) / SCAN_BLOCK;
     uint2 *block_sums = (uint2 *)P.alloc((size_t)n_scan_blocks * sizeof(uint2));
+    const uint64_t max_multi = max_digits / MSM_TSEG + 1;  // a bucket with > TSEG points
+    uint32_t *multi_keys = (uint32_t *)P.alloc((max_multi + 1) * 4ull);  // [0] = counter, then keys
     auto cleanup = [&]() {
         P.release(block_sums);
+        P.release(multi_keys);
         P.release(counts); P.release(offsets); P.release(cursor); P.release(task_off); P.release(sorted);
         P.release(tasks); P.release(partials); P.release(seg_sums); P.release(win_sums); P.release(err);
     };
-    if (!counts || !offsets || !cursor || !task_off || !sorted || !tasks || !partials || !seg_sums || !win_sums || !err || !block_sums) {
+    if (!counts || !offsets || !cursor || !task_off || !sorted || !tasks || !partials || !seg_sums || !win_sums || !err || !block_sums || !multi_keys) {
         cleanup();
         return fail(ctx, DP_E_OOM, "msm scratch for %llu points", (unsigned long long)n);
     }
@@ -563,22 +566,26 @@ int msm_device(dp_ctx *ctx, const G1Affine *bases, const uint4 *scalars_dev, uin
     cudaEventRecord(ctx->ev_msm[0], st);
     cudaMemsetAsync(counts, 0, (g.n_keys + 1) * 4ull, st);
     cudaMemsetAsync(err, 0, 4, st);
+    cudaMemsetAsync(multi_keys, 0, 4, st);
     DP_LAUNCH(msm_count_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, scalars_dev, n, g, counts, err);
     DP_LAUNCH(scan_block_sums_kernel, dim3(n_scan_blocks), dim3(SCAN_TPB), 0, st, counts, g.n_keys, block_sums);
     DP_LAUNCH(scan_block_offsets_kernel, dim3(1), dim3(SCAN_TPB), 0, st, block_sums, n_scan_blocks, offsets, task_off, g.n_keys);
     DP_LAUNCH(scan_write_kernel, dim3(n_scan_blocks), dim3(SCAN_TPB), 0, st, counts, g.n_keys, block_sums, offsets, task_off);
     cudaMemcpyAsync(cursor, offsets, (g.n_keys + 1) * 4ull, cudaMemcpyDeviceToDevice, st);
     DP_LAUNCH(msm_scatter_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, scalars_dev, n, g, cursor, sorted);
-    DP_LAUNCH(msm_tasks_kernel, dim3(blocks_for(g.n_keys, 256)), dim3(256), 0, st, offsets, task_off, g.n_keys, tasks);
+    DP_LAUNCH(msm_tasks_kernel, dim3(blocks_for(g.n_keys, 256)), dim3(256), 0, st, offsets, task_off, g.n_keys, tasks,
+              multi_keys + 1, multi_keys);
     cudaEventRecord(ctx->ev_msm[1], st);
     DP_LAUNCH(msm_accumulate_kernel, dim3(blocks_for(max_tasks, MSM_TPB)), dim3(MSM_TPB), 0, st, tasks,
               task_off + g.n_keys, sorted, bases, partials);
+    DP_LAUNCH(msm_collapse_kernel, dim3(blocks_for(max_multi * 32, MSM_TPB)), dim3(MSM_TPB), 0, st, multi_keys + 1, multi_keys,
+              task_off, partials);
     cudaEventRecord(ctx->ev_msm[2], st);
     DP_LAUNCH(msm_reduce_kernel, dim3(blocks_for(n_segs, MSM_TPB)), dim3(MSM_TPB), 0, st, partials, task_off, g, seg_sums);
     DP_LAUNCH(msm_window_sum_kernel, dim3(g.n_windows), dim3(MSM_TPB), 0, st, seg_sums, g, win_sums);
     DP_LAUNCH(msm_final_kernel, dim3(1), dim3(32), 0, st, win_sums, g, out_dev);
     cudaEventRecord(ctx->ev_msm[3], st);
-    ctx->launches += 10;
+    ctx->launches += 11;
     uint32_t err_host = 0;
     cudaError_t e = cudaMemcpyAsync(&err_host, err, 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);

@@ -15,6 +15,8 @@
 //                     scalars: witness vectors are full of 0/1/small values)
 //   5. msm_accumulate one thread per task: XYZZ accumulator in registers, mixed additions of the
 //                     gathered affine bases (96 B = 6 x 128-bit loads each)
+//   5b. msm_collapse  buckets that were cut into several tasks: one warp per bucket, lanes
+//                     stride over its partial sums, warp-shuffle butterfly reduction
 //   6. msm_reduce     per window, per segment of buckets: running-sum reduction
 //                     sum_k k*B_k (+ small scalar multiple for the segment offset)
 //   7. msm_window_sum block per window: tree reduction of the segment sums
@@ -282,11 +284,13 @@ __global__ void __launch_bounds__(SCAN_TPB) scan_write_kernel(const uint32_t *co
 // ------------------------------------------------------------------ tasks
 // tasks[t] = {first index into sorted[], number of points}; bucket `key` owns tasks
 // [task_off[key], task_off[key+1])
-__global__ void msm_tasks_kernel(const uint32_t *offsets, const uint32_t *task_off, uint32_t n_keys, uint2 *tasks) {
+__global__ void msm_tasks_kernel(const uint32_t *offsets, const uint32_t *task_off, uint32_t n_keys, uint2 *tasks,
+                                 uint32_t *multi_keys, uint32_t *n_multi) {
     const uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
     if (key >= n_keys) return;
     const uint32_t start = offsets[key], cnt = offsets[key + 1] - start;
     uint32_t t = task_off[key];
+    if (cnt > MSM_TSEG) multi_keys[atomicAdd(n_multi, 1u)] = key;  // needs msm_collapse below
     for (uint32_t done = 0; done < cnt; done += MSM_TSEG, t++) {
         uint2 e;
         e.x = start + done;
@@ -324,11 +328,36 @@ __global__ void __launch_bounds__(MSM_TPB) msm_accumulate_kernel(const uint2 *ta
     partials[t] = acc;
 }
 
-// sum of the partial sums of one bucket
+// Buckets cut into several tasks (skewed scalars: one bucket can hold a large share of all points)
+// are folded by ONE WARP each: lanes stride over the bucket's partial sums, then a warp-shuffle
+// butterfly adds the 32 lane sums; the result replaces the bucket's first partial.
+DP_D G1XYZZ shfl_xor_point(const G1XYZZ &p, int mask) {
+    G1XYZZ r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        r.x.l[i] = __shfl_xor_sync(0xffffffffu, p.x.l[i], mask);
+        r.y.l[i] = __shfl_xor_sync(0xffffffffu, p.y.l[i], mask);
+        r.zz.l[i] = __shfl_xor_sync(0xffffffffu, p.zz.l[i], mask);
+        r.zzz.l[i] = __shfl_xor_sync(0xffffffffu, p.zzz.l[i], mask);
+    }
+    return r;
+}
+__global__ void __launch_bounds__(MSM_TPB) msm_collapse_kernel(const uint32_t *multi_keys, const uint32_t *n_multi,
+                                                                const uint32_t *task_off, G1XYZZ *partials) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= *n_multi) return;  // whole warps leave together
+    const uint32_t key = multi_keys[warp];
+    const uint32_t t0 = task_off[key], t1 = task_off[key + 1];
+    G1XYZZ acc = G1XYZZ::inf();
+    for (uint32_t t = t0 + lane; t < t1; t += 32) acc = acc.add(partials[t]);
+    for (int m = 16; m >= 1; m >>= 1) acc = acc.add(shfl_xor_point(acc, m));
+    if (lane == 0) partials[t0] = acc;
+}
+
+// sum of one bucket: its (single, or collapsed) partial sum
 DP_D G1XYZZ bucket_sum(const G1XYZZ *partials, const uint32_t *task_off, uint32_t key) {
-    G1XYZZ b = G1XYZZ::inf();
-    for (uint32_t t = task_off[key]; t < task_off[key + 1]; t++) b = b.add(partials[t]);
-    return b;
+    const uint32_t t0 = task_off[key];
+    return t0 < task_off[key + 1] ? partials[t0] : G1XYZZ::inf();
 }
 
 // k * P for a small non-negative integer k

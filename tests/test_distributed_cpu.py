@@ -21,10 +21,16 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, emul_path, out_dir):
+def _worker(rank, world, port, lib_path, out_dir, backend="gloo"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cuda = backend == "nccl"
+    if cuda:
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    emul_path = lib_path
     from distributed_plonk_b200 import dispatcher as disp
     from distributed_plonk_b200 import parallel
     from distributed_plonk_b200._binding import bind
@@ -32,7 +38,7 @@ def _worker(rank, world, port, emul_path, out_dir):
     from oracle import loader as orc
 
     lib = bind(ctypes.CDLL(emul_path))
-    w = PlonkSlave(lib, rank, world)
+    w = PlonkSlave(lib, rank, world, device=rank if cuda else 0)
     n_bases = 256
     bases = orc.gen_bases(5, n_bases, 32, True)
     w.init(chunks(bases), 1 << 6, 1 << 9)
@@ -49,20 +55,24 @@ def _worker(rank, world, port, emul_path, out_dir):
                 w.fft1(tid, j, chunks(rows[wl[rank][0] + j]))
             w.fft2_prepare(tid, exchange)
             mine = torch.from_numpy(w.fft2_array(tid).view(np.int64))
+            if cuda:
+                mine = mine.cuda()
             gathered = [torch.empty_like(mine) for _ in range(world)]
             dist.all_gather(gathered, mine)
-            cols = torch.cat(gathered).numpy().view(np.uint64)
+            cols = torch.cat(gathered).cpu().numpy().view(np.uint64)
             got = disp.assemble(cols)
             ok &= bool(np.array_equal(got, orc.fft(x, inv, cos)))
     # sharded MSM: index-range split, partials summed by the dispatcher (rank 0 here)
     sc = orc.gen_fr(77, n_bases, False)
     lo, hi = parallel.msm_shard(n_bases, rank, world)
     part = torch.from_numpy(np.frombuffer(w.var_msm((lo, hi), chunks(sc[lo:hi])), dtype=np.uint8).copy())
+    if cuda:
+        part = part.cuda()
     parts = [torch.empty_like(part) for _ in range(world)]
     dist.all_gather(parts, part)
-    acc = parts[0].numpy()
+    acc = parts[0].cpu().numpy()
     for p in parts[1:]:
-        acc = orc.g1_add(acc, p.numpy())
+        acc = orc.g1_add(acc, p.cpu().numpy())
     ok &= bool(np.array_equal(orc.normalize(acc), orc.normalize(orc.msm(bases, sc))))
     with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as f:
         f.write("ok" if ok else "FAIL")

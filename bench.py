@@ -341,7 +341,8 @@ def main():
         wl_n, wl_m = disp.fft_workloads(log_n, W), disp.fft_workloads(log_m, W)
         tid = [rank * 0]
 
-        def fft_host(h_in, h_out, wl, n_rows, is_quot, is_inv, is_coset):
+        def submit(h_in, wl, n_rows, is_quot, is_inv, is_coset):
+            """fft_init + fft1 (async H2D) + fft2_prepare (async row/column kernels)"""
             tid[0] += 1
             ctx.fft_init(tid[0], wl, is_quot, is_inv, is_coset)
             ctx._ck(lib.dp_fft1_rows(ctx.h, tid[0], 0, n_rows, h_in.data_ptr()))
@@ -351,18 +352,29 @@ def main():
                 s, r, blk = ctx.fft_exchange_begin(tid[0])
                 exchange(s, r, blk)
                 ctx.fft_exchange_end(tid[0])
-            ctx._ck(lib.dp_fft2(ctx.h, tid[0], h_out.data_ptr(), h_out.numel() * 8))
+            return tid[0]
+
+        def collect(t, h_out):
+            """fft2: D2H of the task's columns (blocks); the next task is already in flight"""
+            ctx._ck(lib.dp_fft2(ctx.h, t, h_out.data_ptr(), h_out.numel() * 8))
 
         msm_host_out = np.zeros(144, dtype=np.uint8)
 
         def step_e2e():
+            # the dispatcher issues its FFT tasks concurrently (join_all, dispatcher2.rs:294-306,
+            # 382-414); one task of look-ahead is enough to overlap copy-in / compute / copy-out
             for _ in range(N_MSM):
                 ctx._ck(lib.dp_msm(ctx.h, lo, hi, h_scal.data_ptr(), hi - lo, _addr(msm_host_out)))
-            for _ in range(N_INTT_N):
-                fft_host(h_in_n, h_out_n, wl_n, rows_n, False, True, False)
-            for _ in range(N_COSET_8N):
-                fft_host(h_in_m, h_out_m, wl_m, rows_m, True, False, True)
-            fft_host(h_in_m, h_out_m, wl_m, rows_m, True, True, True)
+            jobs = [(h_in_n, h_out_n, wl_n, rows_n, False, True, False)] * N_INTT_N
+            jobs += [(h_in_m, h_out_m, wl_m, rows_m, True, False, True)] * N_COSET_8N
+            jobs += [(h_in_m, h_out_m, wl_m, rows_m, True, True, True)] * N_COSET_INTT_8N
+            pending = None
+            for (h_in, h_out, wl, n_rows, q, inv, cos) in jobs:
+                t = submit(h_in, wl, n_rows, q, inv, cos)
+                if pending is not None:
+                    collect(*pending)
+                pending = (t, h_out)
+            collect(*pending)
 
         e_steps = max(1, min(args.steps, 2))
         dt_e, _ = timed(step_e2e, e_steps, 1)

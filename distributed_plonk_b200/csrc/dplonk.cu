@@ -85,9 +85,12 @@ struct FftTask {
     Fr *rows = nullptr;  // [n_rows][c]
     Fr *send = nullptr;  // W blocks of [n_rows][c/W]           (aliases rows when W == 1)
     Fr *recv = nullptr;  // [r][n_cols] = W blocks of [r/W][n_cols] (aliases send when W == 1)
+    Fr *cols = nullptr;  // [n_cols][r]  column-phase result, produced asynchronously after the exchange
     uint64_t rows_filled = 0;
     std::vector<uint8_t> row_seen;
     bool row_phase_done = false, exchanged = false;
+    cudaEvent_t ev_in = nullptr;  // last fft1 H2D copy (copy-in stream)
+    cudaEvent_t ev_c = nullptr;   // column phase finished (compute stream)
 };
 
 }  // namespace
@@ -95,14 +98,17 @@ struct FftTask {
 struct dp_ctx {
     int device = 0;
     uint64_t me = 0, W = 1;
-    cudaStream_t stream = nullptr;
+    // Three streams so that consecutive tasks overlap: rows of task k+1 stream in (s_in) while task k
+    // computes (stream) and the columns of task k-1 stream out (s_out); PCIe is full duplex.
+    cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_msm[4] = {nullptr, nullptr, nullptr, nullptr};  // sort done | accumulate done | tail done
     float msm_ms[3] = {0.f, 0.f, 0.f};
     std::string err;
     uint64_t launches = 0, launches_at_call = 0;
     float last_ms = 0.f;
-    DevPool pool;
+    DevPool pool;     // everything touched by the compute stream (stream-ordered reuse)
+    DevPool pool_io;  // fft1 row buffers: written by s_in, recycled only after their task fully completed
     uint4 *wf_lo = nullptr, *wf_hi = nullptr, *wi_lo = nullptr, *wi_hi = nullptr;
     G1Affine *bases = nullptr;
     uint64_t n_bases = 0;
@@ -516,11 +522,16 @@ void free_domain(dp_ctx *ctx, DomainDev &d) {
     d = DomainDev();
 }
 
+// only called when every stream is done with the task (after the D2H of dp_fft2, or at dp_init)
 void free_task(dp_ctx *ctx, FftTask &t) {
     if (t.recv && t.recv != t.send) ctx->pool.release(t.recv);
     if (t.send && t.send != t.rows) ctx->pool.release(t.send);
-    ctx->pool.release(t.rows);
-    t.rows = t.send = t.recv = nullptr;
+    ctx->pool.release(t.cols);
+    ctx->pool_io.release(t.rows);
+    t.rows = t.send = t.recv = t.cols = nullptr;
+    if (t.ev_in) cudaEventDestroy(t.ev_in);
+    if (t.ev_c) cudaEventDestroy(t.ev_c);
+    t.ev_in = t.ev_c = nullptr;
 }
 
 // ------------------------------------------------------------------ MSM driver (device pointers)
@@ -619,10 +630,24 @@ int run_row_phase(dp_ctx *ctx, FftTask &t) {
     } else if (ctx->W == 1) {
         t.send = t.rows;
     }
+    cudaStreamWaitEvent(ctx->stream, t.ev_in, 0);
     int rc = plan_row_phase(ctx, d, t.rows, t.send, scratch, t.n_rows, t.row_start, t.is_inv, t.is_coset, ctx->W);
     ctx->pool.release(scratch);
     if (rc == DP_OK) t.row_phase_done = true;
     return rc;
+}
+
+// queue the column phase of a task whose recv matrix is complete; result lands in t.cols
+int queue_col_phase(dp_ctx *ctx, FftTask &t) {
+    const DomainDev &d = ctx->dom[t.is_quot ? 1 : 0];
+    if (!t.cols) {
+        t.cols = (Fr *)ctx->pool.alloc(t.n_cols * d.r() * sizeof(Fr));
+        if (!t.cols) return fail(ctx, DP_E_OOM, "column buffer");
+    }
+    DP_TRY(plan_col_phase(ctx, d, t.recv, t.cols, t.n_cols, t.col_start, t.is_inv, t.is_coset));
+    DP_CUDA(ctx, cudaEventRecord(t.ev_c, ctx->stream));
+    t.exchanged = true;
+    return DP_OK;
 }
 
 }  // namespace
@@ -654,6 +679,8 @@ int dp_create(int cuda_device, uint64_t me, uint64_t n_workers, dp_ctx **out) {
     do {
         if (cudaSetDevice(cuda_device) != cudaSuccess) { rc = DP_E_CUDA; break; }
         if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = DP_E_CUDA; break; }
+        if (cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking) != cudaSuccess) { rc = DP_E_CUDA; break; }
+        if (cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking) != cudaSuccess) { rc = DP_E_CUDA; break; }
         cudaEventCreate(&ctx->ev0);
         cudaEventCreate(&ctx->ev1);
         for (int k = 0; k < 4; k++) cudaEventCreate(&ctx->ev_msm[k]);
@@ -674,6 +701,7 @@ int dp_create(int cuda_device, uint64_t me, uint64_t n_workers, dp_ctx **out) {
     if (rc != DP_OK) {
         fail(nullptr, rc, "dp_create: CUDA initialisation failed on device %d", cuda_device);
         ctx->pool.destroy();
+        ctx->pool_io.destroy();
         delete ctx;
         return rc;
     }
@@ -684,8 +712,17 @@ int dp_create(int cuda_device, uint64_t me, uint64_t n_workers, dp_ctx **out) {
 int dp_destroy(dp_ctx *ctx) {
     if (!ctx) return DP_OK;
     cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->s_in);
     cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->s_out);
+    for (auto &kv : ctx->tasks) {
+        if (kv.second.ev_in) cudaEventDestroy(kv.second.ev_in);
+        if (kv.second.ev_c) cudaEventDestroy(kv.second.ev_c);
+    }
     ctx->pool.destroy();
+    ctx->pool_io.destroy();
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (int k = 0; k < 4; k++)
@@ -697,7 +734,9 @@ int dp_destroy(dp_ctx *ctx) {
 
 int dp_sync(dp_ctx *ctx) {
     if (!ctx) return DP_E_ARG;
+    DP_CUDA(ctx, cudaStreamSynchronize(ctx->s_in));
     DP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    DP_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
     return DP_OK;
 }
 
@@ -717,6 +756,9 @@ int dp_init(dp_ctx *ctx, const void *bases, size_t n_bases, uint64_t domain_size
     DP_CUDA(ctx, cudaSetDevice(ctx->device));
     call_begin(ctx);
     // drop previous state (init may be called again, worker.rs:135-141 overwrites)
+    cudaStreamSynchronize(ctx->s_in);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->s_out);
     for (auto &kv : ctx->tasks) free_task(ctx, kv.second);
     ctx->tasks.clear();
     ctx->pool.release(ctx->bases);
@@ -841,8 +883,13 @@ int dp_fft_init(dp_ctx *ctx, uint64_t id, const dp_fft_workload *workloads, size
     t.n_cols = mine.col_end - mine.col_start;
     t.row_start = mine.row_start;
     t.col_start = mine.col_start;
-    t.rows = (Fr *)ctx->pool.alloc(t.n_rows * c * sizeof(Fr));
+    t.rows = (Fr *)ctx->pool_io.alloc(t.n_rows * c * sizeof(Fr));
     if (!t.rows) return fail(ctx, DP_E_OOM, "dp_fft_init: rows buffer");
+    if (cudaEventCreateWithFlags(&t.ev_in, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&t.ev_c, cudaEventDisableTiming) != cudaSuccess) {
+        ctx->pool_io.release(t.rows);
+        return fail(ctx, DP_E_CUDA, "dp_fft_init: event creation");
+    }
     t.row_seen.assign(t.n_rows, 0);
     ctx->tasks.emplace(id, std::move(t));
     return DP_OK;
@@ -856,7 +903,8 @@ int dp_fft1_rows(dp_ctx *ctx, uint64_t id, uint64_t i_first, uint64_t n_rows, co
     if (i_first + n_rows > t->n_rows) return fail(ctx, DP_E_ARG, "dp_fft1: rows [%llu,%llu) of %llu", (unsigned long long)i_first, (unsigned long long)(i_first + n_rows), (unsigned long long)t->n_rows);
     DP_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint64_t c = ctx->dom[t->is_quot ? 1 : 0].c();
-    DP_CUDA(ctx, cudaMemcpyAsync(t->rows + i_first * c, rows, n_rows * c * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    DP_CUDA(ctx, cudaMemcpyAsync(t->rows + i_first * c, rows, n_rows * c * sizeof(Fr), cudaMemcpyHostToDevice, ctx->s_in));
+    DP_CUDA(ctx, cudaEventRecord(t->ev_in, ctx->s_in));
     for (uint64_t i = i_first; i < i_first + n_rows; i++)
         if (!t->row_seen[i]) {
             t->row_seen[i] = 1;
@@ -902,8 +950,8 @@ int dp_fft_exchange_end(dp_ctx *ctx, uint64_t id) {
     FftTask *t = find_task(ctx, id);
     if (!t) return fail(ctx, DP_E_ARG, "dp_fft_exchange_end: unknown task %llu", (unsigned long long)id);
     if (!t->row_phase_done || !t->recv) return fail(ctx, DP_E_STATE, "dp_fft_exchange_end before dp_fft_exchange_begin");
-    t->exchanged = true;
-    return DP_OK;
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    return queue_col_phase(ctx, *t);
 }
 
 int dp_fft2_prepare(dp_ctx *ctx, uint64_t id) {
@@ -916,34 +964,26 @@ int dp_fft2_prepare(dp_ctx *ctx, uint64_t id) {
     call_begin(ctx);
     DP_TRY(run_row_phase(ctx, *t));
     t->recv = t->send;
-    t->exchanged = true;
+    DP_TRY(queue_col_phase(ctx, *t));
     return call_end(ctx, false);
-}
-
-static int col_phase_to(dp_ctx *ctx, FftTask &t, Fr *cols_dev) {
-    const DomainDev &d = ctx->dom[t.is_quot ? 1 : 0];
-    return plan_col_phase(ctx, d, t.recv, cols_dev, t.n_cols, t.col_start, t.is_inv, t.is_coset);
 }
 
 int dp_fft2(dp_ctx *ctx, uint64_t id, void *out, size_t out_bytes) {
     if (!ctx || !out) return fail(ctx, DP_E_ARG, "dp_fft2: NULL argument");
     FftTask *t = find_task(ctx, id);
     if (!t) return fail(ctx, DP_E_ARG, "dp_fft2: unknown task %llu", (unsigned long long)id);
-    if (!t->exchanged) return fail(ctx, DP_E_STATE, "dp_fft2 before fft2_prepare / exchange");
+    if (!t->exchanged || !t->cols) return fail(ctx, DP_E_STATE, "dp_fft2 before fft2_prepare / exchange");
     DP_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint64_t r = ctx->dom[t->is_quot ? 1 : 0].r();
     const size_t bytes = t->n_cols * r * sizeof(Fr);
     if (out_bytes < bytes) return fail(ctx, DP_E_ARG, "dp_fft2: out buffer %zu < %zu bytes", out_bytes, bytes);
-    call_begin(ctx);
-    Fr *cols = (Fr *)ctx->pool.alloc(bytes);
-    if (!cols) return fail(ctx, DP_E_OOM, "dp_fft2: cols buffer");
-    int rc = col_phase_to(ctx, *t, cols);
-    if (rc == DP_OK) {
-        cudaError_t e = cudaMemcpyAsync(out, cols, bytes, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e != cudaSuccess) rc = fail(ctx, DP_E_CUDA, "dp_fft2 D2H: %s", cudaGetErrorString(e));
-    }
-    if (rc == DP_OK) rc = call_end(ctx, true);
-    ctx->pool.release(cols);
+    // the column phase was queued by fft2_prepare; only the copy-out happens here, on its own stream,
+    // so the next task's copy-in and compute keep running underneath
+    int rc = DP_OK;
+    cudaError_t e = cudaStreamWaitEvent(ctx->s_out, t->ev_c, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, t->cols, bytes, cudaMemcpyDeviceToHost, ctx->s_out);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_out);
+    if (e != cudaSuccess) rc = fail(ctx, DP_E_CUDA, "dp_fft2 D2H: %s", cudaGetErrorString(e));
     free_task(ctx, *t);  // worker.rs:378
     ctx->tasks.erase(id);
     return rc;

@@ -48,3 +48,19 @@ void emu_g1_add_xyzz_self(const void *aff96, void *out96) {  // P + P through th
     *(G1Affine *)out96 = a.add(a).to_affine();
 }
 }
+
+#include "../../distributed_plonk_b200/csrc/ufield.cuh"
+extern "C" {
+// unsaturated-limb fields: operands arrive as raw limb arrays (lazy forms allowed), result limbs out
+void emu_fru_mul(const uint32_t *a, const uint32_t *b, uint32_t *o) { *(FrU *)o = FrU::mul(*(const FrU *)a, *(const FrU *)b); }
+void emu_fqu_mul(const uint32_t *a, const uint32_t *b, uint32_t *o) { *(FqU *)o = FqU::mul(*(const FqU *)a, *(const FqU *)b); }
+void emu_fru_unpack(const uint32_t *w, uint32_t *o) { *(FrU *)o = FrU::unpack(w); }
+void emu_fru_pack(const uint32_t *l, uint32_t *w) { ((const FrU *)l)->pack(w); }
+void emu_fqu_unpack(const uint32_t *w, uint32_t *o) { *(FqU *)o = FqU::unpack(w); }
+void emu_fqu_pack(const uint32_t *l, uint32_t *w) { ((const FqU *)l)->pack(w); }
+void emu_fru_normalize(const uint32_t *l, uint32_t *o) { *(FrU *)o = ((const FrU *)l)->normalized(); }
+void emu_fru_canonical(const uint32_t *l, uint32_t *o) { *(FrU *)o = ((const FrU *)l)->canonical_from_2p(); }
+void emu_fqu_canonical(const uint32_t *l, uint32_t *o) { *(FqU *)o = ((const FqU *)l)->canonical_from_2p(); }
+int emu_fru_bias(uint32_t k_log2, uint32_t floor_log2, uint32_t *o) { return make_sub_bias<FrUParams>(k_log2, floor_log2, *(FrU *)o) ? 1 : 0; }
+int emu_fqu_bias(uint32_t k_log2, uint32_t floor_log2, uint32_t *o) { return make_sub_bias<FqUParams>(k_log2, floor_log2, *(FqU *)o) ? 1 : 0; }
+}

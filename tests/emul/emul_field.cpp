@@ -49,7 +49,7 @@ void emu_g1_add_xyzz_self(const void *aff96, void *out96) {  // P + P through th
 }
 }
 
-#include "../../distributed_plonk_b200/csrc/ufield.cuh"
+#include "../../tools/experiments/ufield.cuh"
 extern "C" {
 // unsaturated-limb fields: operands arrive as raw limb arrays (lazy forms allowed), result limbs out
 void emu_fru_mul(const uint32_t *a, const uint32_t *b, uint32_t *o) { *(FrU *)o = FrU::mul(*(const FrU *)a, *(const FrU *)b); }

@@ -1,3 +1,8 @@
+// EXPERIMENT (negative result, not part of the product): carry-free ("unsaturated limb") Montgomery
+// arithmetic.  Measured on B200 (profiles/r01_microbench_unsaturated.txt): Fr 39 G mul/s against
+// 58 G/s for the carry-chain form of field.cuh, Fq 18 against 30 - the extra partial products and
+// the 64-bit accumulator register traffic cost more than the half-rate carry forms save.
+//
 // Carry-free ("unsaturated limb") Montgomery arithmetic.
 //
 // Why: on B200 the carry forms of the integer multiply-add are half rate - measured
@@ -23,7 +28,7 @@
 // value(a) * value(b) < p * R'; then column sums stay below L*(2^32*B + B*B) < 2^64 and the
 // result is normalized with value < p * (value(a)*value(b)/(p*R') + 1) <= 2p.
 #pragma once
-#include "ptx_arith.cuh"
+#include "../../distributed_plonk_b200/csrc/ptx_arith.cuh"
 
 namespace dp {
 

@@ -2,7 +2,7 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 #include "../distributed_plonk_b200/csrc/field.cuh"
-#include "../distributed_plonk_b200/csrc/ufield.cuh"
+#include "experiments/ufield.cuh"
 using namespace dp;
 
 template <class F>

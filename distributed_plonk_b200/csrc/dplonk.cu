@@ -112,6 +112,8 @@ struct dp_ctx {
     uint4 *wf_lo = nullptr, *wf_hi = nullptr, *wi_lo = nullptr, *wi_hi = nullptr;
     G1Affine *bases = nullptr;
     uint64_t n_bases = 0;
+    G1Affine *pre_table = nullptr;  // [pre_nw][n_bases] window multiples 2^(c*w) * P_i (msm.cuh)
+    uint32_t pre_c = 0, pre_nw = 0;
     DomainDev dom[2];
     bool inited = false;
     std::map<uint64_t, FftTask> tasks;
@@ -122,7 +124,8 @@ struct dp_ctx {
     int dev_flags = -1;
     // pass-planning limits (dp_debug_set_limits lowers them so small tests reach the multi-pass plans)
     uint32_t max_contig_log_k = NTT_WTAB_LOG, max_strided_log_k = NTT_MAX_STRIDED_LOG_K;
-    int msm_force_c = 0;
+    int msm_force_c = 0;       // 0 auto, 1 = windowed path with automatic c, >= 2 forced c (windowed)
+    bool pre_disabled = false;
 };
 
 namespace {
@@ -535,7 +538,7 @@ void free_task(dp_ctx *ctx, FftTask &t) {
 }
 
 // ------------------------------------------------------------------ MSM driver (device pointers)
-int msm_device(dp_ctx *ctx, const G1Affine *bases, const uint4 *scalars_dev, uint64_t n, G1JacobianOut *out_dev,
+int msm_device(dp_ctx *ctx, uint64_t start, const uint4 *scalars_dev, uint64_t n, G1JacobianOut *out_dev,
                uint32_t *err_host_out) {
     if (n == 0) {
         const G1JacobianOut id = G1JacobianOut::from_affine(G1Affine::inf());
@@ -544,10 +547,14 @@ int msm_device(dp_ctx *ctx, const G1Affine *bases, const uint4 *scalars_dev, uin
         return DP_OK;
     }
     if (n >= ((uint64_t)1 << 31)) return fail(ctx, DP_E_ARG, "msm: %llu points exceed 2^31", (unsigned long long)n);
-    const MsmGeom g = msm_geometry(n, ctx->msm_force_c);
+    // precomputed window multiples pay off once the shared bucket set is reasonably filled
+    const bool use_pre = ctx->pre_table && ctx->msm_force_c == 0 && n * ctx->pre_nw >= 4ull * (1ull << (ctx->pre_c - 1));
+    const MsmGeom g = use_pre ? msm_make_geom(ctx->pre_c, true, ctx->n_bases)
+                              : msm_geometry(n, ctx->msm_force_c > 1 ? ctx->msm_force_c : 0);
+    const G1Affine *bases = (use_pre ? ctx->pre_table : ctx->bases) + start;
     const uint64_t max_digits = n * g.n_windows;
     const uint64_t max_tasks = (uint64_t)g.n_keys + max_digits / MSM_TSEG + 1;
-    const uint32_t n_segs = g.n_windows * g.segs_per_window;
+    const uint32_t n_segs = g.red_windows * g.segs_per_window;
     DevPool &P = ctx->pool;
     uint32_t *counts = (uint32_t *)P.alloc((g.n_keys + 1) * 4ull);
     uint32_t *offsets = (uint32_t *)P.alloc((g.n_keys + 1) * 4ull);
@@ -557,7 +564,7 @@ int msm_device(dp_ctx *ctx, const G1Affine *bases, const uint4 *scalars_dev, uin
     uint2 *tasks = (uint2 *)P.alloc(max_tasks * sizeof(uint2));
     G1XYZZ *partials = (G1XYZZ *)P.alloc(max_tasks * sizeof(G1XYZZ));
     G1XYZZ *seg_sums = (G1XYZZ *)P.alloc((uint64_t)n_segs * sizeof(G1XYZZ));
-    G1XYZZ *win_sums = (G1XYZZ *)P.alloc((uint64_t)g.n_windows * sizeof(G1XYZZ));
+    G1XYZZ *win_sums = (G1XYZZ *)P.alloc((uint64_t)g.red_windows * g.slices * sizeof(G1XYZZ));
     uint32_t *err = (uint32_t *)P.alloc(4);
     const uint32_t n_scan_blocks = (g.n_keys + SCAN_BLOCK - 1) / SCAN_BLOCK;
     uint2 *block_sums = (uint2 *)P.alloc((size_t)n_scan_blocks * sizeof(uint2));
@@ -593,7 +600,7 @@ int msm_device(dp_ctx *ctx, const G1Affine *bases, const uint4 *scalars_dev, uin
               task_off, partials);
     cudaEventRecord(ctx->ev_msm[2], st);
     DP_LAUNCH(msm_reduce_kernel, dim3(blocks_for(n_segs, MSM_TPB)), dim3(MSM_TPB), 0, st, partials, task_off, g, seg_sums);
-    DP_LAUNCH(msm_window_sum_kernel, dim3(g.n_windows), dim3(MSM_TPB), 0, st, seg_sums, g, win_sums);
+    DP_LAUNCH(msm_window_sum_kernel, dim3(g.red_windows * g.slices), dim3(MSM_TPB), 0, st, seg_sums, g, win_sums);
     DP_LAUNCH(msm_final_kernel, dim3(1), dim3(32), 0, st, win_sums, g, out_dev);
     cudaEventRecord(ctx->ev_msm[3], st);
     ctx->launches += 11;
@@ -762,7 +769,10 @@ int dp_init(dp_ctx *ctx, const void *bases, size_t n_bases, uint64_t domain_size
     for (auto &kv : ctx->tasks) free_task(ctx, kv.second);
     ctx->tasks.clear();
     ctx->pool.release(ctx->bases);
+    ctx->pool.release(ctx->pre_table);
     ctx->bases = nullptr;
+    ctx->pre_table = nullptr;
+    ctx->pre_c = ctx->pre_nw = 0;
     free_domain(ctx, ctx->dom[0]);
     free_domain(ctx, ctx->dom[1]);
     ctx->inited = false;
@@ -776,6 +786,24 @@ int dp_init(dp_ctx *ctx, const void *bases, size_t n_bases, uint64_t domain_size
                   (const uint64_t *)staging, ctx->bases, (uint64_t)n_bases);
         ctx->launches++;
         ctx->pool.release(staging);
+        // window multiples for the MSM (skipped for tiny SRS or when memory is short)
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const uint32_t c = n_bases >= (1u << 11) && !ctx->pre_disabled ? msm_pick_pre_c(n_bases, free_b / 4) : 0;
+        if (c) {
+            const uint32_t nw = (256 + c - 1) / c;
+            ctx->pre_table = (G1Affine *)ctx->pool.alloc((size_t)nw * n_bases * sizeof(G1Affine));
+            if (ctx->pre_table && nw <= (uint32_t)MSM_PRE_MAX_WINDOWS) {
+                ctx->pre_c = c;
+                ctx->pre_nw = nw;
+                DP_LAUNCH(msm_precompute_kernel, dim3(blocks_for(n_bases, 128)), dim3(128), 0, ctx->stream, ctx->bases,
+                          ctx->pre_table, (uint64_t)n_bases, (uint64_t)n_bases, c, nw);
+                ctx->launches++;
+            } else {
+                ctx->pool.release(ctx->pre_table);
+                ctx->pre_table = nullptr;
+            }
+        }
     }
     DP_TRY(build_domain(ctx, ctx->dom[0], domain_size));
     DP_TRY(build_domain(ctx, ctx->dom[1], quot_domain_size));
@@ -801,7 +829,7 @@ int dp_msm(dp_ctx *ctx, uint64_t start, uint64_t end, const void *scalars, size_
     G1JacobianOut *od = (G1JacobianOut *)ctx->pool.alloc(sizeof(G1JacobianOut));
     if (!sc || !od) return fail(ctx, DP_E_OOM, "dp_msm buffers");
     if (n) DP_CUDA(ctx, cudaMemcpyAsync(sc, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-    int rc = msm_device(ctx, ctx->bases + start, sc, n, od, nullptr);
+    int rc = msm_device(ctx, start, sc, n, od, nullptr);
     if (rc == DP_OK) {
         cudaError_t e = cudaMemcpyAsync(out, od, sizeof(G1JacobianOut), cudaMemcpyDeviceToHost, ctx->stream);
         if (e != cudaSuccess) rc = fail(ctx, DP_E_CUDA, "dp_msm D2H: %s", cudaGetErrorString(e));
@@ -819,7 +847,7 @@ int dp_msm_dev(dp_ctx *ctx, uint64_t start, uint64_t end, const void *scalars_de
     DP_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint64_t n = (end - start) < n_scalars ? (end - start) : n_scalars;
     call_begin(ctx);
-    DP_TRY(msm_device(ctx, ctx->bases + start, (const uint4 *)scalars_dev, n, (G1JacobianOut *)out_dev, nullptr));
+    DP_TRY(msm_device(ctx, start, (const uint4 *)scalars_dev, n, (G1JacobianOut *)out_dev, nullptr));
     return call_end(ctx, true);
 }
 
@@ -833,7 +861,7 @@ static int commit_device(dp_ctx *ctx, const Fr *coeffs_dev, uint64_t n, G1Jacobi
         DP_LAUNCH(fr_into_repr_kernel, dim3(blocks_for(nb, 256)), dim3(256), 0, ctx->stream, coeffs_dev, sc, n, nb);
         ctx->launches++;
     }
-    int rc = msm_device(ctx, ctx->bases, (const uint4 *)sc, nb, out_dev, nullptr);
+    int rc = msm_device(ctx, 0, (const uint4 *)sc, nb, out_dev, nullptr);
     ctx->pool.release(sc);
     return rc;
 }
@@ -1205,7 +1233,7 @@ int dp_debug_gen_bases(dp_ctx *ctx, uint64_t seed, size_t n, void *out) {
 int dp_debug_set_limits(dp_ctx *ctx, uint32_t max_contig_log_k, uint32_t max_strided_log_k, int msm_window_bits) {
     if (!ctx) return DP_E_ARG;
     if (max_contig_log_k < 1 || max_contig_log_k > NTT_WTAB_LOG || max_strided_log_k < 1 || max_strided_log_k > NTT_MAX_STRIDED_LOG_K ||
-        msm_window_bits < 0 || msm_window_bits > 20 || msm_window_bits == 1)
+        msm_window_bits < 0 || msm_window_bits > 20)
         return fail(ctx, DP_E_ARG, "dp_debug_set_limits: out of range");
     ctx->max_contig_log_k = max_contig_log_k;
     ctx->max_strided_log_k = max_strided_log_k;

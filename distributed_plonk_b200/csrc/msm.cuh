@@ -21,6 +21,8 @@
 //                     sum_k k*B_k (+ small scalar multiple for the segment offset)
 //   7. msm_window_sum block per window: tree reduction of the segment sums
 //   8. msm_final      Horner over windows (c doublings each), normalise, emit 144-byte Jacobian
+// With the precomputed table of window multiples (built at dp_init, msm_precompute_kernel) steps
+// 1-7 run over ONE shared bucket set and step 8 has nothing to combine.
 //
 // Work: N*ceil(256/c) mixed additions (10 Fq mul) dominate; HBM traffic is ~96 B gathered per
 // addition plus 32 B per scalar per pass - the kernel set is bound by the INT32 multiply pipe,
@@ -35,37 +37,73 @@ constexpr uint32_t MSM_TSEG = 256;      // max points per accumulate task
 constexpr uint32_t MSM_SEG = 32;        // buckets per reduce segment
 constexpr int MSM_TPB = 128;
 
+constexpr uint32_t MSM_SLICES = 32;     // partial sums per window in the two-level window sum
+
 struct MsmGeom {
-    uint32_t c;          // window bits
-    uint32_t n_windows;  // ceil(256 / c)
-    uint32_t bpw;        // buckets per window = 2^(c-1)
-    uint32_t n_keys;     // n_windows * bpw
-    uint32_t seg;        // buckets per reduce segment
+    uint32_t c;            // window bits
+    uint32_t n_windows;    // digit windows = ceil(256 / c)
+    uint32_t bpw;          // buckets per window = 2^(c-1)
+    uint32_t n_keys;       // bucket sets * bpw
+    uint32_t seg;          // buckets per reduce segment
     uint32_t segs_per_window;
+    uint32_t red_windows;  // bucket sets to reduce: n_windows, or 1 with precomputed window multiples
+    uint32_t pre;          // 1: bases come from the table T[w][i] = 2^(c*w) * P_i, one shared bucket set
+    uint32_t stride;       // table row length (points)
+    uint32_t slices;       // partial sums per bucket set in the two-level window sum (<= 32)
 };
 
+// cost in Fq multiplications of an n-point MSM with window c
+inline double msm_cost(uint64_t n, uint32_t c, bool pre) {
+    const double w = (double)((256 + c - 1) / c), buckets = (double)(1u << (c - 1)) * (pre ? 1.0 : w);
+    // n*W mixed adds (10) + 2 full adds (14) per bucket, the latter at much lower parallelism (x2);
+    // without precomputation also 256 serial doublings at single-thread speed (~ x400)
+    return (double)n * w * 10.0 + 2.0 * 2.0 * buckets * 14.0 + (pre ? 0.0 : 256.0 * 9.0 * 400.0);
+}
+
+inline MsmGeom msm_make_geom(uint32_t c, bool pre, uint64_t stride) {
+    MsmGeom g;
+    g.c = c;
+    g.n_windows = (256 + c - 1) / c;
+    g.bpw = 1u << (c - 1);
+    g.pre = pre ? 1 : 0;
+    g.stride = (uint32_t)stride;
+    g.red_windows = pre ? 1 : g.n_windows;
+    g.n_keys = g.red_windows * g.bpw;
+    g.seg = g.bpw < MSM_SEG ? g.bpw : MSM_SEG;
+    g.segs_per_window = g.bpw / g.seg;
+    g.slices = g.segs_per_window / 64;  // >= 64 segment sums per slice block
+    if (g.slices < 1) g.slices = 1;
+    if (g.slices > MSM_SLICES) g.slices = MSM_SLICES;
+    return g;
+}
+
 inline MsmGeom msm_geometry(uint64_t n, int force_c = 0) {
-    // cost model in Fq multiplications: n*W mixed adds (10) + 2*W*2^(c-1) full adds (14)
-    // + Horner/normalise tail; pick the cheapest c in [4, 18]
     uint32_t best_c = 4;
     double best = 1e300;
     for (uint32_t c = 4; c <= 18; c++) {
-        double w = (double)((256 + c - 1) / c);
-        // (the reduce phase runs with far fewer threads than the accumulate phase: weight it x2)
-        double cost = (double)n * w * 10.0 + 2.0 * 2.0 * w * (double)(1u << (c - 1)) * 14.0;
+        const double cost = msm_cost(n, c, false);
         if (cost < best) {
             best = cost;
             best_c = c;
         }
     }
-    MsmGeom g;
-    g.c = force_c ? (uint32_t)force_c : best_c;
-    g.n_windows = (256 + g.c - 1) / g.c;
-    g.bpw = 1u << (g.c - 1);
-    g.n_keys = g.n_windows * g.bpw;
-    g.seg = g.bpw < MSM_SEG ? g.bpw : MSM_SEG;
-    g.segs_per_window = g.bpw / g.seg;
-    return g;
+    return msm_make_geom(force_c ? (uint32_t)force_c : best_c, false, 0);
+}
+
+// window width for the precomputed table of an n-base context, limited by the table size
+inline uint32_t msm_pick_pre_c(uint64_t n_bases, uint64_t max_table_bytes) {
+    uint32_t best_c = 0;
+    double best = 1e300;
+    for (uint32_t c = 8; c <= 22; c++) {
+        const uint64_t w = (256 + c - 1) / c;
+        if (w * n_bases * 96ull > max_table_bytes || w * n_bases >= (1ull << 31)) continue;
+        const double cost = msm_cost(n_bases, c, true);
+        if (cost < best) {
+            best = cost;
+            best_c = c;
+        }
+    }
+    return best_c;
 }
 
 // ------------------------------------------------------------------ bases import (init time)
@@ -153,12 +191,13 @@ DP_D uint32_t for_each_digit(const Scalar256 &s, const MsmGeom &g, F f) {
     for (uint32_t w = 0; w < g.n_windows; w++) {
         uint32_t raw = scalar_bits(s, w * g.c, g.c) + carry;
         carry = 0;
+        const uint32_t set = g.pre ? 0u : w * g.bpw;
         if (raw > g.bpw) {  // digit = raw - 2^c  (negative)
             const uint32_t mag = (1u << g.c) - raw;
             carry = 1;
-            if (mag) f(w, w * g.bpw + (mag - 1), 1u);
+            if (mag) f(w, set + (mag - 1), 1u);
         } else if (raw) {
-            f(w, w * g.bpw + (raw - 1), 0u);
+            f(w, set + (raw - 1), 0u);
         }
     }
     return carry;
@@ -176,9 +215,9 @@ __global__ void msm_scatter_kernel(const uint4 *scalars, uint64_t n, MsmGeom g, 
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const Scalar256 s = load_scalar(scalars, i);
-    for_each_digit(s, g, [&](uint32_t, uint32_t key, uint32_t neg) {
+    for_each_digit(s, g, [&](uint32_t w, uint32_t key, uint32_t neg) {
         const uint32_t pos = atomicAdd(&cursor[key], 1u);
-        sorted[pos] = (uint32_t)i | (neg << 31);
+        sorted[pos] = ((uint32_t)i + (g.pre ? w * g.stride : 0u)) | (neg << 31);
     });
 }
 
@@ -332,6 +371,9 @@ __global__ void __launch_bounds__(MSM_TPB) msm_accumulate_kernel(const uint2 *ta
 // are folded by ONE WARP each: lanes stride over the bucket's partial sums, then a warp-shuffle
 // butterfly adds the 32 lane sums; the result replaces the bucket's first partial.
 DP_D G1XYZZ shfl_xor_point(const G1XYZZ &p, int mask) {
+#if defined(DP_EMUL)
+    return dp_emul_shfl_struct(p, dp_emul::t_lane ^ (unsigned)mask);
+#endif
     G1XYZZ r;
 #pragma unroll
     for (int i = 0; i < 12; i++) {
@@ -374,7 +416,7 @@ DP_D G1XYZZ small_mul(const G1XYZZ &p, uint32_t k) {
 __global__ void __launch_bounds__(MSM_TPB) msm_reduce_kernel(const G1XYZZ *partials, const uint32_t *task_off, MsmGeom g,
                                                               G1XYZZ *seg_sums) {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= g.n_windows * g.segs_per_window) return;
+    if (idx >= g.red_windows * g.segs_per_window) return;
     const uint32_t w = idx / g.segs_per_window, sgm = idx % g.segs_per_window;
     const uint32_t lo = sgm * g.seg;  // buckets lo+1 .. lo+seg of this window (bucket k <-> digit k)
     G1XYZZ running = G1XYZZ::inf(), acc = G1XYZZ::inf();
@@ -386,30 +428,73 @@ __global__ void __launch_bounds__(MSM_TPB) msm_reduce_kernel(const G1XYZZ *parti
     seg_sums[idx] = acc;
 }
 
-// block per window: sum of the segment sums
-__global__ void __launch_bounds__(MSM_TPB) msm_window_sum_kernel(const G1XYZZ *seg_sums, MsmGeom g, G1XYZZ *win_sums) {
+// two-level sum of the segment sums: block (w, slice) folds its share into slice_sums[w*SLICES+slice]
+__global__ void __launch_bounds__(MSM_TPB) msm_window_sum_kernel(const G1XYZZ *seg_sums, MsmGeom g, G1XYZZ *slice_sums) {
     __shared__ G1XYZZ red[MSM_TPB];
-    const uint32_t w = blockIdx.x, tid = threadIdx.x;
+    const uint32_t w = blockIdx.x / g.slices, slice = blockIdx.x % g.slices, tid = threadIdx.x;
+    const uint32_t per = (g.segs_per_window + g.slices - 1) / g.slices;
+    const uint32_t lo = slice * per, hi = lo + per < g.segs_per_window ? lo + per : g.segs_per_window;
     G1XYZZ acc = G1XYZZ::inf();
-    for (uint32_t s = tid; s < g.segs_per_window; s += MSM_TPB) acc = acc.add(seg_sums[w * g.segs_per_window + s]);
+    for (uint32_t s = lo + tid; s < hi; s += MSM_TPB) acc = acc.add(seg_sums[w * g.segs_per_window + s]);
     red[tid] = acc;
     __syncthreads();
     for (uint32_t off = MSM_TPB / 2; off >= 1; off >>= 1) {
         if (tid < off) red[tid] = red[tid].add(red[tid + off]);
         __syncthreads();
     }
-    if (tid == 0) win_sums[w] = red[0];
+    if (tid == 0) slice_sums[blockIdx.x] = red[0];
 }
 
-// Horner over the windows, optional extra term, normalise, write the raw 144-byte GroupProjective
-__global__ void msm_final_kernel(const G1XYZZ *win_sums, MsmGeom g, G1JacobianOut *out) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    G1XYZZ total = win_sums[g.n_windows - 1];
-    for (int w = (int)g.n_windows - 2; w >= 0; w--) {
-        for (uint32_t k = 0; k < g.c; k++) total = total.dbl();
-        total = total.add(win_sums[w]);
+// one warp: per bucket set fold the SLICES partial sums (warp-shuffle butterfly), Horner over the
+// windows when the bases were not premultiplied, normalise, write the raw 144-byte GroupProjective
+__global__ void msm_final_kernel(const G1XYZZ *slice_sums, MsmGeom g, G1JacobianOut *out) {
+    const uint32_t lane = threadIdx.x & 31;
+    G1XYZZ total = G1XYZZ::inf();
+    for (int w = (int)g.red_windows - 1; w >= 0; w--) {
+        G1XYZZ part = lane < g.slices ? slice_sums[w * g.slices + lane] : G1XYZZ::inf();
+        for (int m = 16; m >= 1; m >>= 1) part = part.add(shfl_xor_point(part, m));
+        if (w != (int)g.red_windows - 1)
+            for (uint32_t k = 0; k < g.c; k++) total = total.dbl();
+        total = total.add(part);
     }
-    *out = G1JacobianOut::from_affine(total.to_affine());
+    if (lane == 0) *out = G1JacobianOut::from_affine(total.to_affine());
+}
+
+// ------------------------------------------------------------------ precomputed window multiples
+// table[w * stride + i] = 2^(c*w) * P_i  (affine), w < n_windows.  With it every digit of every
+// window lands in ONE shared set of 2^(c-1) buckets: no per-window bucket sets, no Horner pass
+// (256 serial doublings), and a wider window for the same bucket count.  Built once per SRS.
+constexpr int MSM_PRE_MAX_WINDOWS = 32;
+__global__ void __launch_bounds__(128) msm_precompute_kernel(const G1Affine *bases, G1Affine *table, uint64_t n,
+                                                              uint64_t stride, uint32_t c, uint32_t n_windows) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const G1Affine b = load_affine(bases + i);
+    table[i] = b;
+    if (b.is_inf()) {
+        for (uint32_t w = 1; w < n_windows; w++) table[w * stride + i] = G1Affine::inf();
+        return;
+    }
+    // doublings never reach infinity (prime-order subgroup); normalise all rows with one inversion
+    G1XYZZ pts[MSM_PRE_MAX_WINDOWS];
+    Fq prefix[MSM_PRE_MAX_WINDOWS];
+    G1XYZZ p = G1XYZZ::from_affine(b);
+    Fq run = Fq::one();
+    for (uint32_t w = 1; w < n_windows; w++) {
+        for (uint32_t k = 0; k < c; k++) p = p.dbl();
+        pts[w] = p;
+        prefix[w] = run;  // product of t_1 .. t_{w-1}
+        run = run * (p.zz * p.zzz);
+    }
+    Fq inv = run.inverse();
+    for (uint32_t w = n_windows - 1; w >= 1; w--) {
+        const Fq t_inv = inv * prefix[w];  // (zz*zzz)^-1 of row w
+        inv = inv * (pts[w].zz * pts[w].zzz);
+        G1Affine a;
+        a.x = pts[w].x * (t_inv * pts[w].zzz);
+        a.y = pts[w].y * (t_inv * pts[w].zz);
+        table[w * stride + i] = a;
+    }
 }
 
 }  // namespace dp

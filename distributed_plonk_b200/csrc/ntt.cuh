@@ -202,7 +202,9 @@ __global__ void __launch_bounds__(NTT_TPB, 2) ntt_tile_kernel(NttPass p) {
                 m = idx >> p.log_g;
             }
             Fr v = gmem_ld(src + (uint64_t)g * p.in_ls + (uint64_t)m * p.in_ps);
-            if (p.pre_a) {
+            // zero inputs stay zero: the quotient-domain transforms are fed n coefficients padded
+            // to 8n (dispatcher2.rs:386-388), so 7/8 of the loads skip both products (whole warps)
+            if (p.pre_a && !v.is_zero()) {
                 const uint64_t lane = lane0 + g;
                 v = v * gmem_ld(p.pre_a + p.pa_o * o + p.pa_l * lane);
                 v = v * gmem_ld(p.pre_b + p.pb_m * m + p.pb_l * lane);

@@ -146,8 +146,9 @@ int dp_last_msm_breakdown(const dp_ctx *ctx, float *sort_ms, float *accumulate_m
 int dp_debug_gen_bases(dp_ctx *ctx, uint64_t seed, size_t n, void *out);
 
 /* test hook: lower the pass-planning limits (sub-transform sizes 2^k handled by one kernel pass;
- * defaults 11 / 9) and/or force the MSM window width (0 = automatic) so that small inputs
- * exercise the multi-pass NTT plans and every MSM geometry. */
+ * defaults 11 / 9) and/or steer the MSM (0 = automatic: precomputed window multiples when the SRS is
+ * large enough; 1 = per-window bucket sets with automatic width; c >= 2 = per-window sets of width c)
+ * so that small inputs exercise the multi-pass NTT plans and every MSM geometry. */
 int dp_debug_set_limits(dp_ctx *ctx, uint32_t max_contig_log_k, uint32_t max_strided_log_k, int msm_window_bits);
 
 /* device-resident variants used by bench.py to time the kernels with inputs already in HBM.

@@ -39,6 +39,7 @@ inline thread_local unsigned char *t_dyn_smem = nullptr;
 struct WarpXchg {
     std::barrier<> bar;
     uint64_t slot[32];
+    unsigned char blob[32][256];  // whole-struct exchange (one barrier pair per struct, not per word)
     explicit WarpXchg(int n) : bar(n) {}
 };
 inline thread_local WarpXchg *t_warp = nullptr;
@@ -109,6 +110,18 @@ inline T dp_emul_shfl(T v, unsigned src_lane) {
     w->bar.arrive_and_wait();
     T out;
     memcpy(&out, &got, sizeof(T));
+    return out;
+}
+// struct-granular shuffle used by kernels under DP_EMUL to keep barrier counts (thread switches) low
+template <class T>
+inline T dp_emul_shfl_struct(const T &v, unsigned src_lane) {
+    static_assert(sizeof(T) <= 256, "shuffle blob");
+    auto *w = dp_emul::t_warp;
+    memcpy(w->blob[dp_emul::t_lane], &v, sizeof(T));
+    w->bar.arrive_and_wait();
+    T out;
+    memcpy(&out, w->blob[src_lane & 31], sizeof(T));
+    w->bar.arrive_and_wait();
     return out;
 }
 template <class T> inline T __shfl_sync(unsigned, T v, int src) { return dp_emul_shfl(v, (unsigned)src); }

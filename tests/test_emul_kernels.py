@@ -63,6 +63,22 @@ def test_msm_distributions_and_geometries(orc, ctx):
     ctx.debug_set_limits(11, 9, 0)
 
 
+def test_msm_precomputed_window_multiples(orc, emul_lib):
+    """SRS of >= 2^11 bases: dp_init builds the table 2^(c*w) * P_i and the MSM runs over one shared
+    bucket set; small sub-ranges and the forced modes still take the per-window path."""
+    n = 2048
+    bases = orc.gen_bases(11, n, 64, True)
+    c = Context(emul_lib, 0, 0, 1)
+    c.init(bases, 1 << 4, 1 << 7)
+    common.check_msm(orc, c, bases, n, 61, which=("uniform", "witness-like", "all one"))
+    sc = orc.gen_fr(62, n, False)
+    common.assert_point_eq(orc, c.msm(500, 1700, sc[:1200]), orc.msm(bases[500:1700], sc[:1200]), "pre sub-range")
+    common.assert_point_eq(orc, c.msm(7, 57, sc[:50]), orc.msm(bases[7:57], sc[:50]), "small range -> windowed")
+    c.debug_set_limits(11, 9, 1)
+    common.assert_point_eq(orc, c.msm(0, n, sc), orc.msm(bases, sc), "forced windowed")
+    c.close()
+
+
 def test_msm_edges(orc, ctx):
     bases = orc.gen_bases(5, 600, 64, True)
     sc = orc.gen_fr(9, 600, False)

@@ -107,6 +107,18 @@ def test_msm_vs_oracle(orc, ctx, bases, n):
     common.check_msm(orc, ctx, bases, n, 300 + (n % 97))
 
 
+def test_msm_windowed_path_vs_precomputed(orc, ctx, bases):
+    """the default path uses the precomputed window multiples (SRS of 2^16+32 bases); mode 1 forces
+    the per-window bucket sets: both must give the oracle's point"""
+    n = (1 << 16) + 32
+    ctx.debug_set_limits(11, 9, 1)
+    try:
+        common.check_msm(orc, ctx, bases, n, 777, which=("uniform", "witness-like"))
+    finally:
+        ctx.debug_set_limits(11, 9, 0)
+    common.check_msm(orc, ctx, bases, n, 777, which=("uniform", "witness-like"))
+
+
 @pytest.mark.parametrize("c", [4, 5, 9, 12, 15, 16, 17, 18])
 def test_msm_every_window_geometry(orc, ctx, bases, c):
     ctx.debug_set_limits(11, 9, c)

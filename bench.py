@@ -197,6 +197,8 @@ def main():
     ap.add_argument("--log-n", type=int, default=22, dest="log_n")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: row kernel stores into peer memory over NVLink (fused) or one NCCL all-to-all")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -265,10 +267,24 @@ def main():
     out_m = torch.empty((cols_m * r_m, 4), dtype=torch.int64, device="cuda")
     msm_out = torch.zeros(18, dtype=torch.int64, device="cuda")
     exchange = parallel.make_exchange() if W > 1 else None
+    fused = False
+    if W > 1 and args.exchange == "fused":
+        try:
+            fused = parallel.attach_peers(ctx, 2 * (m // W) * 32)
+        except dp.DpError as e:                       # e.g. no P2P path between the devices
+            if rank == 0:
+                print(f"fused exchange unavailable ({e}); using the NCCL all-to-all", file=sys.stderr)
+        flag = torch.tensor([1 if fused else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        fused = bool(flag.item())
 
     def fft_resident(src, dst, is_quot, is_inv, is_coset):
         if W == 1:
             ctx.fft_dev(src.data_ptr(), dst.data_ptr(), is_quot, is_inv, is_coset)
+        elif fused:
+            ctx.fft_dev_rows_p2p(src.data_ptr(), is_quot, is_inv, is_coset)
+            dist.barrier()                            # every rank's stores into my arena are complete
+            ctx.fft_dev_cols(dst.data_ptr())
         else:
             s, r, blk = ctx.fft_dev_rows(src.data_ptr(), is_quot, is_inv, is_coset)
             exchange(s, r, blk)
@@ -348,6 +364,9 @@ def main():
             ctx._ck(lib.dp_fft1_rows(ctx.h, tid[0], 0, n_rows, h_in.data_ptr()))
             if W == 1:
                 ctx.fft2_prepare(tid[0])
+            elif fused:
+                ctx.fft2_prepare(tid[0])
+                dist.barrier()
             else:
                 s, r, blk = ctx.fft_exchange_begin(tid[0])
                 exchange(s, r, blk)
@@ -417,7 +436,8 @@ def main():
         "metric": "proofs_per_sec", "value": value, "unit": "proofs/s", "n_gpus": W, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u32 limbs (255/381-bit modular integer)", "data": "synthetic",
-        "config": workload_config(log_n, W), "gpu_launches": int(launches), "clocks": clocks,
+        "config": dict(workload_config(log_n, W), exchange=("none" if W == 1 else "fused peer-memory stores" if fused else "nccl all_to_all_single")),
+        "gpu_launches": int(launches), "clocks": clocks,
         "msm_g1_adds_per_sec": (adds / N_MSM) / (statistics.mean(stats["msm_ms"]) * 1e-3) if stats["msm_ms"] else None,
         "ntt_butterflies_per_sec": butterflies(log_m) / (statistics.mean(stats["ntt_m_ms"]) * 1e-3) if stats["ntt_m_ms"] else None,
         "breakdown_ms": {"msm_total": msm_total, "msm_accumulate": acc_total, "intt_n_total": sum(stats["ntt_n_ms"]),

@@ -13,7 +13,7 @@ EXPORTS = [
     "dp_fft1", "dp_fft1_rows", "dp_fft2_prepare", "dp_fft_exchange_begin", "dp_fft_exchange_end", "dp_fft2",
     "dp_ntt", "dp_round1", "dp_get_wire", "dp_peer_arena_create", "dp_peer_attach", "dp_last_timing",
     "dp_launch_count", "dp_sync", "dp_msm_dev", "dp_ntt_dev", "dp_fft_dev", "dp_debug_set_limits",
-    "dp_last_msm_breakdown", "dp_debug_gen_bases", "dp_fft_dev_rows", "dp_fft_dev_cols",
+    "dp_last_msm_breakdown", "dp_debug_gen_bases", "dp_fft_dev_rows", "dp_fft_dev_cols", "dp_peer_ready", "dp_fft_dev_rows_p2p",
 ]
 
 
@@ -61,6 +61,8 @@ def bind(cdll: C.CDLL) -> C.CDLL:
         "dp_debug_gen_bases": (i, [vp, u64, sz, vp]),
         "dp_fft_dev_rows": (i, [vp, vp, i, i, i, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]),
         "dp_fft_dev_cols": (i, [vp, vp]),
+        "dp_peer_ready": (i, [vp]),
+        "dp_fft_dev_rows_p2p": (i, [vp, vp, i, i, i]),
     }
     assert set(sig) == set(EXPORTS)
     for name, (res, args) in sig.items():
@@ -191,6 +193,20 @@ class Context:
         self._ck(self.lib.dp_fft_dev_rows(self.h, rows_ptr, int(is_quot), int(is_inv), int(is_coset),
                                           C.byref(s), C.byref(r), C.byref(n)))
         return s.value, r.value, n.value
+
+    def peer_arena_create(self, arena_bytes: int) -> bytes:
+        h = C.create_string_buffer(64)
+        self._ck(self.lib.dp_peer_arena_create(self.h, arena_bytes, h))
+        return h.raw
+
+    def peer_attach(self, peer: int, handle: bytes):
+        self._ck(self.lib.dp_peer_attach(self.h, peer, C.create_string_buffer(handle, 64)))
+
+    def peer_ready(self) -> bool:
+        return bool(self.lib.dp_peer_ready(self.h))
+
+    def fft_dev_rows_p2p(self, rows_ptr: int, is_quot: bool, is_inv: bool, is_coset: bool):
+        self._ck(self.lib.dp_fft_dev_rows_p2p(self.h, rows_ptr, int(is_quot), int(is_inv), int(is_coset)))
 
     def fft_dev_cols(self, cols_ptr: int):
         self._ck(self.lib.dp_fft_dev_cols(self.h, cols_ptr))

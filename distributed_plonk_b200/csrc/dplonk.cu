@@ -89,6 +89,7 @@ struct FftTask {
     uint64_t rows_filled = 0;
     std::vector<uint8_t> row_seen;
     bool row_phase_done = false, exchanged = false;
+    bool p2p = false;  // rows were stored straight into the peers' arenas; column phase waits for fft2
     cudaEvent_t ev_in = nullptr;  // last fft1 H2D copy (copy-in stream)
     cudaEvent_t ev_c = nullptr;   // column phase finished (compute stream)
 };
@@ -120,7 +121,13 @@ struct dp_ctx {
     Fr *wire = nullptr;
     uint64_t wire_len = 0;
     uint64_t rng_state = 0x9E3779B97F4A7C15ull;
+    // fused peer-memory exchange (dp_peer_arena_create / dp_peer_attach)
+    Fr *arena = nullptr;            // my receive arena: two slots, alternating per exchange
+    uint64_t arena_bytes = 0;
+    Fr *peer_arena[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint64_t p2p_seq = 0;           // exchanges issued so far; must advance identically on every rank
     Fr *dev_send = nullptr, *dev_recv = nullptr;  // dp_fft_dev_rows / _cols staging (one transform in flight)
+    Fr *dev_p2p_slot = nullptr;                   // receive slot of the last dp_fft_dev_rows_p2p
     int dev_flags = -1;
     // pass-planning limits (dp_debug_set_limits lowers them so small tests reach the multi-pass plans)
     uint32_t max_contig_log_k = NTT_WTAB_LOG, max_strided_log_k = NTT_MAX_STRIDED_LOG_K;
@@ -212,8 +219,13 @@ int launch_pass(dp_ctx *ctx, NttPass &p, uint64_t n_lanes) {
 // Row phase of the 2-D transform (fft1_helper, worker.rs:66-94) over all local rows:
 //   src  [n_rows][c] row-major;  dst = exchange layout: W blocks of [n_rows][c/W]
 // scratch ([n_rows][c]) is used when c > 2^11 (row split into two passes).
+struct PeerDst {
+    Fr *base[8];
+    uint64_t row_off;
+};
+
 int plan_row_phase(dp_ctx *ctx, const DomainDev &d, const Fr *src, Fr *dst, Fr *scratch, uint64_t n_rows,
-                   uint64_t row_start, bool is_inv, bool is_coset, uint64_t W) {
+                   uint64_t row_start, bool is_inv, bool is_coset, uint64_t W, const PeerDst *peers = nullptr) {
     const uint32_t lc = d.log_c;
     const uint64_t c = d.c();
     const uint32_t log_ncq = lc - log2_ceil_u64(W);
@@ -225,6 +237,11 @@ int plan_row_phase(dp_ctx *ctx, const DomainDev &d, const Fr *src, Fr *dst, Fr *
             p.split_on = 1;
             p.split_log = log_ncq;
             p.split_stride = n_rows << log_ncq;
+            if (peers) {
+                p.peer_on = 1;
+                p.peer_row_off = peers->row_off;
+                for (uint64_t q = 0; q < W; q++) p.peer_base[q] = peers->base[q];
+            }
         }
         if (is_inv) {
             p.post_const_on = 1;
@@ -527,7 +544,7 @@ void free_domain(dp_ctx *ctx, DomainDev &d) {
 
 // only called when every stream is done with the task (after the D2H of dp_fft2, or at dp_init)
 void free_task(dp_ctx *ctx, FftTask &t) {
-    if (t.recv && t.recv != t.send) ctx->pool.release(t.recv);
+    if (t.recv && t.recv != t.send && !t.p2p) ctx->pool.release(t.recv);
     if (t.send && t.send != t.rows) ctx->pool.release(t.send);
     ctx->pool.release(t.cols);
     ctx->pool_io.release(t.rows);
@@ -621,7 +638,25 @@ FftTask *find_task(dp_ctx *ctx, uint64_t id) {
     return it == ctx->tasks.end() ? nullptr : &it->second;
 }
 
-int run_row_phase(dp_ctx *ctx, FftTask &t) {
+bool p2p_ready(const dp_ctx *ctx) {
+    if (ctx->W <= 1 || !ctx->arena) return false;
+    for (uint64_t q = 0; q < ctx->W; q++)
+        if (!ctx->peer_arena[q]) return false;
+    return true;
+}
+
+// receive slot of the next exchange in every rank's arena (same sequence number on all ranks)
+int p2p_next_slot(dp_ctx *ctx, uint64_t recv_bytes, PeerDst &dst, Fr *&my_slot, uint64_t row_off) {
+    const uint64_t slot_bytes = ctx->arena_bytes / 2;
+    if (recv_bytes > slot_bytes) return fail(ctx, DP_E_COMM, "peer arena slot %llu B < receive matrix %llu B", (unsigned long long)slot_bytes, (unsigned long long)recv_bytes);
+    const uint64_t off = (ctx->p2p_seq++ & 1) * (slot_bytes / sizeof(Fr));
+    for (uint64_t q = 0; q < ctx->W; q++) dst.base[q] = ctx->peer_arena[q] + off;
+    dst.row_off = row_off;
+    my_slot = ctx->arena + off;
+    return DP_OK;
+}
+
+int run_row_phase(dp_ctx *ctx, FftTask &t, bool use_p2p = false) {
     if (t.row_phase_done) return DP_OK;
     if (t.rows_filled != t.n_rows) return fail(ctx, DP_E_STATE, "fft task: %llu of %llu rows received", (unsigned long long)t.rows_filled, (unsigned long long)t.n_rows);
     const DomainDev &d = ctx->dom[t.is_quot ? 1 : 0];
@@ -631,14 +666,26 @@ int run_row_phase(dp_ctx *ctx, FftTask &t) {
         scratch = (Fr *)ctx->pool.alloc(t.n_rows * c * sizeof(Fr));
         if (!scratch) return fail(ctx, DP_E_OOM, "row-phase scratch");
     }
-    if (ctx->W > 1 && !t.send) {
+    PeerDst peers;
+    if (use_p2p) {
+        // block q of my rows goes straight to rows [me*n_rows, ...) of worker q's receive matrix
+        Fr *slot = nullptr;
+        int rc0 = p2p_next_slot(ctx, d.r() * t.n_cols * sizeof(Fr), peers, slot, ctx->me * t.n_rows * t.n_cols);
+        if (rc0 != DP_OK) {
+            ctx->pool.release(scratch);
+            return rc0;
+        }
+        t.recv = slot;
+        t.p2p = true;
+    } else if (ctx->W > 1 && !t.send) {
         t.send = (Fr *)ctx->pool.alloc(t.n_rows * c * sizeof(Fr));
         if (!t.send) return fail(ctx, DP_E_OOM, "exchange send buffer");
     } else if (ctx->W == 1) {
         t.send = t.rows;
     }
     cudaStreamWaitEvent(ctx->stream, t.ev_in, 0);
-    int rc = plan_row_phase(ctx, d, t.rows, t.send, scratch, t.n_rows, t.row_start, t.is_inv, t.is_coset, ctx->W);
+    int rc = plan_row_phase(ctx, d, t.rows, t.send, scratch, t.n_rows, t.row_start, t.is_inv, t.is_coset, ctx->W,
+                            use_p2p ? &peers : nullptr);
     ctx->pool.release(scratch);
     if (rc == DP_OK) t.row_phase_done = true;
     return rc;
@@ -728,6 +775,9 @@ int dp_destroy(dp_ctx *ctx) {
     }
     ctx->pool.destroy();
     ctx->pool_io.destroy();
+    for (uint64_t q = 0; q < 8; q++)
+        if (ctx->peer_arena[q] && q != ctx->me) cudaIpcCloseMemHandle(ctx->peer_arena[q]);
+    if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -986,9 +1036,17 @@ int dp_fft2_prepare(dp_ctx *ctx, uint64_t id) {
     if (!ctx) return DP_E_ARG;
     FftTask *t = find_task(ctx, id);
     if (!t) return fail(ctx, DP_E_ARG, "dp_fft2_prepare: unknown task %llu", (unsigned long long)id);
-    if (ctx->W > 1)
-        return fail(ctx, DP_E_COMM, "dp_fft2_prepare: %llu workers but no peer transport attached; use dp_fft_exchange_begin/_end around an all-to-all", (unsigned long long)ctx->W);
     DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->W > 1) {
+        if (!p2p_ready(ctx))
+            return fail(ctx, DP_E_COMM, "dp_fft2_prepare: %llu workers but no peer transport attached; use dp_fft_exchange_begin/_end around an all-to-all", (unsigned long long)ctx->W);
+        // fused exchange: the row kernel stores into the owners' arenas over NVLink.  Returning only
+        // after the stream drained makes "every worker answered fft2Prepare" (the dispatcher's join,
+        // dispatcher2.rs:767-772) the barrier that orders these stores before any fft2.
+        call_begin(ctx);
+        DP_TRY(run_row_phase(ctx, *t, true));
+        return call_end(ctx, true);
+    }
     call_begin(ctx);
     DP_TRY(run_row_phase(ctx, *t));
     t->recv = t->send;
@@ -1000,8 +1058,9 @@ int dp_fft2(dp_ctx *ctx, uint64_t id, void *out, size_t out_bytes) {
     if (!ctx || !out) return fail(ctx, DP_E_ARG, "dp_fft2: NULL argument");
     FftTask *t = find_task(ctx, id);
     if (!t) return fail(ctx, DP_E_ARG, "dp_fft2: unknown task %llu", (unsigned long long)id);
-    if (!t->exchanged || !t->cols) return fail(ctx, DP_E_STATE, "dp_fft2 before fft2_prepare / exchange");
     DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (t->p2p && t->row_phase_done && !t->cols) DP_TRY(queue_col_phase(ctx, *t));  // peers' stores are complete by now
+    if (!t->exchanged || !t->cols) return fail(ctx, DP_E_STATE, "dp_fft2 before fft2_prepare / exchange");
     const uint64_t r = ctx->dom[t->is_quot ? 1 : 0].r();
     const size_t bytes = t->n_cols * r * sizeof(Fr);
     if (out_bytes < bytes) return fail(ctx, DP_E_ARG, "dp_fft2: out buffer %zu < %zu bytes", out_bytes, bytes);
@@ -1071,7 +1130,8 @@ int dp_fft_dev_cols(dp_ctx *ctx, void *cols_dev) {
     const DomainDev &d = ctx->dom[(f & 4) ? 1 : 0];
     const uint64_t n_cols = d.c() / ctx->W;
     call_begin(ctx);
-    Fr *src = ctx->W > 1 ? ctx->dev_recv : ctx->dev_send;
+    Fr *src = ctx->dev_p2p_slot ? ctx->dev_p2p_slot : (ctx->W > 1 ? ctx->dev_recv : ctx->dev_send);
+    ctx->dev_p2p_slot = nullptr;
     DP_TRY(plan_col_phase(ctx, d, src, (Fr *)cols_dev, n_cols, ctx->me * n_cols, (f & 2) != 0, (f & 1) != 0));
     ctx->dev_flags = -1;
     return call_end(ctx, true);
@@ -1241,11 +1301,72 @@ int dp_debug_set_limits(dp_ctx *ctx, uint32_t max_contig_log_k, uint32_t max_str
     return DP_OK;
 }
 
-int dp_peer_arena_create(dp_ctx *ctx, uint64_t, void *) {
-    return fail(ctx, DP_E_COMM, "peer arena: not available in this build; use the split exchange API");
+int dp_peer_arena_create(dp_ctx *ctx, uint64_t arena_bytes, void *handle_out) {
+    if (!ctx || !handle_out) return fail(ctx, DP_E_ARG, "dp_peer_arena_create: NULL argument");
+    if (ctx->arena) return fail(ctx, DP_E_STATE, "dp_peer_arena_create: arena already exists");
+    if (arena_bytes < 2 * sizeof(Fr)) return fail(ctx, DP_E_ARG, "dp_peer_arena_create: arena too small");
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    arena_bytes = (arena_bytes + 1023) & ~(uint64_t)1023;
+    void *p = nullptr;
+    // a dedicated cudaMalloc (not the pool): IPC handles cover whole allocations
+    if (cudaMalloc(&p, arena_bytes) != cudaSuccess) return fail(ctx, DP_E_OOM, "peer arena of %llu bytes", (unsigned long long)arena_bytes);
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(cudaIpcMemHandle_t) == DP_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail(ctx, DP_E_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle_out, &h, sizeof h);
+    ctx->arena = (Fr *)p;
+    ctx->arena_bytes = arena_bytes;
+    ctx->peer_arena[ctx->me] = ctx->arena;
+    return DP_OK;
 }
-int dp_peer_attach(dp_ctx *ctx, uint64_t, const void *) {
-    return fail(ctx, DP_E_COMM, "peer arena: not available in this build; use the split exchange API");
+
+int dp_peer_attach(dp_ctx *ctx, uint64_t peer, const void *handle) {
+    if (!ctx || !handle) return fail(ctx, DP_E_ARG, "dp_peer_attach: NULL argument");
+    if (peer >= ctx->W || peer >= 8) return fail(ctx, DP_E_ARG, "dp_peer_attach: peer %llu of %llu", (unsigned long long)peer, (unsigned long long)ctx->W);
+    if (!ctx->arena) return fail(ctx, DP_E_STATE, "dp_peer_attach before dp_peer_arena_create");
+    if (peer == ctx->me) return DP_OK;
+    if (ctx->peer_arena[peer]) return fail(ctx, DP_E_STATE, "dp_peer_attach: peer %llu already attached", (unsigned long long)peer);
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    void *p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(ctx, DP_E_COMM, "cudaIpcOpenMemHandle(peer %llu): %s", (unsigned long long)peer, cudaGetErrorString(e));
+    ctx->peer_arena[peer] = (Fr *)p;
+    return DP_OK;
+}
+
+int dp_peer_ready(const dp_ctx *ctx) { return ctx && p2p_ready(ctx) ? 1 : 0; }
+
+int dp_fft_dev_rows_p2p(dp_ctx *ctx, const void *rows_dev, int is_quot, int is_inv, int is_coset) {
+    if (!ctx || !rows_dev) return fail(ctx, DP_E_ARG, "dp_fft_dev_rows_p2p: NULL argument");
+    if (!ctx->inited) return fail(ctx, DP_E_STATE, "dp_fft_dev_rows_p2p before dp_init");
+    if (!p2p_ready(ctx)) return fail(ctx, DP_E_COMM, "dp_fft_dev_rows_p2p: peers not attached");
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const DomainDev &d = ctx->dom[is_quot ? 1 : 0];
+    const uint64_t W = ctx->W, n_rows = d.r() / W, n_cols = d.c() / W, c = d.c();
+    call_begin(ctx);
+    PeerDst peers;
+    Fr *slot = nullptr;
+    DP_TRY(p2p_next_slot(ctx, d.r() * n_cols * sizeof(Fr), peers, slot, ctx->me * n_rows * n_cols));
+    const bool need_scratch = d.log_c > ctx->max_contig_log_k;
+    Fr *scratch = need_scratch ? (Fr *)ctx->pool.alloc(n_rows * c * sizeof(Fr)) : nullptr;
+    if (need_scratch && !scratch) return fail(ctx, DP_E_OOM, "dp_fft_dev_rows_p2p scratch");
+    int rc = plan_row_phase(ctx, d, (const Fr *)rows_dev, nullptr, scratch, n_rows, ctx->me * n_rows, is_inv != 0, is_coset != 0, W, &peers);
+    ctx->pool.release(scratch);
+    if (rc != DP_OK) return rc;
+    DP_TRY(call_end(ctx, true));
+    ctx->pool.release(ctx->dev_send);
+    ctx->pool.release(ctx->dev_recv);
+    ctx->dev_send = nullptr;
+    ctx->dev_recv = nullptr;
+    ctx->dev_p2p_slot = slot;
+    ctx->dev_flags = (is_quot ? 4 : 0) | (is_inv ? 2 : 0) | (is_coset ? 1 : 0);
+    return DP_OK;
 }
 
 }  // extern "C"

@@ -66,6 +66,14 @@ struct NttPass {
     // + (k & (2^split_log - 1)):  the pack step of worker.rs:327-330 fused into the store
     uint64_t out_lc, split_stride;
     uint32_t split_on, split_log;
+    // fused exchange over peer memory: block q of the exchange layout is not a slice of `out` but
+    // the receive matrix of worker q, mapped into this process through CUDA IPC (NVLink stores):
+    //   address = peer_base[k >> split_log] + peer_row_off + o*out_os + lane*out_ls + (k & mask)
+    // This is PlonkPeer.fftExchange (worker.rs:327-330 send side + 432-435 scatter side) done by the
+    // row kernel's own epilogue, tile by tile, while other tiles are still computing.
+    uint32_t peer_on;
+    uint64_t peer_row_off;
+    Fr *peer_base[8];
     const uint4 *w_lo, *w_hi;         // stage-major butterfly twiddles, plane-split, >= K entries
     // output twiddle omega_N^(+-e),  e = (tw_la*lane + tw_oa*o + tw_c0) * (tw_fb*f + tw_lb*lane)
     const Fr *tw_tab;                 // omega_N^e, e < N/2   (nullptr = no twiddle)
@@ -290,6 +298,11 @@ __global__ void __launch_bounds__(NTT_TPB, 2) ntt_tile_kernel(NttPass p) {
             }
             if (p.post_const_on) v = v * p.post_const;
             uint64_t col = lane * p.out_lc + (uint64_t)f * p.out_ps;
+            if (p.peer_on) {
+                Fr *pd = p.peer_base[col >> p.split_log] + p.peer_row_off + (uint64_t)o * p.out_os + lane * p.out_ls;
+                gmem_st(pd + (col & (((uint64_t)1 << p.split_log) - 1)), v);
+                continue;
+            }
             if (p.split_on) col = (col >> p.split_log) * p.split_stride + (col & (((uint64_t)1 << p.split_log) - 1));
             gmem_st(dst + lane * p.out_ls + col, v);
         }

@@ -56,3 +56,19 @@ def make_exchange(group=None, cuda: bool | None = None):
 def msm_shard(n_bases: int, rank: int, world: int):
     """MsmWorkload of `rank`: the global index range of dispatcher2.rs:870-881."""
     return rank * n_bases // world, (rank + 1) * n_bases // world
+
+
+def attach_peers(ctx, arena_bytes: int, group=None):
+    """Fused exchange set-up (one process per GPU of one box): every rank creates its receive arena,
+    the CUDA IPC handles are swapped with all_gather, every rank maps the others' arenas.  After
+    this PlonkSlave.fft2_prepare / Context.fft_dev_rows_p2p store straight into peer memory and
+    the only synchronisation left is a barrier between the row and the column phase."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    handle = ctx.peer_arena_create(arena_bytes)
+    handles = [None] * world
+    dist.all_gather_object(handles, handle, group=group)
+    for q, h in enumerate(handles):
+        if q != rank:
+            ctx.peer_attach(q, h)
+    dist.barrier(group=group)
+    return ctx.peer_ready()

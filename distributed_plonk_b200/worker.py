@@ -64,7 +64,9 @@ class PlonkSlave:
     def fft2_prepare(self, task_id: int, exchange=None):
         """n_workers == 1: local.  Otherwise `exchange(send_ptr, recv_ptr, block_elems)` must move
         block q of send to rank q's recv block `me` (an all-to-all; see parallel.py)."""
-        if self.n_workers == 1:
+        if self.n_workers == 1 or self.ctx.peer_ready():
+            # peers attached: the row kernel stores into the owners' arenas over NVLink; the caller
+            # (the dispatcher's join over all fft2Prepare replies) is the barrier before fft2
             self.ctx.fft2_prepare(task_id)
             return
         if exchange is None:

@@ -123,11 +123,15 @@ int dp_get_wire(dp_ctx *ctx, void *out, size_t out_bytes, size_t *n_coeffs);
 /* ---- peer transport for n_workers > 1 ---------------------------------------------------------
  * Exchange arena shared between the GPUs of one box through CUDA IPC: every rank exports a
  * handle, the ranks swap them out of band (torch.distributed / the capnp control plane) and attach
- * the others'.  Afterwards dp_fft2_prepare writes over NVLink and needs only dp_peer_barrier-style
- * ordering from the caller (any barrier across ranks between fft2Prepare and fft2). */
+ * the others'.  Afterwards dp_fft2_prepare stores the row-phase output straight into the owners'
+ * arenas over NVLink (two slots, alternating per exchange: every rank must issue its exchanges in
+ * the same order) and returns when its stores are complete; the caller provides the barrier across
+ * ranks between fft2Prepare and fft2 - the dispatcher's join over the fft2Prepare replies is one.
+ * arena_bytes >= 2 * (r * c / n_workers) * 32 for the largest domain. */
 #define DP_IPC_HANDLE_BYTES 64
 int dp_peer_arena_create(dp_ctx *ctx, uint64_t arena_bytes, void *handle_out /* DP_IPC_HANDLE_BYTES */);
 int dp_peer_attach(dp_ctx *ctx, uint64_t peer, const void *handle /* DP_IPC_HANDLE_BYTES */);
+int dp_peer_ready(const dp_ctx *ctx); /* 1 when the arena exists and every peer is attached */
 
 /* ---- instrumentation --------------------------------------------------------------------------*/
 /* device-side time (ms, CUDA events on the context stream) and kernel launches of the last call */
@@ -165,6 +169,9 @@ int dp_fft_dev(dp_ctx *ctx, const void *rows_dev, void *cols_dev, int is_quot, i
 int dp_fft_dev_rows(dp_ctx *ctx, const void *rows_dev, int is_quot, int is_inv, int is_coset, void **send_dev,
                     void **recv_dev, uint64_t *block_elems);
 int dp_fft_dev_cols(dp_ctx *ctx, void *cols_dev);
+/* fused variant of _rows for attached peers: the row kernel stores into the owners' arenas; the
+ * caller then only needs a barrier across ranks before dp_fft_dev_cols */
+int dp_fft_dev_rows_p2p(dp_ctx *ctx, const void *rows_dev, int is_quot, int is_inv, int is_coset);
 
 #ifdef __cplusplus
 }

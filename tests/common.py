@@ -42,6 +42,16 @@ def local_exchange(ctxs, tid):
         c.fft_exchange_end(tid)
 
 
+def attach_in_process(workers, arena_bytes):
+    """single process holding every worker: swap the arena handles directly"""
+    handles = [w.ctx.peer_arena_create(arena_bytes) for w in workers]
+    for p, w in enumerate(workers):
+        for q, h in enumerate(handles):
+            if q != p:
+                w.ctx.peer_attach(q, h)
+        assert w.ctx.peer_ready()
+
+
 def check_distributed_fft(orc, workers, domain_log, is_quot, seed, copy_fn, n_in=None):
     """test_fft (dispatcher.rs:246-350): all flag combos through fft_init / fft1 / fft2_prepare /
     fft2 must equal Radix2EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}."""
@@ -57,7 +67,9 @@ def check_distributed_fft(orc, workers, domain_log, is_quot, seed, copy_fn, n_in
         def exchange(send, recv, n, _tid=tid):
             raise AssertionError("single-process test drives the split API directly")
 
-        if W == 1:
+        if W == 1 or workers[0].ctx.peer_ready():
+            # one worker, or fused peer-memory exchange: the plain dispatcher sequence is enough
+            # (all fft2_prepare calls return before the first fft2 = the barrier)
             got = disp.fft(workers, domain_log, x, is_quot, inv, cos, tid)
         else:
             # drive the stubs by hand so the exchange can be done in-process

@@ -223,4 +223,17 @@ inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
 inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated error"; }
 template <class F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+// CUDA IPC: all emulated "devices" live in this process, so a handle is just the pointer
+struct cudaIpcMemHandle_t { char reserved[64]; };
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) {
+    memset(h, 0, sizeof *h);
+    memcpy(h->reserved, &p, sizeof p);
+    return cudaSuccess;
+}
+inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) {
+    memcpy(p, h.reserved, sizeof *p);
+    return cudaSuccess;
+}
+inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
 inline cudaError_t cudaMemGetInfo(size_t *f, size_t *t) { *f = *t = (size_t)8 << 30; return cudaSuccess; }

@@ -44,24 +44,34 @@ def _worker(rank, world, port, lib_path, out_dir, backend="gloo"):
     w.init(chunks(bases), 1 << 6, 1 << 9)
     exchange = parallel.make_exchange()
     ok = True
-    for is_quot, L in ((False, 6), (True, 9)):
-        wl = disp.fft_workloads(L, world)
-        for k, (inv, cos) in enumerate([(False, False), (True, False), (False, True), (True, True)]):
-            x = orc.gen_fr(100 + L + k, 1 << L)
-            rows = disp.dispatcher_rows(x, L)
-            tid = 500 + 10 * L + k
-            w.fft_init(tid, wl, is_quot, inv, cos)
-            for j in range(wl[rank][1] - wl[rank][0]):
-                w.fft1(tid, j, chunks(rows[wl[rank][0] + j]))
-            w.fft2_prepare(tid, exchange)
-            mine = torch.from_numpy(w.fft2_array(tid).view(np.int64))
-            if cuda:
-                mine = mine.cuda()
-            gathered = [torch.empty_like(mine) for _ in range(world)]
-            dist.all_gather(gathered, mine)
-            cols = torch.cat(gathered).cpu().numpy().view(np.uint64)
-            got = disp.assemble(cols)
-            ok &= bool(np.array_equal(got, orc.fft(x, inv, cos)))
+    def run_ffts(mode):
+        good = True
+        for is_quot, L in ((False, 6), (True, 9)):
+            wl = disp.fft_workloads(L, world)
+            for k, (inv, cos) in enumerate([(False, False), (True, False), (False, True), (True, True)]):
+                x = orc.gen_fr(100 + L + k, 1 << L)
+                rows = disp.dispatcher_rows(x, L)
+                tid = 500 + 10 * L + k + (1000 if mode == "fused" else 0)
+                w.fft_init(tid, wl, is_quot, inv, cos)
+                for j in range(wl[rank][1] - wl[rank][0]):
+                    w.fft1(tid, j, chunks(rows[wl[rank][0] + j]))
+                w.fft2_prepare(tid, exchange)
+                if mode == "fused":
+                    dist.barrier()    # the dispatcher's join over the fft2Prepare replies
+                mine = torch.from_numpy(w.fft2_array(tid).view(np.int64))
+                if cuda:
+                    mine = mine.cuda()
+                gathered = [torch.empty_like(mine) for _ in range(world)]
+                dist.all_gather(gathered, mine)
+                cols = torch.cat(gathered).cpu().numpy().view(np.uint64)
+                good &= bool(np.array_equal(disp.assemble(cols), orc.fft(x, inv, cos)))
+        return good
+
+    ok &= run_ffts("collective")          # one all_to_all_single per transform
+    if cuda:
+        # CUDA IPC arenas need real GPUs (an emulated handle is a bare pointer of another process)
+        ok &= bool(parallel.attach_peers(w.ctx, 2 * (1 << 9) * 32 // world))
+        ok &= run_ffts("fused")           # row kernel stores straight into peer memory
     # sharded MSM: index-range split, partials summed by the dispatcher (rank 0 here)
     sc = orc.gen_fr(77, n_bases, False)
     lo, hi = parallel.msm_shard(n_bases, rank, world)

@@ -53,6 +53,21 @@ def test_distributed_fft_like_reference_test_fft(orc, emul_lib, W, logn, logq, l
         w.close()
 
 
+@pytest.mark.parametrize("W,limits", [(2, (11, 9)), (4, (2, 2))])
+def test_distributed_fft_fused_peer_exchange(orc, emul_lib, W, limits):
+    """dp_peer_arena_create / dp_peer_attach: the row kernel stores into the owners' arenas (the
+    emulator's IPC handle is the pointer itself); two slots alternate across consecutive tasks"""
+    workers = [PlonkSlave(emul_lib, p, W) for p in range(W)]
+    for w in workers:
+        w.init([b""], 1 << 6, 1 << 9)
+        w.ctx.debug_set_limits(limits[0], limits[1], 0)
+    common.attach_in_process(workers, 2 * (1 << 9) * 32 // W)
+    common.check_distributed_fft(orc, workers, 6, False, 3, host_copy)
+    common.check_distributed_fft(orc, workers, 9, True, 4, host_copy)
+    for w in workers:
+        w.close()
+
+
 def test_msm_distributions_and_geometries(orc, ctx):
     bases = orc.gen_bases(5, 600, 64, True)
     ctx.debug_set_limits(11, 9, 0)

@@ -81,6 +81,25 @@ def test_distributed_fft_like_reference_test_fft(orc, gpu_lib, W, logn, logq, li
             w.close()
 
 
+@pytest.mark.parametrize("W,logn,logq,limits", [(2, 12, 15, (11, 9)), (4, 8, 11, (3, 2))])
+def test_distributed_fft_fused_peer_exchange(orc, gpu_lib, W, logn, logq, limits):
+    """W contexts on ONE GPU attached through CUDA IPC is not possible (IPC handles cannot be opened
+    in the exporting process), so on a single device the peer arenas are exercised across processes
+    in tests/test_gpu_multi.py; here only the API's error behaviour is checked."""
+    w = PlonkSlave(gpu_lib, 0, W)
+    try:
+        w.init([b""], 1 << logn, 1 << logq)
+        assert not w.ctx.peer_ready()
+        h = w.ctx.peer_arena_create(2 * (1 << logq) * 32 // W)
+        assert len(h) == 64 and not w.ctx.peer_ready()
+        with pytest.raises(DpError):
+            w.ctx.peer_arena_create(1 << 20)          # second arena
+        with pytest.raises(DpError):
+            w.ctx.peer_attach(W, h)                   # peer index out of range
+    finally:
+        w.close()
+
+
 @pytest.mark.parametrize("logq", [20, 23])
 def test_distributed_fft_large(orc, gpu_lib, logq):
     """2^20: single-pass rows/cols (r = c = 2^10); 2^23: r = 2^11, c = 2^12 -> both phases split"""

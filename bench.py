@@ -427,8 +427,34 @@ def main():
         per_launch_ms = statistics.mean(stats["ntt_m_ms"]) / max(1, stats["ntt_m_launches"]) if stats["ntt_m_ms"] else float("nan")
         alg_bytes = 64 * m                                 # one read + one write of every element per pass
     achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms == per_launch_ms else None
+    traffic = None
+    try:  # DRAM bytes per launch of the same kernel at this size, from the committed ncu capture
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        key = "msm_accumulate_kernel" if dominant.startswith("msm") else "ntt_tile_kernel"
+        if W == 1 and str(log_n) in tr.get(key, {}) and dominant.startswith("msm"):
+            traffic = tr[key][str(log_n)]["bytes"]
+    except (OSError, ValueError, KeyError):
+        pass
+    # the bound that actually applies: 32x32+64 multiply-accumulates on the FMA pipe.  Peak = plain
+    # IMAD.WIDE.U32 rate measured on this part (profiles/r01_microbench_pipes.txt: 61.9 lane-MAC/clk/SM);
+    # the carry form IMAD.WIDE.U32.X that multi-precision chains need sustains 28.3 (r01_microbench_carry_chains.txt)
+    sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
+    mac_peak = 61.9 * 148 * sm_clk * 1e6
+    macs_msm = (hi - lo) * 1.0 * ((256 + 19) // 20) * 10 * 288        # digits x (8M+2S) x 12x12x2 MACs
+    macs_ntt = (m / 2) * log_m * 128 + 4 * m * 128                     # butterflies + twiddle/coset products, 8x8x2 MACs
+    compute = {
+        "bound": "int32 multiply-add pipe", "peak_mac_per_s": mac_peak, "peak_source": "measured IMAD.WIDE.U32 rate x 148 SMs x sampled SM clock",
+        "msm_accumulate_frac": (macs_msm / (statistics.mean(stats["msm_acc_ms"]) * 1e-3) / mac_peak) if stats["msm_acc_ms"] else None,
+        "ntt_tile_8n_frac": (macs_ntt / (statistics.mean(stats["ntt_m_ms"]) * 1e-3) / mac_peak) if stats["ntt_m_ms"] else None,
+        "carry_form_ceiling_frac": 28.3 / 61.9,
+    }
+    ntt_hbm = None
+    if stats["ntt_m_ms"]:
+        per = statistics.mean(stats["ntt_m_ms"]) / max(1, stats["ntt_m_launches"])
+        ntt_hbm = {"kernel": "ntt_tile_kernel(8n)", "achieved": 64 * m / (per * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                   "frac": 64 * m / (per * 1e-3) / 1e9 / peak, "avg_launch_ms": per, "algorithmic_bytes_per_launch": 64 * m}
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(alg_bytes), "avg_launch_ms": per_launch_ms,
                 "note": "both kernels are bound by the INT32 multiply pipe, not HBM (DESIGN.md); HBM fraction reported as BASELINE asks",
                 "step_share_ms": shares}
@@ -442,7 +468,7 @@ def main():
         "ntt_butterflies_per_sec": butterflies(log_m) / (statistics.mean(stats["ntt_m_ms"]) * 1e-3) if stats["ntt_m_ms"] else None,
         "breakdown_ms": {"msm_total": msm_total, "msm_accumulate": acc_total, "intt_n_total": sum(stats["ntt_n_ms"]),
                          "coset_ntt_8n_total": ntt_m_total},
-        "roofline": roofline, "e2e": e2e,
+        "roofline": roofline, "roofline_ntt": ntt_hbm, "roofline_compute": compute, "e2e": e2e,
     }
     if not args.no_cpu and W == 1:
         from oracle import loader as orc

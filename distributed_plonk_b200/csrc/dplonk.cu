@@ -613,8 +613,8 @@ int msm_device(dp_ctx *ctx, uint64_t start, const uint4 *scalars_dev, uint64_t n
     cudaEventRecord(ctx->ev_msm[1], st);
     DP_LAUNCH(msm_accumulate_kernel, dim3(blocks_for(max_tasks, MSM_TPB)), dim3(MSM_TPB), 0, st, tasks,
               task_off + g.n_keys, sorted, bases, partials);
-    DP_LAUNCH(msm_collapse_kernel, dim3(blocks_for(max_multi * 32, MSM_TPB)), dim3(MSM_TPB), 0, st, multi_keys + 1, multi_keys,
-              task_off, partials);
+    DP_LAUNCH(msm_collapse_kernel, dim3(max_multi * 32 < 148ull * 8 * MSM_TPB ? blocks_for(max_multi * 32, MSM_TPB) : 148 * 8),
+              dim3(MSM_TPB), 0, st, multi_keys + 1, multi_keys, task_off, partials);
     cudaEventRecord(ctx->ev_msm[2], st);
     DP_LAUNCH(msm_reduce_kernel, dim3(blocks_for(n_segs, MSM_TPB)), dim3(MSM_TPB), 0, st, partials, task_off, g, seg_sums);
     DP_LAUNCH(msm_window_sum_kernel, dim3(g.red_windows * g.slices), dim3(MSM_TPB), 0, st, seg_sums, g, win_sums);

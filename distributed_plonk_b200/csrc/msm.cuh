@@ -34,7 +34,7 @@
 namespace dp {
 
 constexpr uint32_t MSM_TSEG = 256;      // max points per accumulate task
-constexpr uint32_t MSM_SEG = 32;        // buckets per reduce segment
+constexpr uint32_t MSM_SEG = 16;        // buckets per reduce segment
 constexpr int MSM_TPB = 128;
 
 constexpr uint32_t MSM_SLICES = 32;     // partial sums per window in the two-level window sum
@@ -386,14 +386,16 @@ DP_D G1XYZZ shfl_xor_point(const G1XYZZ &p, int mask) {
 }
 __global__ void __launch_bounds__(MSM_TPB) msm_collapse_kernel(const uint32_t *multi_keys, const uint32_t *n_multi,
                                                                 const uint32_t *task_off, G1XYZZ *partials) {
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= *n_multi) return;  // whole warps leave together
-    const uint32_t key = multi_keys[warp];
-    const uint32_t t0 = task_off[key], t1 = task_off[key + 1];
-    G1XYZZ acc = G1XYZZ::inf();
-    for (uint32_t t = t0 + lane; t < t1; t += 32) acc = acc.add(partials[t]);
-    for (int m = 16; m >= 1; m >>= 1) acc = acc.add(shfl_xor_point(acc, m));
-    if (lane == 0) partials[t0] = acc;
+    // fixed-size grid, warps loop over the (usually empty) list: the count is only known on the device
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5, lane = threadIdx.x & 31;
+    for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < *n_multi; w += n_warps) {  // warp-uniform
+        const uint32_t key = multi_keys[w];
+        const uint32_t t0 = task_off[key], t1 = task_off[key + 1];
+        G1XYZZ acc = G1XYZZ::inf();
+        for (uint32_t t = t0 + lane; t < t1; t += 32) acc = acc.add(partials[t]);
+        for (int m = 16; m >= 1; m >>= 1) acc = acc.add(shfl_xor_point(acc, m));
+        if (lane == 0) partials[t0] = acc;
+    }
 }
 
 // sum of one bucket: its (single, or collapsed) partial sum

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_nccl_fft_and_msm(tmp_path, world):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs, box has {torch.cuda.device_count()}")

@@ -113,8 +113,11 @@ struct dp_ctx {
     uint4 *wf_lo = nullptr, *wf_hi = nullptr, *wi_lo = nullptr, *wi_hi = nullptr;
     G1Affine *bases = nullptr;
     uint64_t n_bases = 0;
-    G1Affine *pre_table = nullptr;  // [pre_nw][n_bases] window multiples 2^(c*w) * P_i (msm.cuh)
+    // window multiples 2^(c*w) * P_i (msm.cuh) for bases [pre_lo, pre_hi): the whole SRS for a single
+    // worker, this worker's MsmWorkload shard (dispatcher.rs:219-229) otherwise; row length pre_hi-pre_lo
+    G1Affine *pre_table = nullptr;
     uint32_t pre_c = 0, pre_nw = 0;
+    uint64_t pre_lo = 0, pre_hi = 0;
     DomainDev dom[2];
     bool inited = false;
     std::map<uint64_t, FftTask> tasks;
@@ -565,10 +568,11 @@ int msm_device(dp_ctx *ctx, uint64_t start, const uint4 *scalars_dev, uint64_t n
     }
     if (n >= ((uint64_t)1 << 31)) return fail(ctx, DP_E_ARG, "msm: %llu points exceed 2^31", (unsigned long long)n);
     // precomputed window multiples pay off once the shared bucket set is reasonably filled
-    const bool use_pre = ctx->pre_table && ctx->msm_force_c == 0 && n * ctx->pre_nw >= 4ull * (1ull << (ctx->pre_c - 1));
-    const MsmGeom g = use_pre ? msm_make_geom(ctx->pre_c, true, ctx->n_bases)
+    const bool use_pre = ctx->pre_table && ctx->msm_force_c == 0 && start >= ctx->pre_lo && start + n <= ctx->pre_hi &&
+                         n * ctx->pre_nw >= 4ull * (1ull << (ctx->pre_c - 1));
+    const MsmGeom g = use_pre ? msm_make_geom(ctx->pre_c, true, ctx->pre_hi - ctx->pre_lo)
                               : msm_geometry(n, ctx->msm_force_c > 1 ? ctx->msm_force_c : 0);
-    const G1Affine *bases = (use_pre ? ctx->pre_table : ctx->bases) + start;
+    const G1Affine *bases = use_pre ? ctx->pre_table + (start - ctx->pre_lo) : ctx->bases + start;
     const uint64_t max_digits = n * g.n_windows;
     const uint64_t max_tasks = (uint64_t)g.n_keys + max_digits / MSM_TSEG + 1;
     const uint32_t n_segs = g.red_windows * g.segs_per_window;
@@ -823,6 +827,7 @@ int dp_init(dp_ctx *ctx, const void *bases, size_t n_bases, uint64_t domain_size
     ctx->bases = nullptr;
     ctx->pre_table = nullptr;
     ctx->pre_c = ctx->pre_nw = 0;
+    ctx->pre_lo = ctx->pre_hi = 0;
     free_domain(ctx, ctx->dom[0]);
     free_domain(ctx, ctx->dom[1]);
     ctx->inited = false;
@@ -839,19 +844,19 @@ int dp_init(dp_ctx *ctx, const void *bases, size_t n_bases, uint64_t domain_size
         // window multiples for the MSM (skipped for tiny SRS or when memory is short)
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
-        const uint32_t c = n_bases >= (1u << 11) && !ctx->pre_disabled ? msm_pick_pre_c(n_bases, free_b / 4) : 0;
+        const uint64_t lo = ctx->me * n_bases / ctx->W, hi = (ctx->me + 1) * n_bases / ctx->W, span = hi - lo;
+        const uint32_t c = span >= (1u << 11) && !ctx->pre_disabled ? msm_pick_pre_c(span, free_b / 4) : 0;
         if (c) {
             const uint32_t nw = (256 + c - 1) / c;
-            ctx->pre_table = (G1Affine *)ctx->pool.alloc((size_t)nw * n_bases * sizeof(G1Affine));
-            if (ctx->pre_table && nw <= (uint32_t)MSM_PRE_MAX_WINDOWS) {
+            ctx->pre_table = nw <= (uint32_t)MSM_PRE_MAX_WINDOWS ? (G1Affine *)ctx->pool.alloc((size_t)nw * span * sizeof(G1Affine)) : nullptr;
+            if (ctx->pre_table) {
                 ctx->pre_c = c;
                 ctx->pre_nw = nw;
-                DP_LAUNCH(msm_precompute_kernel, dim3(blocks_for(n_bases, 128)), dim3(128), 0, ctx->stream, ctx->bases,
-                          ctx->pre_table, (uint64_t)n_bases, (uint64_t)n_bases, c, nw);
+                ctx->pre_lo = lo;
+                ctx->pre_hi = hi;
+                DP_LAUNCH(msm_precompute_kernel, dim3(blocks_for(span, 128)), dim3(128), 0, ctx->stream, ctx->bases + lo,
+                          ctx->pre_table, span, span, c, nw);
                 ctx->launches++;
-            } else {
-                ctx->pool.release(ctx->pre_table);
-                ctx->pre_table = nullptr;
             }
         }
     }

@@ -92,6 +92,14 @@ def test_msm_precomputed_window_multiples(orc, emul_lib):
     c.debug_set_limits(11, 9, 1)
     common.assert_point_eq(orc, c.msm(0, n, sc), orc.msm(bases, sc), "forced windowed")
     c.close()
+    # worker 1 of 2: the table covers only its MsmWorkload shard [n, 2n)
+    bases2 = orc.gen_bases(12, 2 * n, 64, True)
+    c = Context(emul_lib, 0, 1, 2)
+    c.init(bases2, 1 << 4, 1 << 7)
+    common.assert_point_eq(orc, c.msm(n, 2 * n, sc), orc.msm(bases2[n:], sc), "own shard (table)")
+    common.assert_point_eq(orc, c.msm(0, n, sc), orc.msm(bases2[:n], sc), "other shard (per-window path)")
+    common.assert_point_eq(orc, c.msm(n - 5, 2 * n, sc), orc.msm(bases2[n - 5:], sc), "straddling range")
+    c.close()
 
 
 def test_msm_edges(orc, ctx):

@@ -188,8 +188,9 @@ __global__ void __launch_bounds__(NTT_TPB, 2) ntt_tile_kernel(NttPass p) {
         memcpy(whi, p.w_hi, (size_t)K * 16);
     }
 #else
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();  // nobody may wait on the barrier before it is initialised (tiny tiles get here at once)
     if (tid == 0) {
-        mbar_init(bar, 1);
         mbar_expect_tx(bar, 2 * K * 16);
         tma_bulk_g2s(wlo, p.w_lo, K * 16, bar);
         tma_bulk_g2s(whi, p.w_hi, K * 16, bar);

@@ -101,7 +101,7 @@ struct dp_ctx {
     uint64_t me = 0, W = 1;
     // Three streams so that consecutive tasks overlap: rows of task k+1 stream in (s_in) while task k
     // computes (stream) and the columns of task k-1 stream out (s_out); PCIe is full duplex.
-    cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
+    cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr, s_tail = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_msm[4] = {nullptr, nullptr, nullptr, nullptr};  // sort done | accumulate done | tail done
     float msm_ms[3] = {0.f, 0.f, 0.f};
@@ -558,12 +558,23 @@ void free_task(dp_ctx *ctx, FftTask &t) {
 }
 
 // ------------------------------------------------------------------ MSM driver (device pointers)
-int msm_device(dp_ctx *ctx, uint64_t start, const uint4 *scalars_dev, uint64_t n, G1JacobianOut *out_dev,
-               uint32_t *err_host_out) {
+// One MSM in flight: its scratch lives until msm_finish().  The head (digit sort + bucket
+// accumulation: wide kernels) runs on the compute stream, the tail (bucket reduction, window sum,
+// normalisation: narrow, latency-bound kernels) on s_tail, so that in a batch the tail of MSM k
+// overlaps the head of MSM k+1 - the dispatcher issues the commitments of a round concurrently
+// (join_all, dispatcher2.rs:316-321, 526-532).
+struct MsmJob {
+    std::vector<void *> scratch;
+    uint32_t *err = nullptr;
+    cudaEvent_t ev_head = nullptr;
+};
+
+int msm_enqueue(dp_ctx *ctx, uint64_t start, const uint4 *scalars_dev, uint64_t n, G1JacobianOut *out_dev, MsmJob &job,
+                bool record_breakdown) {
+    cudaStream_t st = ctx->stream, tl = ctx->s_tail;
     if (n == 0) {
-        const G1JacobianOut id = G1JacobianOut::from_affine(G1Affine::inf());
-        DP_CUDA(ctx, cudaMemcpyAsync(out_dev, &id, sizeof id, cudaMemcpyHostToDevice, ctx->stream));
-        DP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        static const G1JacobianOut id = G1JacobianOut::from_affine(G1Affine::inf());
+        DP_CUDA(ctx, cudaMemcpyAsync(out_dev, &id, sizeof id, cudaMemcpyHostToDevice, st));
         return DP_OK;
     }
     if (n >= ((uint64_t)1 << 31)) return fail(ctx, DP_E_ARG, "msm: %llu points exceed 2^31", (unsigned long long)n);
@@ -576,37 +587,34 @@ int msm_device(dp_ctx *ctx, uint64_t start, const uint4 *scalars_dev, uint64_t n
     const uint64_t max_digits = n * g.n_windows;
     const uint64_t max_tasks = (uint64_t)g.n_keys + max_digits / MSM_TSEG + 1;
     const uint32_t n_segs = g.red_windows * g.segs_per_window;
-    DevPool &P = ctx->pool;
-    uint32_t *counts = (uint32_t *)P.alloc((g.n_keys + 1) * 4ull);
-    uint32_t *offsets = (uint32_t *)P.alloc((g.n_keys + 1) * 4ull);
-    uint32_t *cursor = (uint32_t *)P.alloc((g.n_keys + 1) * 4ull);
-    uint32_t *task_off = (uint32_t *)P.alloc((g.n_keys + 1) * 4ull);
-    uint32_t *sorted = (uint32_t *)P.alloc(max_digits * 4ull);
-    uint2 *tasks = (uint2 *)P.alloc(max_tasks * sizeof(uint2));
-    G1XYZZ *partials = (G1XYZZ *)P.alloc(max_tasks * sizeof(G1XYZZ));
-    G1XYZZ *seg_sums = (G1XYZZ *)P.alloc((uint64_t)n_segs * sizeof(G1XYZZ));
-    G1XYZZ *win_sums = (G1XYZZ *)P.alloc((uint64_t)g.red_windows * g.slices * sizeof(G1XYZZ));
-    uint32_t *err = (uint32_t *)P.alloc(4);
     const uint32_t n_scan_blocks = (g.n_keys + SCAN_BLOCK - 1) / SCAN_BLOCK;
-    uint2 *block_sums = (uint2 *)P.alloc((size_t)n_scan_blocks * sizeof(uint2));
     const uint64_t max_multi = max_digits / MSM_TSEG + 1;  // a bucket with > TSEG points
-    uint32_t *multi_keys = (uint32_t *)P.alloc((max_multi + 1) * 4ull);  // [0] = counter, then keys
-    auto cleanup = [&]() {
-        P.release(block_sums);
-        P.release(multi_keys);
-        P.release(counts); P.release(offsets); P.release(cursor); P.release(task_off); P.release(sorted);
-        P.release(tasks); P.release(partials); P.release(seg_sums); P.release(win_sums); P.release(err);
+    bool oom = false;
+    auto grab = [&](size_t bytes) -> void * {
+        void *p = ctx->pool.alloc(bytes);
+        if (!p) oom = true;
+        job.scratch.push_back(p);
+        return p;
     };
-    if (!counts || !offsets || !cursor || !task_off || !sorted || !tasks || !partials || !seg_sums || !win_sums || !err || !block_sums || !multi_keys) {
-        cleanup();
-        return fail(ctx, DP_E_OOM, "msm scratch for %llu points", (unsigned long long)n);
-    }
-    cudaStream_t st = ctx->stream;
-    cudaEventRecord(ctx->ev_msm[0], st);
+    uint32_t *counts = (uint32_t *)grab((g.n_keys + 1) * 4ull);
+    uint32_t *offsets = (uint32_t *)grab((g.n_keys + 1) * 4ull);
+    uint32_t *cursor = (uint32_t *)grab((g.n_keys + 1) * 4ull);
+    uint32_t *task_off = (uint32_t *)grab((g.n_keys + 1) * 4ull);
+    uint32_t *sorted = (uint32_t *)grab(max_digits * 4ull);
+    uint2 *tasks = (uint2 *)grab(max_tasks * sizeof(uint2));
+    G1XYZZ *partials = (G1XYZZ *)grab(max_tasks * sizeof(G1XYZZ));
+    G1XYZZ *seg_sums = (G1XYZZ *)grab((uint64_t)n_segs * sizeof(G1XYZZ));
+    G1XYZZ *win_sums = (G1XYZZ *)grab((uint64_t)g.red_windows * g.slices * sizeof(G1XYZZ));
+    uint2 *block_sums = (uint2 *)grab((size_t)n_scan_blocks * sizeof(uint2));
+    uint32_t *multi_keys = (uint32_t *)grab((max_multi + 1) * 4ull);  // [0] = counter, then keys
+    job.err = (uint32_t *)grab(4);
+    if (oom) return fail(ctx, DP_E_OOM, "msm scratch for %llu points", (unsigned long long)n);
+    if (!job.ev_head) DP_CUDA(ctx, cudaEventCreateWithFlags(&job.ev_head, cudaEventDisableTiming));
+    if (record_breakdown) cudaEventRecord(ctx->ev_msm[0], st);
     cudaMemsetAsync(counts, 0, (g.n_keys + 1) * 4ull, st);
-    cudaMemsetAsync(err, 0, 4, st);
+    cudaMemsetAsync(job.err, 0, 4, st);
     cudaMemsetAsync(multi_keys, 0, 4, st);
-    DP_LAUNCH(msm_count_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, scalars_dev, n, g, counts, err);
+    DP_LAUNCH(msm_count_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, scalars_dev, n, g, counts, job.err);
     DP_LAUNCH(scan_block_sums_kernel, dim3(n_scan_blocks), dim3(SCAN_TPB), 0, st, counts, g.n_keys, block_sums);
     DP_LAUNCH(scan_block_offsets_kernel, dim3(1), dim3(SCAN_TPB), 0, st, block_sums, n_scan_blocks, offsets, task_off, g.n_keys);
     DP_LAUNCH(scan_write_kernel, dim3(n_scan_blocks), dim3(SCAN_TPB), 0, st, counts, g.n_keys, block_sums, offsets, task_off);
@@ -614,27 +622,54 @@ int msm_device(dp_ctx *ctx, uint64_t start, const uint4 *scalars_dev, uint64_t n
     DP_LAUNCH(msm_scatter_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, scalars_dev, n, g, cursor, sorted);
     DP_LAUNCH(msm_tasks_kernel, dim3(blocks_for(g.n_keys, 256)), dim3(256), 0, st, offsets, task_off, g.n_keys, tasks,
               multi_keys + 1, multi_keys);
-    cudaEventRecord(ctx->ev_msm[1], st);
+    if (record_breakdown) cudaEventRecord(ctx->ev_msm[1], st);
     DP_LAUNCH(msm_accumulate_kernel, dim3(blocks_for(max_tasks, MSM_TPB)), dim3(MSM_TPB), 0, st, tasks,
               task_off + g.n_keys, sorted, bases, partials);
     DP_LAUNCH(msm_collapse_kernel, dim3(max_multi * 32 < 148ull * 8 * MSM_TPB ? blocks_for(max_multi * 32, MSM_TPB) : 148 * 8),
               dim3(MSM_TPB), 0, st, multi_keys + 1, multi_keys, task_off, partials);
-    cudaEventRecord(ctx->ev_msm[2], st);
-    DP_LAUNCH(msm_reduce_kernel, dim3(blocks_for(n_segs, MSM_TPB)), dim3(MSM_TPB), 0, st, partials, task_off, g, seg_sums);
-    DP_LAUNCH(msm_window_sum_kernel, dim3(g.red_windows * g.slices), dim3(MSM_TPB), 0, st, seg_sums, g, win_sums);
-    DP_LAUNCH(msm_final_kernel, dim3(1), dim3(32), 0, st, win_sums, g, out_dev);
-    cudaEventRecord(ctx->ev_msm[3], st);
+    if (record_breakdown) cudaEventRecord(ctx->ev_msm[2], st);
+    DP_CUDA(ctx, cudaEventRecord(job.ev_head, st));
+    DP_CUDA(ctx, cudaStreamWaitEvent(tl, job.ev_head, 0));
+    DP_LAUNCH(msm_reduce_kernel, dim3(blocks_for(n_segs, MSM_TPB)), dim3(MSM_TPB), 0, tl, partials, task_off, g, seg_sums);
+    DP_LAUNCH(msm_window_sum_kernel, dim3(g.red_windows * g.slices), dim3(MSM_TPB), 0, tl, seg_sums, g, win_sums);
+    DP_LAUNCH(msm_final_kernel, dim3(1), dim3(32), 0, tl, win_sums, g, out_dev);
+    if (record_breakdown) cudaEventRecord(ctx->ev_msm[3], tl);
     ctx->launches += 11;
-    uint32_t err_host = 0;
-    cudaError_t e = cudaMemcpyAsync(&err_host, err, 4, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e == cudaSuccess) e = cudaGetLastError();
-    cleanup();
-    if (e != cudaSuccess) return fail(ctx, DP_E_CUDA, "msm kernels: %s", cudaGetErrorString(e));
-    for (int k = 0; k < 3; k++) cudaEventElapsedTime(&ctx->msm_ms[k], ctx->ev_msm[k], ctx->ev_msm[k + 1]);
-    if (err_host_out) *err_host_out = err_host;
-    if (err_host) return fail(ctx, DP_E_ARG, "msm: a scalar is not a canonical Fr integer (>= 2^255)");
+    DP_CUDA(ctx, cudaGetLastError());
     return DP_OK;
+}
+
+// wait for every job, collect the error flags, give the scratch back
+int msm_finish(dp_ctx *ctx, std::vector<MsmJob> &jobs, bool breakdown) {
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_tail);
+    uint32_t bad = 0;
+    for (MsmJob &j : jobs) {
+        if (e == cudaSuccess && j.err) {
+            uint32_t flag = 0;
+            e = cudaMemcpy(&flag, j.err, 4, cudaMemcpyDeviceToHost);
+            bad |= flag;
+        }
+        for (void *p : j.scratch) ctx->pool.release(p);
+        j.scratch.clear();
+        if (j.ev_head) cudaEventDestroy(j.ev_head);
+        j.ev_head = nullptr;
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, DP_E_CUDA, "msm kernels: %s", cudaGetErrorString(e));
+    if (breakdown)
+        for (int k = 0; k < 3; k++) cudaEventElapsedTime(&ctx->msm_ms[k], ctx->ev_msm[k], ctx->ev_msm[k + 1]);
+    if (bad) return fail(ctx, DP_E_ARG, "msm: a scalar is not a canonical Fr integer (>= 2^255)");
+    return DP_OK;
+}
+
+int msm_device(dp_ctx *ctx, uint64_t start, const uint4 *scalars_dev, uint64_t n, G1JacobianOut *out_dev,
+               uint32_t *err_host_out) {
+    (void)err_host_out;
+    std::vector<MsmJob> jobs(1);
+    int rc = msm_enqueue(ctx, start, scalars_dev, n, out_dev, jobs[0], n != 0);
+    int rc2 = msm_finish(ctx, jobs, rc == DP_OK && n != 0);
+    return rc != DP_OK ? rc : rc2;
 }
 
 FftTask *find_task(dp_ctx *ctx, uint64_t id) {
@@ -739,6 +774,7 @@ int dp_create(int cuda_device, uint64_t me, uint64_t n_workers, dp_ctx **out) {
         if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = DP_E_CUDA; break; }
         if (cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking) != cudaSuccess) { rc = DP_E_CUDA; break; }
         if (cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking) != cudaSuccess) { rc = DP_E_CUDA; break; }
+        if (cudaStreamCreateWithFlags(&ctx->s_tail, cudaStreamNonBlocking) != cudaSuccess) { rc = DP_E_CUDA; break; }
         cudaEventCreate(&ctx->ev0);
         cudaEventCreate(&ctx->ev1);
         for (int k = 0; k < 4; k++) cudaEventCreate(&ctx->ev_msm[k]);
@@ -784,6 +820,7 @@ int dp_destroy(dp_ctx *ctx) {
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+    if (ctx->s_tail) cudaStreamDestroy(ctx->s_tail);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (int k = 0; k < 4; k++)
@@ -797,6 +834,7 @@ int dp_sync(dp_ctx *ctx) {
     if (!ctx) return DP_E_ARG;
     DP_CUDA(ctx, cudaStreamSynchronize(ctx->s_in));
     DP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    DP_CUDA(ctx, cudaStreamSynchronize(ctx->s_tail));
     DP_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
     return DP_OK;
 }
@@ -903,6 +941,26 @@ int dp_msm_dev(dp_ctx *ctx, uint64_t start, uint64_t end, const void *scalars_de
     const uint64_t n = (end - start) < n_scalars ? (end - start) : n_scalars;
     call_begin(ctx);
     DP_TRY(msm_device(ctx, start, (const uint4 *)scalars_dev, n, (G1JacobianOut *)out_dev, nullptr));
+    return call_end(ctx, true);
+}
+
+int dp_msm_dev_batch(dp_ctx *ctx, size_t n_jobs, const uint64_t *starts, const uint64_t *ends, const void *const *scalars_dev,
+                     const size_t *n_scalars, void *const *outs_dev) {
+    if (!ctx || (n_jobs && (!starts || !ends || !scalars_dev || !n_scalars || !outs_dev))) return fail(ctx, DP_E_ARG, "dp_msm_dev_batch: NULL argument");
+    if (!ctx->inited) return fail(ctx, DP_E_STATE, "dp_msm_dev_batch before dp_init");
+    for (size_t k = 0; k < n_jobs; k++)
+        if (starts[k] > ends[k] || ends[k] > ctx->n_bases || !outs_dev[k]) return fail(ctx, DP_E_ARG, "dp_msm_dev_batch: job %zu has a bad range / output", k);
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    call_begin(ctx);
+    std::vector<MsmJob> jobs(n_jobs);
+    int rc = DP_OK;
+    for (size_t k = 0; k < n_jobs && rc == DP_OK; k++) {
+        const uint64_t n = (ends[k] - starts[k]) < n_scalars[k] ? (ends[k] - starts[k]) : n_scalars[k];
+        rc = msm_enqueue(ctx, starts[k], (const uint4 *)scalars_dev[k], n, (G1JacobianOut *)outs_dev[k], jobs[k], false);
+    }
+    int rc2 = msm_finish(ctx, jobs, false);
+    if (rc != DP_OK) return rc;
+    if (rc2 != DP_OK) return rc2;
     return call_end(ctx, true);
 }
 

@@ -158,6 +158,11 @@ int dp_debug_set_limits(dp_ctx *ctx, uint32_t max_contig_log_k, uint32_t max_str
 /* device-resident variants used by bench.py to time the kernels with inputs already in HBM.
  * All pointers are DEVICE pointers owned by the caller (e.g. torch tensors). */
 int dp_msm_dev(dp_ctx *ctx, uint64_t start, uint64_t end, const void *scalars_dev, size_t n_scalars, void *out_dev);
+/* several MSMs issued together (the commitments of one prover round, join_all in dispatcher2.rs:
+ * 316-321, 526-532): the narrow tail kernels of MSM k overlap the wide head kernels of MSM k+1.
+ * Arrays of n_jobs entries; same semantics per job as dp_msm_dev. */
+int dp_msm_dev_batch(dp_ctx *ctx, size_t n_jobs, const uint64_t *starts, const uint64_t *ends, const void *const *scalars_dev,
+                     const size_t *n_scalars, void *const *outs_dev);
 int dp_ntt_dev(dp_ctx *ctx, void *data_dev, uint32_t log_n, int is_inv, int is_coset);
 /* full 2-D pipeline of one worker on device-resident rows: rows_dev = my rows (n_rows*c Fr),
  * cols_dev receives my columns (n_cols*r Fr); n_workers must be 1 or peers attached. */

@@ -102,6 +102,18 @@ def test_msm_precomputed_window_multiples(orc, emul_lib):
     c.close()
 
 
+def test_msm_dev_batch(orc, ctx):
+    """dp_msm_dev_batch: three MSMs in flight (tails on their own stream), device pointers in/out
+    (host memory under the emulator)"""
+    bases = orc.gen_bases(5, 600, 64, True)
+    scs = [np.ascontiguousarray(orc.gen_fr(70 + k, 600, False)) for k in range(3)]
+    outs = [np.zeros(144, dtype=np.uint8) for _ in range(3)]
+    ranges = [(0, 600), (100, 400), (0, 0)]
+    ctx.msm_dev_batch([(lo, hi, scs[k].ctypes.data, hi - lo, outs[k].ctypes.data) for k, (lo, hi) in enumerate(ranges)])
+    for k, (lo, hi) in enumerate(ranges):
+        common.assert_point_eq(orc, outs[k], orc.msm(bases[lo:hi], scs[k][: hi - lo]), f"batch job {k}")
+
+
 def test_msm_edges(orc, ctx):
     bases = orc.gen_bases(5, 600, 64, True)
     sc = orc.gen_fr(9, 600, False)

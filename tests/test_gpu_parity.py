@@ -147,6 +147,19 @@ def test_msm_every_window_geometry(orc, ctx, bases, c):
         ctx.debug_set_limits(11, 9, 0)
 
 
+def test_msm_dev_batch(orc, ctx, bases):
+    """a round's commitments issued together (dp_msm_dev_batch): device pointers, tails overlapped"""
+    n = (1 << 16) + 32
+    scs = [orc.gen_fr(900 + k, n, False) for k in range(5)]
+    dev = [torch.from_numpy(s.view(np.int64)).cuda() for s in scs]
+    outs = [torch.zeros(18, dtype=torch.int64, device="cuda") for _ in range(5)]
+    ranges = [(0, n), (0, n), (5, 60000), (0, n), (n - 100, n)]
+    ctx.msm_dev_batch([(lo, hi, dev[k].data_ptr(), hi - lo, outs[k].data_ptr()) for k, (lo, hi) in enumerate(ranges)])
+    for k, (lo, hi) in enumerate(ranges):
+        got = outs[k].cpu().numpy().view(np.uint8)
+        common.assert_point_eq(orc, got, orc.msm(bases[lo:hi], scs[k][: hi - lo]), f"batch job {k}")
+
+
 def test_msm_edges(orc, ctx, bases):
     sc = orc.gen_fr(9, 600, False)
     assert orc.normalize(ctx.msm(10, 10, sc[:0]))[96] == 1

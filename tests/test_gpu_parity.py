@@ -245,6 +245,24 @@ def test_full_size_msm_2p20_vs_oracle_and_linearity(orc, gpu_lib):
         c.close()
 
 
+def test_full_size_msm_2p22_vs_oracle(orc, gpu_lib):
+    """BASELINE's headline size: MSM over 2^22+32 DISTINCT bases (the synthetic SRS bench.py uses,
+    generated on the device; points checked on-curve by the oracle's own arithmetic when it adds
+    them) against the oracle's Pippenger, uniform and witness-like scalars."""
+    n = (1 << 22) + 32
+    c = Context(gpu_lib, 0, 0, 1)
+    try:
+        bases = c.gen_bases(0xD15791B07E5EED, n)
+        bases[3, :] = 0
+        bases[3, 96] = 1                       # infinity at index 3 (dispatcher2.rs:1100-1101)
+        c.init(bases, 1 << 10, 1 << 13)
+        for name, sc in common.scalar_sets(orc, n, 4242).items():
+            if name in ("uniform", "witness-like"):
+                common.assert_point_eq(orc, c.msm(0, n, sc), orc.msm(bases, sc), f"msm 2^22+32 {name}")
+    finally:
+        c.close()
+
+
 def test_full_size_ntt_2p25_roundtrip_and_spot_checks(orc, gpu_lib):
     """quotient-domain size of the 2^22-gate config: coset NTT of an n-coefficient polynomial on
     the 8n domain through the worker path; spot-check outputs by O(N) Horner evaluation, then the

@@ -585,10 +585,11 @@ int msm_enqueue(dp_ctx *ctx, uint64_t start, const uint4 *scalars_dev, uint64_t 
                               : msm_geometry(n, ctx->msm_force_c > 1 ? ctx->msm_force_c : 0);
     const G1Affine *bases = use_pre ? ctx->pre_table + (start - ctx->pre_lo) : ctx->bases + start;
     const uint64_t max_digits = n * g.n_windows;
-    const uint64_t max_tasks = (uint64_t)g.n_keys + max_digits / MSM_TSEG + 1;
+    const uint64_t max_chunks = max_digits / MSM_CHUNK + 1;
+    const uint64_t n_slots = max_chunks + g.n_keys;  // partial (chunk j, bucket b) lives in slot j + b
     const uint32_t n_segs = g.red_windows * g.segs_per_window;
     const uint32_t n_scan_blocks = (g.n_keys + SCAN_BLOCK - 1) / SCAN_BLOCK;
-    const uint64_t max_multi = max_digits / MSM_TSEG + 1;  // a bucket with > TSEG points
+    const uint64_t max_multi = max_chunks / MSM_BIG_SPAN + 1;  // buckets spread over > BIG_SPAN chunks
     bool oom = false;
     auto grab = [&](size_t bytes) -> void * {
         void *p = ctx->pool.alloc(bytes);
@@ -599,13 +600,11 @@ int msm_enqueue(dp_ctx *ctx, uint64_t start, const uint4 *scalars_dev, uint64_t 
     uint32_t *counts = (uint32_t *)grab((g.n_keys + 1) * 4ull);
     uint32_t *offsets = (uint32_t *)grab((g.n_keys + 1) * 4ull);
     uint32_t *cursor = (uint32_t *)grab((g.n_keys + 1) * 4ull);
-    uint32_t *task_off = (uint32_t *)grab((g.n_keys + 1) * 4ull);
     uint32_t *sorted = (uint32_t *)grab(max_digits * 4ull);
-    uint2 *tasks = (uint2 *)grab(max_tasks * sizeof(uint2));
-    G1XYZZ *partials = (G1XYZZ *)grab(max_tasks * sizeof(G1XYZZ));
+    G1XYZZ *partials = (G1XYZZ *)grab(n_slots * sizeof(G1XYZZ));
     G1XYZZ *seg_sums = (G1XYZZ *)grab((uint64_t)n_segs * sizeof(G1XYZZ));
     G1XYZZ *win_sums = (G1XYZZ *)grab((uint64_t)g.red_windows * g.slices * sizeof(G1XYZZ));
-    uint2 *block_sums = (uint2 *)grab((size_t)n_scan_blocks * sizeof(uint2));
+    uint32_t *block_sums = (uint32_t *)grab((size_t)n_scan_blocks * 4ull);
     uint32_t *multi_keys = (uint32_t *)grab((max_multi + 1) * 4ull);  // [0] = counter, then keys
     job.err = (uint32_t *)grab(4);
     if (oom) return fail(ctx, DP_E_OOM, "msm scratch for %llu points", (unsigned long long)n);
@@ -616,21 +615,20 @@ int msm_enqueue(dp_ctx *ctx, uint64_t start, const uint4 *scalars_dev, uint64_t 
     cudaMemsetAsync(multi_keys, 0, 4, st);
     DP_LAUNCH(msm_count_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, scalars_dev, n, g, counts, job.err);
     DP_LAUNCH(scan_block_sums_kernel, dim3(n_scan_blocks), dim3(SCAN_TPB), 0, st, counts, g.n_keys, block_sums);
-    DP_LAUNCH(scan_block_offsets_kernel, dim3(1), dim3(SCAN_TPB), 0, st, block_sums, n_scan_blocks, offsets, task_off, g.n_keys);
-    DP_LAUNCH(scan_write_kernel, dim3(n_scan_blocks), dim3(SCAN_TPB), 0, st, counts, g.n_keys, block_sums, offsets, task_off);
+    DP_LAUNCH(scan_block_offsets_kernel, dim3(1), dim3(SCAN_TPB), 0, st, block_sums, n_scan_blocks, offsets, g.n_keys);
+    DP_LAUNCH(scan_write_kernel, dim3(n_scan_blocks), dim3(SCAN_TPB), 0, st, counts, g.n_keys, block_sums, offsets);
     cudaMemcpyAsync(cursor, offsets, (g.n_keys + 1) * 4ull, cudaMemcpyDeviceToDevice, st);
     DP_LAUNCH(msm_scatter_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, scalars_dev, n, g, cursor, sorted);
-    DP_LAUNCH(msm_tasks_kernel, dim3(blocks_for(g.n_keys, 256)), dim3(256), 0, st, offsets, task_off, g.n_keys, tasks,
-              multi_keys + 1, multi_keys);
+    DP_LAUNCH(msm_find_big_kernel, dim3(blocks_for(g.n_keys, 256)), dim3(256), 0, st, offsets, g.n_keys, multi_keys + 1, multi_keys);
     if (record_breakdown) cudaEventRecord(ctx->ev_msm[1], st);
-    DP_LAUNCH(msm_accumulate_kernel, dim3(blocks_for(max_tasks, MSM_TPB)), dim3(MSM_TPB), 0, st, tasks,
-              task_off + g.n_keys, sorted, bases, partials);
+    DP_LAUNCH(msm_accumulate_kernel, dim3(blocks_for(max_chunks, MSM_TPB)), dim3(MSM_TPB), 0, st, offsets, g.n_keys, sorted, bases,
+              partials);
     DP_LAUNCH(msm_collapse_kernel, dim3(max_multi * 32 < 148ull * 8 * MSM_TPB ? blocks_for(max_multi * 32, MSM_TPB) : 148 * 8),
-              dim3(MSM_TPB), 0, st, multi_keys + 1, multi_keys, task_off, partials);
+              dim3(MSM_TPB), 0, st, multi_keys + 1, multi_keys, offsets, partials);
     if (record_breakdown) cudaEventRecord(ctx->ev_msm[2], st);
     DP_CUDA(ctx, cudaEventRecord(job.ev_head, st));
     DP_CUDA(ctx, cudaStreamWaitEvent(tl, job.ev_head, 0));
-    DP_LAUNCH(msm_reduce_kernel, dim3(blocks_for(n_segs, MSM_TPB)), dim3(MSM_TPB), 0, tl, partials, task_off, g, seg_sums);
+    DP_LAUNCH(msm_reduce_kernel, dim3(blocks_for(n_segs, MSM_TPB)), dim3(MSM_TPB), 0, tl, partials, offsets, g, seg_sums);
     DP_LAUNCH(msm_window_sum_kernel, dim3(g.red_windows * g.slices), dim3(MSM_TPB), 0, tl, seg_sums, g, win_sums);
     DP_LAUNCH(msm_final_kernel, dim3(1), dim3(32), 0, tl, win_sums, g, out_dev);
     if (record_breakdown) cudaEventRecord(ctx->ev_msm[3], tl);

@@ -9,14 +9,15 @@
 //
 //   1. msm_count      signed-digit recode (digits in [-2^(c-1), 2^(c-1)]), histogram of
 //                     (window, |digit|) keys with L2 atomics; 128-bit coalesced scalar loads
-//   2. scan (3 kernels) exclusive prefix sums -> bucket offsets and task offsets
+//   2. scan (3 kernels) exclusive prefix sums -> bucket offsets
 //   3. msm_scatter    counting-sort the point indices by key (sign kept in bit 31)
-//   4. msm_tasks      cut every bucket into tasks of <= TSEG points (load balance for skewed
-//                     scalars: witness vectors are full of 0/1/small values)
-//   5. msm_accumulate one thread per task: XYZZ accumulator in registers, mixed additions of the
-//                     gathered affine bases (96 B = 6 x 128-bit loads each)
-//   5b. msm_collapse  buckets that were cut into several tasks: one warp per bucket, lanes
-//                     stride over its partial sums, warp-shuffle butterfly reduction
+//   4. msm_accumulate one thread per CHUNK of 64 sorted digits (chunks ignore bucket boundaries, so
+//                     every lane does the same number of additions whatever the scalars look
+//                     like): XYZZ accumulator in registers, mixed additions of the gathered affine
+//                     bases (96 B = 6 x 128-bit loads each), one partial sum per bucket touched
+//   5. msm_collapse   buckets spread over many chunks (witness vectors are full of 0/1/small
+//                     values): one warp per bucket, lanes stride over its partial sums,
+//                     warp-shuffle butterfly reduction
 //   6. msm_reduce     per window, per segment of buckets: running-sum reduction
 //                     sum_k k*B_k (+ small scalar multiple for the segment offset)
 //   7. msm_window_sum block per window: tree reduction of the segment sums
@@ -33,7 +34,8 @@
 
 namespace dp {
 
-constexpr uint32_t MSM_TSEG = 256;      // max points per accumulate task
+constexpr uint32_t MSM_CHUNK = 64;      // sorted digits per accumulate thread (chunks ignore bucket boundaries)
+constexpr uint32_t MSM_BIG_SPAN = 8;    // buckets spread over more chunks than this are folded by a warp first
 constexpr uint32_t MSM_SEG = 16;        // buckets per reduce segment
 constexpr int MSM_TPB = 128;
 
@@ -221,14 +223,11 @@ __global__ void msm_scatter_kernel(const uint4 *scalars, uint64_t n, MsmGeom g, 
     });
 }
 
-// ------------------------------------------------------------------ exclusive scans (3 phases)
-// offsets[i]  = sum_{k<i} counts[k]                  (bucket start in sorted[])
-// task_off[i] = sum_{k<i} ceil(counts[k] / TSEG)     (first task of bucket i)     for i <= n
+// ------------------------------------------------------------------ exclusive scan (3 phases)
+// offsets[i] = sum_{k<i} counts[k]  (bucket start in sorted[]) for i <= n; offsets[n] = number of digits
 constexpr int SCAN_TPB = 256;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_BLOCK = SCAN_TPB * SCAN_ITEMS;
-
-DP_D uint32_t tasks_of(uint32_t cnt) { return (cnt + MSM_TSEG - 1) / MSM_TSEG; }
 
 // block-wide exclusive scan of one value per thread (Hillis-Steele in shared memory); returns the
 // exclusive prefix of this thread and the block total
@@ -248,94 +247,75 @@ DP_D uint32_t block_exclusive_scan(uint32_t v, uint32_t *sh, uint32_t &total) {
     return excl;
 }
 
-__global__ void __launch_bounds__(SCAN_TPB) scan_block_sums_kernel(const uint32_t *counts, uint32_t n, uint2 *block_sums) {
+__global__ void __launch_bounds__(SCAN_TPB) scan_block_sums_kernel(const uint32_t *counts, uint32_t n, uint32_t *block_sums) {
     __shared__ uint32_t sh[SCAN_TPB];
     const uint32_t base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
-    uint32_t a = 0, t = 0;
+    uint32_t a = 0;
     for (int k = 0; k < SCAN_ITEMS; k++)
-        if (base + k < n) {
-            const uint32_t c = counts[base + k];
-            a += c;
-            t += tasks_of(c);
-        }
-    uint32_t ta, tt;
+        if (base + k < n) a += counts[base + k];
+    uint32_t ta;
     block_exclusive_scan(a, sh, ta);
-    block_exclusive_scan(t, sh, tt);
-    if (threadIdx.x == 0) {
-        uint2 r;
-        r.x = ta;
-        r.y = tt;
-        block_sums[blockIdx.x] = r;
-    }
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = ta;
 }
 
-// single block: exclusive scan of the per-block sums in place; grand totals -> offsets[n], task_off[n]
-__global__ void __launch_bounds__(SCAN_TPB) scan_block_offsets_kernel(uint2 *block_sums, uint32_t n_blocks, uint32_t *offsets,
-                                                                       uint32_t *task_off, uint32_t n) {
+// single block: exclusive scan of the per-block sums in place; grand total -> offsets[n]
+__global__ void __launch_bounds__(SCAN_TPB) scan_block_offsets_kernel(uint32_t *block_sums, uint32_t n_blocks, uint32_t *offsets,
+                                                                       uint32_t n) {
     __shared__ uint32_t sh[SCAN_TPB];
-    uint32_t run_a = 0, run_t = 0;
+    uint32_t run = 0;
     for (uint32_t base = 0; base < n_blocks; base += SCAN_TPB) {
         const uint32_t i = base + threadIdx.x;
-        uint2 v;
-        v.x = v.y = 0;
-        if (i < n_blocks) v = block_sums[i];
-        uint32_t ta, tt;
-        const uint32_t ea = block_exclusive_scan(v.x, sh, ta);
-        const uint32_t et = block_exclusive_scan(v.y, sh, tt);
-        if (i < n_blocks) {
-            uint2 o;
-            o.x = run_a + ea;
-            o.y = run_t + et;
-            block_sums[i] = o;
-        }
-        run_a += ta;
-        run_t += tt;
+        const uint32_t v = i < n_blocks ? block_sums[i] : 0;
+        uint32_t total;
+        const uint32_t e = block_exclusive_scan(v, sh, total);
+        if (i < n_blocks) block_sums[i] = run + e;
+        run += total;
     }
-    if (threadIdx.x == 0) {
-        offsets[n] = run_a;
-        task_off[n] = run_t;
-    }
+    if (threadIdx.x == 0) offsets[n] = run;
 }
 
-__global__ void __launch_bounds__(SCAN_TPB) scan_write_kernel(const uint32_t *counts, uint32_t n, const uint2 *block_sums,
-                                                               uint32_t *offsets, uint32_t *task_off) {
+__global__ void __launch_bounds__(SCAN_TPB) scan_write_kernel(const uint32_t *counts, uint32_t n, const uint32_t *block_sums,
+                                                               uint32_t *offsets) {
     __shared__ uint32_t sh[SCAN_TPB];
     const uint32_t base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
     uint32_t c[SCAN_ITEMS];
-    uint32_t a = 0, t = 0;
+    uint32_t a = 0;
     for (int k = 0; k < SCAN_ITEMS; k++) {
         c[k] = base + k < n ? counts[base + k] : 0;
         a += c[k];
-        t += tasks_of(c[k]);
     }
-    uint32_t ta, tt;
-    uint32_t ea = block_exclusive_scan(a, sh, ta) + block_sums[blockIdx.x].x;
-    uint32_t et = block_exclusive_scan(t, sh, tt) + block_sums[blockIdx.x].y;
+    uint32_t total;
+    uint32_t e = block_exclusive_scan(a, sh, total) + block_sums[blockIdx.x];
     for (int k = 0; k < SCAN_ITEMS; k++)
         if (base + k < n) {
-            offsets[base + k] = ea;
-            task_off[base + k] = et;
-            ea += c[k];
-            et += tasks_of(c[k]);
+            offsets[base + k] = e;
+            e += c[k];
         }
 }
 
-// ------------------------------------------------------------------ tasks
-// tasks[t] = {first index into sorted[], number of points}; bucket `key` owns tasks
-// [task_off[key], task_off[key+1])
-__global__ void msm_tasks_kernel(const uint32_t *offsets, const uint32_t *task_off, uint32_t n_keys, uint2 *tasks,
-                                 uint32_t *multi_keys, uint32_t *n_multi) {
+// ------------------------------------------------------------------ chunks
+// The sorted digit array is cut into chunks of MSM_CHUNK entries regardless of bucket boundaries, one
+// thread per chunk: every thread does the same number of additions (with one thread per bucket
+// the Poisson spread of bucket sizes left 18 % of the lanes idle, ncu: 26.1 active threads per
+// warp instruction).  A chunk that crosses bucket boundaries emits one partial sum per bucket it
+// touches; the partial of (chunk j, bucket b) lives in slot j + b, which is unique and dense along
+// the staircase of (chunk, bucket) pairs.  Bucket b therefore owns slots j0+b .. j1+b with
+// j0 = offsets[b] / CHUNK, j1 = (offsets[b+1]-1) / CHUNK.
+DP_D void bucket_span(const uint32_t *offsets, uint32_t key, uint32_t &j0, uint32_t &j1, bool &empty) {
+    const uint32_t lo = offsets[key], hi = offsets[key + 1];
+    empty = lo == hi;
+    j0 = lo / MSM_CHUNK;
+    j1 = empty ? j0 : (hi - 1) / MSM_CHUNK;
+}
+
+// buckets spread over many chunks (skewed scalars) are listed for msm_collapse
+__global__ void msm_find_big_kernel(const uint32_t *offsets, uint32_t n_keys, uint32_t *multi_keys, uint32_t *n_multi) {
     const uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
     if (key >= n_keys) return;
-    const uint32_t start = offsets[key], cnt = offsets[key + 1] - start;
-    uint32_t t = task_off[key];
-    if (cnt > MSM_TSEG) multi_keys[atomicAdd(n_multi, 1u)] = key;  // needs msm_collapse below
-    for (uint32_t done = 0; done < cnt; done += MSM_TSEG, t++) {
-        uint2 e;
-        e.x = start + done;
-        e.y = cnt - done < MSM_TSEG ? cnt - done : MSM_TSEG;
-        tasks[t] = e;
-    }
+    uint32_t j0, j1;
+    bool empty;
+    bucket_span(offsets, key, j0, j1, empty);
+    if (!empty && j1 - j0 + 1 > MSM_BIG_SPAN) multi_keys[atomicAdd(n_multi, 1u)] = key;
 }
 
 DP_D G1Affine load_affine(const G1Affine *p) {
@@ -350,21 +330,36 @@ DP_D G1Affine load_affine(const G1Affine *p) {
     return r;
 }
 
-__global__ void __launch_bounds__(MSM_TPB) msm_accumulate_kernel(const uint2 *tasks, const uint32_t *n_tasks,
-                                                                  const uint32_t *sorted, const G1Affine *bases,
-                                                                  G1XYZZ *partials) {
-    // the grid is sized for the worst case; the real task count is only known on the device
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= *n_tasks) return;
-    const uint2 task = tasks[t];
+__global__ void __launch_bounds__(MSM_TPB) msm_accumulate_kernel(const uint32_t *offsets, uint32_t n_keys, const uint32_t *sorted,
+                                                                  const G1Affine *bases, G1XYZZ *partials) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_digits = offsets[n_keys];  // the grid is sized for the worst case
+    const uint64_t pos0 = (uint64_t)j * MSM_CHUNK;
+    if (pos0 >= n_digits) return;
+    const uint32_t pos1 = pos0 + MSM_CHUNK < n_digits ? (uint32_t)pos0 + MSM_CHUNK : n_digits;
+    // bucket holding the first digit: largest b with offsets[b] <= pos0 (skips empty buckets)
+    uint32_t lo = 0, hi = n_keys;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (offsets[mid] <= (uint32_t)pos0) lo = mid; else hi = mid;
+    }
+    uint32_t b = lo, next = offsets[b + 1];
     G1XYZZ acc = G1XYZZ::inf();
-    for (uint32_t k = 0; k < task.y; k++) {
-        const uint32_t e = sorted[task.x + k];
-        G1Affine p = load_affine(bases + (e & 0x7fffffffu));
-        if (e >> 31) p = p.neg();
+    for (uint32_t e = (uint32_t)pos0; e < pos1; e++) {
+        if (e == next) {  // leaving bucket b: emit its partial, move to the bucket that holds digit e
+            partials[j + b] = acc;
+            acc = G1XYZZ::inf();
+            do {
+                b++;
+                next = offsets[b + 1];
+            } while (next == e);
+        }
+        const uint32_t v = sorted[e];
+        G1Affine p = load_affine(bases + (v & 0x7fffffffu));
+        if (v >> 31) p = p.neg();
         acc = acc.add_mixed(p);
     }
-    partials[t] = acc;
+    partials[j + b] = acc;
 }
 
 // Buckets cut into several tasks (skewed scalars: one bucket can hold a large share of all points)
@@ -385,23 +380,31 @@ DP_D G1XYZZ shfl_xor_point(const G1XYZZ &p, int mask) {
     return r;
 }
 __global__ void __launch_bounds__(MSM_TPB) msm_collapse_kernel(const uint32_t *multi_keys, const uint32_t *n_multi,
-                                                                const uint32_t *task_off, G1XYZZ *partials) {
+                                                                const uint32_t *offsets, G1XYZZ *partials) {
     // fixed-size grid, warps loop over the (usually empty) list: the count is only known on the device
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5, lane = threadIdx.x & 31;
     for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < *n_multi; w += n_warps) {  // warp-uniform
         const uint32_t key = multi_keys[w];
-        const uint32_t t0 = task_off[key], t1 = task_off[key + 1];
+        uint32_t j0, j1;
+        bool empty;
+        bucket_span(offsets, key, j0, j1, empty);
         G1XYZZ acc = G1XYZZ::inf();
-        for (uint32_t t = t0 + lane; t < t1; t += 32) acc = acc.add(partials[t]);
+        for (uint32_t j = j0 + lane; j <= j1; j += 32) acc = acc.add(partials[j + key]);
         for (int m = 16; m >= 1; m >>= 1) acc = acc.add(shfl_xor_point(acc, m));
-        if (lane == 0) partials[t0] = acc;
+        if (lane == 0) partials[j0 + key] = acc;
     }
 }
 
-// sum of one bucket: its (single, or collapsed) partial sum
-DP_D G1XYZZ bucket_sum(const G1XYZZ *partials, const uint32_t *task_off, uint32_t key) {
-    const uint32_t t0 = task_off[key];
-    return t0 < task_off[key + 1] ? partials[t0] : G1XYZZ::inf();
+// sum of one bucket: its few partial sums, or the folded one when msm_collapse handled it
+DP_D G1XYZZ bucket_sum(const G1XYZZ *partials, const uint32_t *offsets, uint32_t key) {
+    uint32_t j0, j1;
+    bool empty;
+    bucket_span(offsets, key, j0, j1, empty);
+    if (empty) return G1XYZZ::inf();
+    G1XYZZ b = partials[j0 + key];
+    if (j1 - j0 + 1 <= MSM_BIG_SPAN)
+        for (uint32_t j = j0 + 1; j <= j1; j++) b = b.add(partials[j + key]);
+    return b;
 }
 
 // k * P for a small non-negative integer k
@@ -415,7 +418,7 @@ DP_D G1XYZZ small_mul(const G1XYZZ &p, uint32_t k) {
 }
 
 // one thread per (window, segment): sum_{k in segment} k * B_k with the running-sum trick
-__global__ void __launch_bounds__(MSM_TPB) msm_reduce_kernel(const G1XYZZ *partials, const uint32_t *task_off, MsmGeom g,
+__global__ void __launch_bounds__(MSM_TPB) msm_reduce_kernel(const G1XYZZ *partials, const uint32_t *offsets, MsmGeom g,
                                                               G1XYZZ *seg_sums) {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= g.red_windows * g.segs_per_window) return;
@@ -423,7 +426,7 @@ __global__ void __launch_bounds__(MSM_TPB) msm_reduce_kernel(const G1XYZZ *parti
     const uint32_t lo = sgm * g.seg;  // buckets lo+1 .. lo+seg of this window (bucket k <-> digit k)
     G1XYZZ running = G1XYZZ::inf(), acc = G1XYZZ::inf();
     for (uint32_t k = g.seg; k >= 1; k--) {
-        running = running.add(bucket_sum(partials, task_off, w * g.bpw + lo + k - 1));
+        running = running.add(bucket_sum(partials, offsets, w * g.bpw + lo + k - 1));
         acc = acc.add(running);
     }
     if (lo) acc = acc.add(small_mul(running, lo));

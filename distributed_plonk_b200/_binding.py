@@ -13,7 +13,7 @@ EXPORTS = [
     "dp_fft1", "dp_fft1_rows", "dp_fft2_prepare", "dp_fft_exchange_begin", "dp_fft_exchange_end", "dp_fft2",
     "dp_ntt", "dp_round1", "dp_get_wire", "dp_peer_arena_create", "dp_peer_attach", "dp_last_timing",
     "dp_launch_count", "dp_sync", "dp_msm_dev", "dp_ntt_dev", "dp_fft_dev", "dp_debug_set_limits",
-    "dp_last_msm_breakdown", "dp_debug_gen_bases", "dp_fft_dev_rows", "dp_fft_dev_cols", "dp_peer_ready", "dp_fft_dev_rows_p2p", "dp_msm_dev_batch",
+    "dp_last_msm_breakdown", "dp_debug_gen_bases", "dp_fft_dev_rows", "dp_fft_dev_cols", "dp_peer_ready", "dp_fft_dev_rows_p2p", "dp_msm_dev_batch", "dp_perm_product",
 ]
 
 
@@ -62,6 +62,7 @@ def bind(cdll: C.CDLL) -> C.CDLL:
         "dp_fft_dev_rows": (i, [vp, vp, i, i, i, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]),
         "dp_fft_dev_cols": (i, [vp, vp]),
         "dp_peer_ready": (i, [vp]),
+        "dp_perm_product": (i, [vp, vp, vp, vp, sz, sz, vp, vp, vp]),
         "dp_msm_dev_batch": (i, [vp, sz, C.POINTER(u64), C.POINTER(u64), C.POINTER(vp), C.POINTER(sz), C.POINTER(vp)]),
         "dp_fft_dev_rows_p2p": (i, [vp, vp, i, i, i]),
     }
@@ -170,6 +171,14 @@ class Context:
         out = np.zeros(G1_PROJECTIVE_BYTES, dtype=np.uint8)
         b = np.ascontiguousarray(blind) if blind is not None else None
         self._ck(self.lib.dp_round1(self.h, _addr(evals), evals.nbytes // 32, _addr(b) if b is not None else None, _addr(out)))
+        return out
+
+    def perm_product(self, wires: np.ndarray, id_perm: np.ndarray, sigma_perm: np.ndarray, beta: np.ndarray, gamma: np.ndarray) -> np.ndarray:
+        """round-2 grand product (dispatcher2.rs:329-345); inputs [n_types, n, 4] u64 raw Fr"""
+        a = [np.ascontiguousarray(x, dtype=np.uint64) for x in (wires, id_perm, sigma_perm, beta, gamma)]
+        n_types, n = a[0].shape[0], a[0].shape[1]
+        out = np.empty((n, 4), dtype=np.uint64)
+        self._ck(self.lib.dp_perm_product(self.h, _addr(a[0]), _addr(a[1]), _addr(a[2]), n_types, n, _addr(a[3]), _addr(a[4]), _addr(out)))
         return out
 
     def get_wire(self) -> np.ndarray:

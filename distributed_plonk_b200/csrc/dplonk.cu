@@ -13,6 +13,7 @@
 
 #include "msm.cuh"
 #include "ntt.cuh"
+#include "perm.cuh"
 
 using namespace dp;
 
@@ -134,6 +135,7 @@ struct dp_ctx {
     int dev_flags = -1;
     // pass-planning limits (dp_debug_set_limits lowers them so small tests reach the multi-pass plans)
     uint32_t max_contig_log_k = NTT_WTAB_LOG, max_strided_log_k = NTT_MAX_STRIDED_LOG_K;
+    uint32_t msm_chunk = 0;    // experiment knob (env DP_MSM_CHUNK): digits per accumulate thread, 0 = default
     int msm_force_c = 0;       // 0 auto, 1 = windowed path with automatic c, >= 2 forced c (windowed)
     bool pre_disabled = false;
 };
@@ -581,11 +583,12 @@ int msm_enqueue(dp_ctx *ctx, uint64_t start, const uint4 *scalars_dev, uint64_t 
     // precomputed window multiples pay off once the shared bucket set is reasonably filled
     const bool use_pre = ctx->pre_table && ctx->msm_force_c == 0 && start >= ctx->pre_lo && start + n <= ctx->pre_hi &&
                          n * ctx->pre_nw >= 4ull * (1ull << (ctx->pre_c - 1));
-    const MsmGeom g = use_pre ? msm_make_geom(ctx->pre_c, true, ctx->pre_hi - ctx->pre_lo)
-                              : msm_geometry(n, ctx->msm_force_c > 1 ? ctx->msm_force_c : 0);
+    MsmGeom g = use_pre ? msm_make_geom(ctx->pre_c, true, ctx->pre_hi - ctx->pre_lo)
+                        : msm_geometry(n, ctx->msm_force_c > 1 ? ctx->msm_force_c : 0);
+    if (ctx->msm_chunk) g.chunk = ctx->msm_chunk;
     const G1Affine *bases = use_pre ? ctx->pre_table + (start - ctx->pre_lo) : ctx->bases + start;
     const uint64_t max_digits = n * g.n_windows;
-    const uint64_t max_chunks = max_digits / MSM_CHUNK + 1;
+    const uint64_t max_chunks = max_digits / g.chunk + 1;
     const uint64_t n_slots = max_chunks + g.n_keys;  // partial (chunk j, bucket b) lives in slot j + b
     const uint32_t n_segs = g.red_windows * g.segs_per_window;
     const uint32_t n_scan_blocks = (g.n_keys + SCAN_BLOCK - 1) / SCAN_BLOCK;
@@ -619,12 +622,13 @@ int msm_enqueue(dp_ctx *ctx, uint64_t start, const uint4 *scalars_dev, uint64_t 
     DP_LAUNCH(scan_write_kernel, dim3(n_scan_blocks), dim3(SCAN_TPB), 0, st, counts, g.n_keys, block_sums, offsets);
     cudaMemcpyAsync(cursor, offsets, (g.n_keys + 1) * 4ull, cudaMemcpyDeviceToDevice, st);
     DP_LAUNCH(msm_scatter_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, scalars_dev, n, g, cursor, sorted);
-    DP_LAUNCH(msm_find_big_kernel, dim3(blocks_for(g.n_keys, 256)), dim3(256), 0, st, offsets, g.n_keys, multi_keys + 1, multi_keys);
+    DP_LAUNCH(msm_find_big_kernel, dim3(blocks_for(g.n_keys, 256)), dim3(256), 0, st, offsets, g.n_keys, g.chunk, multi_keys + 1,
+              multi_keys);
     if (record_breakdown) cudaEventRecord(ctx->ev_msm[1], st);
-    DP_LAUNCH(msm_accumulate_kernel, dim3(blocks_for(max_chunks, MSM_TPB)), dim3(MSM_TPB), 0, st, offsets, g.n_keys, sorted, bases,
-              partials);
+    DP_LAUNCH(msm_accumulate_kernel, dim3(blocks_for(max_chunks, MSM_TPB)), dim3(MSM_TPB), 0, st, offsets, g.n_keys, g.chunk, sorted,
+              bases, partials);
     DP_LAUNCH(msm_collapse_kernel, dim3(max_multi * 32 < 148ull * 8 * MSM_TPB ? blocks_for(max_multi * 32, MSM_TPB) : 148 * 8),
-              dim3(MSM_TPB), 0, st, multi_keys + 1, multi_keys, offsets, partials);
+              dim3(MSM_TPB), 0, st, multi_keys + 1, multi_keys, offsets, g.chunk, partials);
     if (record_breakdown) cudaEventRecord(ctx->ev_msm[2], st);
     DP_CUDA(ctx, cudaEventRecord(job.ev_head, st));
     DP_CUDA(ctx, cudaStreamWaitEvent(tl, job.ev_head, 0));
@@ -764,6 +768,7 @@ int dp_create(int cuda_device, uint64_t me, uint64_t n_workers, dp_ctx **out) {
     if (prop.major < 10) return fail(nullptr, DP_E_CUDA, "dp_create: device %d is sm_%d%d, need sm_100", cuda_device, prop.major, prop.minor);
     dp_ctx *ctx = new dp_ctx();
     ctx->device = cuda_device;
+    if (const char *e = getenv("DP_MSM_CHUNK")) ctx->msm_chunk = (uint32_t)atoi(e) >= 8 ? (uint32_t)atoi(e) : 0;
     ctx->me = me;
     ctx->W = n_workers;
     int rc = DP_OK;
@@ -1313,6 +1318,85 @@ int dp_round1(dp_ctx *ctx, const void *evals, size_t n, const void *blind, void 
     }
     if (rc == DP_OK) rc = call_end(ctx, true);
     ctx->pool.release(od);
+    return rc;
+}
+
+// multiplicative scan of n Fr on the compute stream: out[i] = product of the logical elements before
+// (exclusive) or up to (inclusive) i, logical order reversed when `reverse`; *total_dev = whole product
+static int perm_scan(dp_ctx *ctx, const Fr *x, uint64_t n, bool reverse, bool inclusive, Fr *out, Fr *total_dev) {
+    const uint32_t n_blocks = (uint32_t)((n + PERM_BLOCK - 1) / PERM_BLOCK);
+    Fr *block_tot = (Fr *)ctx->pool.alloc((size_t)n_blocks * sizeof(Fr));
+    if (!block_tot) return fail(ctx, DP_E_OOM, "perm scan scratch");
+    DP_LAUNCH(perm_block_products_kernel, dim3(n_blocks), dim3(PERM_TPB), 0, ctx->stream, x, n, reverse ? 1u : 0u, block_tot);
+    DP_LAUNCH(perm_block_offsets_kernel, dim3(1), dim3(PERM_TPB), 0, ctx->stream, block_tot, n_blocks, total_dev);
+    DP_LAUNCH(perm_scan_write_kernel, dim3(n_blocks), dim3(PERM_TPB), 0, ctx->stream, x, n, reverse ? 1u : 0u, inclusive ? 1u : 0u,
+              (const Fr *)block_tot, out);
+    ctx->launches += 3;
+    ctx->pool.release(block_tot);
+    DP_CUDA(ctx, cudaGetLastError());
+    return DP_OK;
+}
+
+static int perm_product_device(dp_ctx *ctx, const Fr *wires, const Fr *id, const Fr *sigma, uint32_t n_types, uint64_t n,
+                               const Fr &beta, const Fr &gamma, Fr *z_dev) {
+    Fr *a = (Fr *)ctx->pool.alloc(n * sizeof(Fr)), *b = (Fr *)ctx->pool.alloc(n * sizeof(Fr));
+    Fr *tot = (Fr *)ctx->pool.alloc(2 * sizeof(Fr));
+    int rc = DP_OK;
+    if (!a || !b || !tot) rc = fail(ctx, DP_E_OOM, "dp_perm_product scratch");
+    if (rc == DP_OK) {
+        DP_LAUNCH(perm_terms_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, ctx->stream, wires, id, sigma, n_types, n, beta, gamma, a, b);
+        ctx->launches++;
+        rc = perm_scan(ctx, a, n, false, false, a, tot);          // a <- exclusive prefix products (in place)
+    }
+    if (rc == DP_OK) rc = perm_scan(ctx, b, n, true, true, b, tot + 1);  // b <- inclusive suffix products; tot[1] = T
+    if (rc == DP_OK) {
+        DP_LAUNCH(perm_invert_kernel, dim3(1), dim3(32), 0, ctx->stream, tot + 1);
+        DP_LAUNCH(perm_finish_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, ctx->stream, (const Fr *)a, (const Fr *)b,
+                  (const Fr *)(tot + 1), n, z_dev);
+        ctx->launches += 2;
+        Fr t_inv;
+        cudaError_t e = cudaMemcpyAsync(&t_inv, tot + 1, sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) rc = fail(ctx, DP_E_CUDA, "dp_perm_product: %s", cudaGetErrorString(e));
+        else if (t_inv.is_zero()) rc = fail(ctx, DP_E_ARG, "dp_perm_product: a denominator is zero (the reference's division panics)");
+    }
+    ctx->pool.release(a);
+    ctx->pool.release(b);
+    ctx->pool.release(tot);
+    return rc;
+}
+
+int dp_perm_product(dp_ctx *ctx, const void *wires, const void *id_perm, const void *sigma_perm, size_t num_wire_types, size_t n,
+                    const void *beta, const void *gamma, void *out) {
+    if (!ctx || !wires || !id_perm || !sigma_perm || !beta || !gamma || !out) return fail(ctx, DP_E_ARG, "dp_perm_product: NULL argument");
+    if (n == 0 || num_wire_types == 0 || num_wire_types > 16) return fail(ctx, DP_E_ARG, "dp_perm_product: n = %zu, %zu wire types", n, num_wire_types);
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    call_begin(ctx);
+    const size_t bytes = num_wire_types * n * sizeof(Fr);
+    Fr *w = (Fr *)ctx->pool.alloc(bytes), *i = (Fr *)ctx->pool.alloc(bytes), *s = (Fr *)ctx->pool.alloc(bytes);
+    Fr *z = (Fr *)ctx->pool.alloc(n * sizeof(Fr));
+    int rc = DP_OK;
+    if (!w || !i || !s || !z) rc = fail(ctx, DP_E_OOM, "dp_perm_product buffers");
+    if (rc == DP_OK) {
+        cudaError_t e = cudaMemcpyAsync(w, wires, bytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(i, id_perm, bytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s, sigma_perm, bytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) rc = fail(ctx, DP_E_CUDA, "dp_perm_product H2D: %s", cudaGetErrorString(e));
+    }
+    Fr be, ga;
+    memcpy(&be, beta, sizeof be);
+    memcpy(&ga, gamma, sizeof ga);
+    if (rc == DP_OK) rc = perm_product_device(ctx, w, i, s, (uint32_t)num_wire_types, n, be, ga, z);
+    if (rc == DP_OK) {
+        cudaError_t e = cudaMemcpyAsync(out, z, n * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) rc = fail(ctx, DP_E_CUDA, "dp_perm_product D2H: %s", cudaGetErrorString(e));
+    }
+    if (rc == DP_OK) rc = call_end(ctx, true);
+    ctx->pool.release(w);
+    ctx->pool.release(i);
+    ctx->pool.release(s);
+    ctx->pool.release(z);
     return rc;
 }
 

@@ -52,6 +52,7 @@ struct MsmGeom {
     uint32_t pre;          // 1: bases come from the table T[w][i] = 2^(c*w) * P_i, one shared bucket set
     uint32_t stride;       // table row length (points)
     uint32_t slices;       // partial sums per bucket set in the two-level window sum (<= 32)
+    uint32_t chunk;        // sorted digits per accumulate thread
 };
 
 // cost in Fq multiplications of an n-point MSM with window c
@@ -76,6 +77,7 @@ inline MsmGeom msm_make_geom(uint32_t c, bool pre, uint64_t stride) {
     g.slices = g.segs_per_window / 64;  // >= 64 segment sums per slice block
     if (g.slices < 1) g.slices = 1;
     if (g.slices > MSM_SLICES) g.slices = MSM_SLICES;
+    g.chunk = MSM_CHUNK;
     return g;
 }
 
@@ -301,20 +303,20 @@ __global__ void __launch_bounds__(SCAN_TPB) scan_write_kernel(const uint32_t *co
 // touches; the partial of (chunk j, bucket b) lives in slot j + b, which is unique and dense along
 // the staircase of (chunk, bucket) pairs.  Bucket b therefore owns slots j0+b .. j1+b with
 // j0 = offsets[b] / CHUNK, j1 = (offsets[b+1]-1) / CHUNK.
-DP_D void bucket_span(const uint32_t *offsets, uint32_t key, uint32_t &j0, uint32_t &j1, bool &empty) {
+DP_D void bucket_span(const uint32_t *offsets, uint32_t key, uint32_t chunk, uint32_t &j0, uint32_t &j1, bool &empty) {
     const uint32_t lo = offsets[key], hi = offsets[key + 1];
     empty = lo == hi;
-    j0 = lo / MSM_CHUNK;
-    j1 = empty ? j0 : (hi - 1) / MSM_CHUNK;
+    j0 = lo / chunk;
+    j1 = empty ? j0 : (hi - 1) / chunk;
 }
 
 // buckets spread over many chunks (skewed scalars) are listed for msm_collapse
-__global__ void msm_find_big_kernel(const uint32_t *offsets, uint32_t n_keys, uint32_t *multi_keys, uint32_t *n_multi) {
+__global__ void msm_find_big_kernel(const uint32_t *offsets, uint32_t n_keys, uint32_t chunk, uint32_t *multi_keys, uint32_t *n_multi) {
     const uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
     if (key >= n_keys) return;
     uint32_t j0, j1;
     bool empty;
-    bucket_span(offsets, key, j0, j1, empty);
+    bucket_span(offsets, key, chunk, j0, j1, empty);
     if (!empty && j1 - j0 + 1 > MSM_BIG_SPAN) multi_keys[atomicAdd(n_multi, 1u)] = key;
 }
 
@@ -330,13 +332,13 @@ DP_D G1Affine load_affine(const G1Affine *p) {
     return r;
 }
 
-__global__ void __launch_bounds__(MSM_TPB) msm_accumulate_kernel(const uint32_t *offsets, uint32_t n_keys, const uint32_t *sorted,
-                                                                  const G1Affine *bases, G1XYZZ *partials) {
+__global__ void __launch_bounds__(MSM_TPB) msm_accumulate_kernel(const uint32_t *offsets, uint32_t n_keys, uint32_t chunk,
+                                                                  const uint32_t *sorted, const G1Affine *bases, G1XYZZ *partials) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_digits = offsets[n_keys];  // the grid is sized for the worst case
-    const uint64_t pos0 = (uint64_t)j * MSM_CHUNK;
+    const uint64_t pos0 = (uint64_t)j * chunk;
     if (pos0 >= n_digits) return;
-    const uint32_t pos1 = pos0 + MSM_CHUNK < n_digits ? (uint32_t)pos0 + MSM_CHUNK : n_digits;
+    const uint32_t pos1 = pos0 + chunk < n_digits ? (uint32_t)pos0 + chunk : n_digits;
     // bucket holding the first digit: largest b with offsets[b] <= pos0 (skips empty buckets)
     uint32_t lo = 0, hi = n_keys;
     while (hi - lo > 1) {
@@ -380,14 +382,14 @@ DP_D G1XYZZ shfl_xor_point(const G1XYZZ &p, int mask) {
     return r;
 }
 __global__ void __launch_bounds__(MSM_TPB) msm_collapse_kernel(const uint32_t *multi_keys, const uint32_t *n_multi,
-                                                                const uint32_t *offsets, G1XYZZ *partials) {
+                                                                const uint32_t *offsets, uint32_t chunk, G1XYZZ *partials) {
     // fixed-size grid, warps loop over the (usually empty) list: the count is only known on the device
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5, lane = threadIdx.x & 31;
     for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < *n_multi; w += n_warps) {  // warp-uniform
         const uint32_t key = multi_keys[w];
         uint32_t j0, j1;
         bool empty;
-        bucket_span(offsets, key, j0, j1, empty);
+        bucket_span(offsets, key, chunk, j0, j1, empty);
         G1XYZZ acc = G1XYZZ::inf();
         for (uint32_t j = j0 + lane; j <= j1; j += 32) acc = acc.add(partials[j + key]);
         for (int m = 16; m >= 1; m >>= 1) acc = acc.add(shfl_xor_point(acc, m));
@@ -396,10 +398,10 @@ __global__ void __launch_bounds__(MSM_TPB) msm_collapse_kernel(const uint32_t *m
 }
 
 // sum of one bucket: its few partial sums, or the folded one when msm_collapse handled it
-DP_D G1XYZZ bucket_sum(const G1XYZZ *partials, const uint32_t *offsets, uint32_t key) {
+DP_D G1XYZZ bucket_sum(const G1XYZZ *partials, const uint32_t *offsets, uint32_t chunk, uint32_t key) {
     uint32_t j0, j1;
     bool empty;
-    bucket_span(offsets, key, j0, j1, empty);
+    bucket_span(offsets, key, chunk, j0, j1, empty);
     if (empty) return G1XYZZ::inf();
     G1XYZZ b = partials[j0 + key];
     if (j1 - j0 + 1 <= MSM_BIG_SPAN)
@@ -426,7 +428,7 @@ __global__ void __launch_bounds__(MSM_TPB) msm_reduce_kernel(const G1XYZZ *parti
     const uint32_t lo = sgm * g.seg;  // buckets lo+1 .. lo+seg of this window (bucket k <-> digit k)
     G1XYZZ running = G1XYZZ::inf(), acc = G1XYZZ::inf();
     for (uint32_t k = g.seg; k >= 1; k--) {
-        running = running.add(bucket_sum(partials, offsets, w * g.bpw + lo + k - 1));
+        running = running.add(bucket_sum(partials, offsets, g.chunk, w * g.bpw + lo + k - 1));
         acc = acc.add(running);
     }
     if (lo) acc = acc.add(small_mul(running, lo));

@@ -120,6 +120,16 @@ int dp_ntt(dp_ctx *ctx, void *data, size_t n, uint32_t log_n, int is_inv, int is
 int dp_round1(dp_ctx *ctx, const void *evals, size_t n, const void *blind, void *out);
 int dp_get_wire(dp_ctx *ctx, void *out, size_t out_bytes, size_t *n_coeffs);
 
+/* ---- "next" row: the round-2 permutation grand product -----------------------
+ * What the dispatcher computes serially with one field division per row (src/dispatcher2.rs:
+ * 329-345): z[0] = 1, z[j+1] = z[j] * prod_i (w_i[j] + gamma + beta*id_i[j])
+ *                                     / prod_i (w_i[j] + gamma + beta*sigma_i[j]),  j < n-1.
+ * wires[i][j] = circuit.witness[wire_variables[i][j]], id_perm[i][j] = extended_id_permutation[i*n+j],
+ * sigma_perm[i][j] = extended_id_permutation[perm_i*n+perm_j]; all [num_wire_types][n] raw Fr, as are
+ * beta, gamma (one Fr each) and out (n Fr).  DP_E_ARG when a denominator is zero. */
+int dp_perm_product(dp_ctx *ctx, const void *wires, const void *id_perm, const void *sigma_perm, size_t num_wire_types, size_t n,
+                    const void *beta, const void *gamma, void *out);
+
 /* ---- peer transport for n_workers > 1 ---------------------------------------------------------
  * Exchange arena shared between the GPUs of one box through CUDA IPC: every rank exports a
  * handle, the ranks swap them out of band (torch.distributed / the capnp control plane) and attach

@@ -448,6 +448,40 @@ void orc_ntt_output_at(const u64 *data, u64 n, u64 k, int inverse, int coset, u6
     memcpy(out, &acc, 32);
 }
 
+/* Round-2 permutation grand product exactly as the dispatcher computes it (src/dispatcher2.rs:329-345):
+ * product_vec[0] = 1; product_vec[j+1] = product_vec[j] * a / b with one field division per row.
+ * wires / id / sigma: [n_types][n] Montgomery Fr (wire value, extended_id_permutation at (i,j), and at
+ * the permuted position).  Returns 0, or -1 when a denominator is zero (the reference panics). */
+int orc_perm_product(const u64 *wires, const u64 *id, const u64 *sigma, u64 n_types, u64 n, const u64 *beta,
+                     const u64 *gamma, u64 *out) {
+    const fr_t *w = (const fr_t *)wires, *idp = (const fr_t *)id, *sg = (const fr_t *)sigma;
+    const fr_t *be = (const fr_t *)beta, *ga = (const fr_t *)gamma;
+    fr_t *z = (fr_t *)out;
+    if (n == 0) return 0;
+    fr_set_one(&z[0]);
+    for (u64 j = 0; j + 1 < n; j++) {
+        fr_t a, b;
+        fr_set_one(&a);
+        fr_set_one(&b);
+        for (u64 i = 0; i < n_types; i++) {
+            fr_t tmp, t;
+            fr_add(&tmp, &w[i * n + j], ga);
+            fr_mul(&t, be, &idp[i * n + j]);
+            fr_add(&t, &t, &tmp);
+            fr_mul(&a, &a, &t);
+            fr_mul(&t, be, &sg[i * n + j]);
+            fr_add(&t, &t, &tmp);
+            fr_mul(&b, &b, &t);
+        }
+        if (fr_is_zero(&b)) return -1;
+        fr_t bi;
+        fr_inv(&bi, &b);
+        fr_mul(&a, &a, &bi);
+        fr_mul(&z[j + 1], &z[j], &a);
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------ raw Fr utilities for tests */
 void orc_fr_mul(const u64 *a, const u64 *b, u64 *out) { fr_mul((fr_t *)out, (const fr_t *)a, (const fr_t *)b); }
 void orc_fr_add(const u64 *a, const u64 *b, u64 *out) { fr_add((fr_t *)out, (const fr_t *)a, (const fr_t *)b); }

@@ -69,6 +69,7 @@ def lib():
             "orc_commit": (None, [p, u64, p, u64, p]),
             "orc_num_threads": (i, []),
             "orc_ntt_output_at": (None, [p, u64, u64, i, i, p]),
+            "orc_perm_product": (i, [p, p, p, u64, u64, p, p, p]),
         }
         for name, (res, args) in sig.items():
             f = getattr(L, name)
@@ -128,6 +129,17 @@ def ntt_output_at(x: np.ndarray, k: int, inverse: bool, coset: bool) -> np.ndarr
     x = np.ascontiguousarray(x, dtype=np.uint64)
     out = np.zeros(4, dtype=np.uint64)
     lib().orc_ntt_output_at(_ptr(x), x.shape[0], k, int(inverse), int(coset), _ptr(out))
+    return out
+
+
+def perm_product(wires: np.ndarray, idp: np.ndarray, sigma: np.ndarray, beta: np.ndarray, gamma: np.ndarray) -> np.ndarray:
+    """dispatcher2.rs:329-345; wires/idp/sigma: [n_types, n, 4] Montgomery Fr"""
+    n_types, n = wires.shape[0], wires.shape[1]
+    out = np.zeros((n, 4), dtype=np.uint64)
+    args = [np.ascontiguousarray(a, dtype=np.uint64) for a in (wires, idp, sigma, beta, gamma)]
+    rc = lib().orc_perm_product(_ptr(args[0]), _ptr(args[1]), _ptr(args[2]), n_types, n, _ptr(args[3]), _ptr(args[4]), _ptr(out))
+    if rc != 0:
+        raise ZeroDivisionError("zero denominator in the permutation product")
     return out
 
 

@@ -135,3 +135,15 @@ def check_sharded_msm(orc, workers, bases, n, seed):
         acc = orc.g1_add(acc, np.frombuffer(p, dtype=np.uint8))
     ref = orc.msm(bases[:n], sc)
     assert np.array_equal(orc.normalize(acc), orc.normalize(ref))
+
+
+def check_perm_product(orc, ctx: Context, n: int, n_types: int, seed: int):
+    """round-2 grand product: GPU scans + one inversion vs the dispatcher's row-by-row division"""
+    w = np.stack([orc.gen_fr(seed + i, n) for i in range(n_types)])
+    idp = np.stack([orc.gen_fr(seed + 20 + i, n) for i in range(n_types)])
+    sg = np.stack([orc.gen_fr(seed + 40 + i, n) for i in range(n_types)])
+    beta, gamma = orc.gen_fr(seed + 60, 1)[0], orc.gen_fr(seed + 61, 1)[0]
+    got = ctx.perm_product(w, idp, sg, beta, gamma)
+    assert np.array_equal(got, orc.perm_product(w, idp, sg, beta, gamma)), f"perm product n={n}"
+    # a valid permutation (sigma = id re-ordered) closes the cycle: z[n-1] * a[n-1]/b[n-1] = 1
+    return got

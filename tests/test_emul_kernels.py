@@ -155,6 +155,26 @@ def test_commit_and_round1(orc, ctx):
     common.assert_point_eq(orc, got, orc.commit(bases, wire), "round1 commitment")
 
 
+def test_perm_product(orc, ctx):
+    for n, t in ((1, 1), (2, 5), (7, 5), (256, 5), (1025, 3), (2500, 5)):
+        common.check_perm_product(orc, ctx, n, t, 300 + n)
+    # zero denominator -> DP_E_ARG (the reference's `a / b` panics)
+    n = 8
+    w = np.stack([orc.gen_fr(1, n)])
+    sg = np.stack([orc.gen_fr(2, n)])
+    beta = orc.gen_fr(3, 1)[0]
+    L = orc.lib()
+    t = np.zeros(4, dtype=np.uint64)
+    L.orc_fr_mul(beta.ctypes.data, sg[0, 3].ctypes.data, t.ctypes.data)       # beta * sigma[3]
+    gamma = np.zeros(4, dtype=np.uint64)
+    zero = np.zeros(4, dtype=np.uint64)
+    L.orc_fr_add(w[0, 3].ctypes.data, t.ctypes.data, t.ctypes.data)           # w + beta*sigma
+    L.orc_fr_sub(zero.ctypes.data, t.ctypes.data, gamma.ctypes.data)          # gamma = -(w + beta*sigma)
+    with pytest.raises(DpError) as e:
+        ctx.perm_product(w, w, sg, beta, gamma)
+    assert e.value.code == -1
+
+
 def test_error_behaviour(orc, emul_lib):
     c = Context(emul_lib, 0, 0, 1)
     with pytest.raises(DpError) as e:

@@ -210,6 +210,12 @@ def test_commit_and_round1(orc, ctx, bases):
     common.assert_point_eq(orc, got2, orc.commit(bases, ctx.get_wire()), "round1 (internal blinders)")
 
 
+@pytest.mark.parametrize("n", [1, 2, 1000, 1 << 12, (1 << 16) + 3])
+def test_perm_product(orc, ctx, n):
+    """next row §8(f)-3: round-2 grand product (dispatcher2.rs:329-345), 5 wire types"""
+    common.check_perm_product(orc, ctx, n, 5, 500 + (n % 89))
+
+
 # ---------------------------------------------------------------- full BASELINE sizes: properties
 def test_full_size_msm_2p20_vs_oracle_and_linearity(orc, gpu_lib):
     """MSM at 2^20+32 against the oracle, then linearity msm(s)+msm(t) == msm(s+t mod r) and the

@@ -386,22 +386,24 @@ def main():
             ctx._ck(lib.dp_fft2(ctx.h, t, h_out.data_ptr(), h_out.numel() * 8))
 
         msm_host_out = np.zeros(144, dtype=np.uint8)
+        LOOKAHEAD = 2 if W == 1 or not fused else 0    # the fused exchange has one transform in flight per context
 
         def step_e2e():
             # the dispatcher issues its FFT tasks concurrently (join_all, dispatcher2.rs:294-306,
-            # 382-414); one task of look-ahead is enough to overlap copy-in / compute / copy-out
-            for _ in range(N_MSM):
-                ctx._ck(lib.dp_msm(ctx.h, lo, hi, h_scal.data_ptr(), hi - lo, _addr(msm_host_out)))
+            # 382-414: up to 25 in flight); two tasks of look-ahead keep the copy-in stream, the
+            # kernels and the copy-out stream busy at the same time (PCIe is full duplex)
+            for cnt in ROUNDS:       # one varMsm batch per prover round (join_all)
+                ctx.msm_batch([(lo, hi, h_scal.data_ptr(), hi - lo)] * cnt)
             jobs = [(h_in_n, h_out_n, wl_n, rows_n, False, True, False)] * N_INTT_N
             jobs += [(h_in_m, h_out_m, wl_m, rows_m, True, False, True)] * N_COSET_8N
             jobs += [(h_in_m, h_out_m, wl_m, rows_m, True, True, True)] * N_COSET_INTT_8N
-            pending = None
+            pending = []
             for (h_in, h_out, wl, n_rows, q, inv, cos) in jobs:
-                t = submit(h_in, wl, n_rows, q, inv, cos)
-                if pending is not None:
-                    collect(*pending)
-                pending = (t, h_out)
-            collect(*pending)
+                pending.append((submit(h_in, wl, n_rows, q, inv, cos), h_out))
+                if len(pending) > LOOKAHEAD:
+                    collect(*pending.pop(0))
+            while pending:
+                collect(*pending.pop(0))
 
         e_steps = max(1, min(args.steps, 2))
         dt_e, _ = timed(step_e2e, e_steps, 1)

@@ -13,7 +13,7 @@ EXPORTS = [
     "dp_fft1", "dp_fft1_rows", "dp_fft2_prepare", "dp_fft_exchange_begin", "dp_fft_exchange_end", "dp_fft2",
     "dp_ntt", "dp_round1", "dp_get_wire", "dp_peer_arena_create", "dp_peer_attach", "dp_last_timing",
     "dp_launch_count", "dp_sync", "dp_msm_dev", "dp_ntt_dev", "dp_fft_dev", "dp_debug_set_limits",
-    "dp_last_msm_breakdown", "dp_debug_gen_bases", "dp_fft_dev_rows", "dp_fft_dev_cols", "dp_peer_ready", "dp_fft_dev_rows_p2p", "dp_msm_dev_batch", "dp_perm_product",
+    "dp_last_msm_breakdown", "dp_debug_gen_bases", "dp_fft_dev_rows", "dp_fft_dev_cols", "dp_peer_ready", "dp_fft_dev_rows_p2p", "dp_msm_dev_batch", "dp_perm_product", "dp_msm_batch",
 ]
 
 
@@ -63,6 +63,7 @@ def bind(cdll: C.CDLL) -> C.CDLL:
         "dp_fft_dev_cols": (i, [vp, vp]),
         "dp_peer_ready": (i, [vp]),
         "dp_perm_product": (i, [vp, vp, vp, vp, sz, sz, vp, vp, vp]),
+        "dp_msm_batch": (i, [vp, sz, C.POINTER(u64), C.POINTER(u64), C.POINTER(vp), C.POINTER(sz), C.POINTER(vp)]),
         "dp_msm_dev_batch": (i, [vp, sz, C.POINTER(u64), C.POINTER(u64), C.POINTER(vp), C.POINTER(sz), C.POINTER(vp)]),
         "dp_fft_dev_rows_p2p": (i, [vp, vp, i, i, i]),
     }
@@ -191,6 +192,18 @@ class Context:
     # ---- device-pointer variants (bench)
     def msm_dev(self, start, end, scalars_ptr: int, n: int, out_ptr: int):
         self._ck(self.lib.dp_msm_dev(self.h, start, end, scalars_ptr, n, out_ptr))
+
+    def msm_batch(self, jobs):
+        """jobs: list of (start, end, scalars ndarray | host address, n_scalars); returns [144-byte arrays]"""
+        k = len(jobs)
+        outs = [np.zeros(G1_PROJECTIVE_BYTES, dtype=np.uint8) for _ in range(k)]
+        st = (C.c_uint64 * k)(*[j[0] for j in jobs])
+        en = (C.c_uint64 * k)(*[j[1] for j in jobs])
+        sc = (C.c_void_p * k)(*[_addr(j[2]) for j in jobs])
+        ns = (C.c_size_t * k)(*[j[3] for j in jobs])
+        ou = (C.c_void_p * k)(*[_addr(o) for o in outs])
+        self._ck(self.lib.dp_msm_batch(self.h, k, st, en, sc, ns, ou))
+        return outs
 
     def msm_dev_batch(self, jobs):
         """jobs: list of (start, end, scalars_ptr, n_scalars, out_ptr)"""

@@ -967,6 +967,55 @@ int dp_msm_dev_batch(dp_ctx *ctx, size_t n_jobs, const uint64_t *starts, const u
     return call_end(ctx, true);
 }
 
+int dp_msm_batch(dp_ctx *ctx, size_t n_jobs, const uint64_t *starts, const uint64_t *ends, const void *const *scalars,
+                 const size_t *n_scalars, void *const *outs) {
+    if (!ctx || (n_jobs && (!starts || !ends || !scalars || !n_scalars || !outs))) return fail(ctx, DP_E_ARG, "dp_msm_batch: NULL argument");
+    if (!ctx->inited) return fail(ctx, DP_E_STATE, "dp_msm_batch before dp_init");
+    for (size_t k = 0; k < n_jobs; k++)
+        if (starts[k] > ends[k] || ends[k] > ctx->n_bases || !outs[k] || (n_scalars[k] && !scalars[k]))
+            return fail(ctx, DP_E_ARG, "dp_msm_batch: job %zu has a bad range / buffer", k);
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    call_begin(ctx);
+    // copy-in of job k+1 runs on s_in under the kernels of job k; tails overlap as in dp_msm_dev_batch
+    std::vector<MsmJob> jobs(n_jobs);
+    std::vector<uint4 *> sc(n_jobs, nullptr);
+    std::vector<cudaEvent_t> ev(n_jobs, nullptr);
+    G1JacobianOut *od = (G1JacobianOut *)ctx->pool.alloc((n_jobs ? n_jobs : 1) * sizeof(G1JacobianOut));
+    int rc = od ? DP_OK : fail(ctx, DP_E_OOM, "dp_msm_batch outputs");
+    for (size_t k = 0; k < n_jobs && rc == DP_OK; k++) {
+        const uint64_t n = (ends[k] - starts[k]) < n_scalars[k] ? (ends[k] - starts[k]) : n_scalars[k];
+        sc[k] = (uint4 *)ctx->pool_io.alloc((n ? n : 1) * 32);
+        if (!sc[k] || cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming) != cudaSuccess) {
+            rc = fail(ctx, DP_E_OOM, "dp_msm_batch staging");
+            break;
+        }
+        cudaError_t e = n ? cudaMemcpyAsync(sc[k], scalars[k], n * 32, cudaMemcpyHostToDevice, ctx->s_in) : cudaSuccess;
+        if (e == cudaSuccess) e = cudaEventRecord(ev[k], ctx->s_in);
+        if (e != cudaSuccess) rc = fail(ctx, DP_E_CUDA, "dp_msm_batch H2D: %s", cudaGetErrorString(e));
+    }
+    for (size_t k = 0; k < n_jobs && rc == DP_OK; k++) {
+        const uint64_t n = (ends[k] - starts[k]) < n_scalars[k] ? (ends[k] - starts[k]) : n_scalars[k];
+        cudaStreamWaitEvent(ctx->stream, ev[k], 0);
+        rc = msm_enqueue(ctx, starts[k], sc[k], n, od + k, jobs[k], false);
+    }
+    int rc2 = msm_finish(ctx, jobs, false);   // drains the compute and tail streams
+    if (rc == DP_OK) rc = rc2;
+    if (rc == DP_OK) {
+        std::vector<G1JacobianOut> host(n_jobs);
+        cudaError_t e = n_jobs ? cudaMemcpy(host.data(), od, n_jobs * sizeof(G1JacobianOut), cudaMemcpyDeviceToHost) : cudaSuccess;
+        if (e != cudaSuccess) rc = fail(ctx, DP_E_CUDA, "dp_msm_batch D2H: %s", cudaGetErrorString(e));
+        for (size_t k = 0; k < n_jobs && rc == DP_OK; k++) memcpy(outs[k], &host[k], sizeof(G1JacobianOut));
+    }
+    cudaStreamSynchronize(ctx->s_in);
+    for (size_t k = 0; k < n_jobs; k++) {
+        ctx->pool_io.release(sc[k]);
+        if (ev[k]) cudaEventDestroy(ev[k]);
+    }
+    ctx->pool.release(od);
+    if (rc != DP_OK) return rc;
+    return call_end(ctx, true);
+}
+
 static int commit_device(dp_ctx *ctx, const Fr *coeffs_dev, uint64_t n, G1JacobianOut *out_dev) {
     // into_repr + zero-pad to bases.len() (worker.rs:118-120)
     const uint64_t nb = ctx->n_bases;

@@ -68,6 +68,13 @@ int dp_init(dp_ctx *ctx, const void *bases, size_t n_bases, uint64_t domain_size
  * scalars: canonical BigInteger256.  out: 144 B raw G1Projective, normalised (Z = 1) or identity. */
 int dp_msm(dp_ctx *ctx, uint64_t start, uint64_t end, const void *scalars, size_t n_scalars, void *out);
 
+/* Several varMsm requests issued together (the dispatcher joins the commitments of a round,
+ * dispatcher2.rs:316-321, 526-532): scalars of request k+1 are copied in under the kernels of
+ * request k, and the narrow tail kernels of k overlap the wide head kernels of k+1.  Arrays of
+ * n_jobs entries, each with the semantics of dp_msm. */
+int dp_msm_batch(dp_ctx *ctx, size_t n_jobs, const uint64_t *starts, const uint64_t *ends, const void *const *scalars,
+                 const size_t *n_scalars, void *const *outs);
+
 /* ---- commit_polynomial (src/worker.rs:117-123) -----------------------------------------------
  * Fr::into_repr on every coefficient, zero-pad to bases.len(), MSM over all bases.
  * coeffs: n raw Fr (Montgomery), n <= n_bases. */

@@ -112,6 +112,10 @@ def test_msm_dev_batch(orc, ctx):
     ctx.msm_dev_batch([(lo, hi, scs[k].ctypes.data, hi - lo, outs[k].ctypes.data) for k, (lo, hi) in enumerate(ranges)])
     for k, (lo, hi) in enumerate(ranges):
         common.assert_point_eq(orc, outs[k], orc.msm(bases[lo:hi], scs[k][: hi - lo]), f"batch job {k}")
+    # host-buffer variant (dp_msm_batch): copy-in of job k+1 under the kernels of job k
+    outs = ctx.msm_batch([(lo, hi, scs[k], hi - lo) for k, (lo, hi) in enumerate(ranges)])
+    for k, (lo, hi) in enumerate(ranges):
+        common.assert_point_eq(orc, outs[k], orc.msm(bases[lo:hi], scs[k][: hi - lo]), f"host batch job {k}")
 
 
 def test_msm_edges(orc, ctx):

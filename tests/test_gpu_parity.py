@@ -158,6 +158,9 @@ def test_msm_dev_batch(orc, ctx, bases):
     for k, (lo, hi) in enumerate(ranges):
         got = outs[k].cpu().numpy().view(np.uint8)
         common.assert_point_eq(orc, got, orc.msm(bases[lo:hi], scs[k][: hi - lo]), f"batch job {k}")
+    outs = ctx.msm_batch([(lo, hi, scs[k], hi - lo) for k, (lo, hi) in enumerate(ranges)])
+    for k, (lo, hi) in enumerate(ranges):
+        common.assert_point_eq(orc, outs[k], orc.msm(bases[lo:hi], scs[k][: hi - lo]), f"host batch job {k}")
 
 
 def test_msm_edges(orc, ctx, bases):

@@ -16,7 +16,10 @@
  * Conventions: every function returns DP_OK (0) or a negative DP_E_* code and never throws or
  * aborts across the boundary; dp_last_error() gives the text.  All buffers are caller-owned,
  * borrowed only for the duration of the call, may be unaligned, and are HOST memory unless a
- * parameter says "dev".  A context is bound to one CUDA device and must be used from one thread
+ * parameter says "dev".  One exception, for page-locked (cudaHostAlloc / cudaHostRegister) row
+ * buffers handed to dp_fft1 / dp_fft1_rows: their copy-in is truly asynchronous, so they must stay
+ * unchanged until dp_fft2 of that task (or dp_sync) returns; ordinary pageable memory - what a
+ * Cap'n Proto message gives the reference worker - is staged before the call returns.  A context is bound to one CUDA device and must be used from one thread
  * at a time (the reference worker is single-threaded: worker.rs:441,453).  There is no CPU
  * fallback: dp_create fails with DP_E_CUDA when no sm_100 device is usable.
  */

@@ -66,6 +66,24 @@ struct DevPool {
     }
 };
 
+// scope guard: pool blocks borrowed for one call go back on every exit path
+struct Scratch {
+    DevPool &pool;
+    std::vector<void *> held;
+    explicit Scratch(DevPool &p) : pool(p) {}
+    ~Scratch() {
+        for (void *p : held) pool.release(p);
+    }
+    template <class T>
+    T *get(size_t count) {
+        void *p = pool.alloc((count ? count : 1) * sizeof(T));
+        if (p) held.push_back(p);
+        return static_cast<T *>(p);
+    }
+    Scratch(const Scratch &) = delete;
+    Scratch &operator=(const Scratch &) = delete;
+};
+
 struct DomainDev {
     uint32_t log_n = 0, log_r = 0, log_c = 0;
     Fr *H = nullptr;       // omega_N^e, e < N/2
@@ -921,19 +939,14 @@ int dp_msm(dp_ctx *ctx, uint64_t start, uint64_t end, const void *scalars, size_
     DP_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint64_t n = (end - start) < n_scalars ? (end - start) : n_scalars;
     call_begin(ctx);
-    uint4 *sc = (uint4 *)ctx->pool.alloc((n ? n : 1) * 32);
-    G1JacobianOut *od = (G1JacobianOut *)ctx->pool.alloc(sizeof(G1JacobianOut));
+    Scratch tmp(ctx->pool);
+    uint4 *sc = tmp.get<uint4>(2 * n);
+    G1JacobianOut *od = tmp.get<G1JacobianOut>(1);
     if (!sc || !od) return fail(ctx, DP_E_OOM, "dp_msm buffers");
     if (n) DP_CUDA(ctx, cudaMemcpyAsync(sc, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-    int rc = msm_device(ctx, start, sc, n, od, nullptr);
-    if (rc == DP_OK) {
-        cudaError_t e = cudaMemcpyAsync(out, od, sizeof(G1JacobianOut), cudaMemcpyDeviceToHost, ctx->stream);
-        if (e != cudaSuccess) rc = fail(ctx, DP_E_CUDA, "dp_msm D2H: %s", cudaGetErrorString(e));
-    }
-    if (rc == DP_OK) rc = call_end(ctx, true);
-    ctx->pool.release(sc);
-    ctx->pool.release(od);
-    return rc;
+    DP_TRY(msm_device(ctx, start, sc, n, od, nullptr));
+    DP_CUDA(ctx, cudaMemcpyAsync(out, od, sizeof(G1JacobianOut), cudaMemcpyDeviceToHost, ctx->stream));
+    return call_end(ctx, true);
 }
 
 int dp_msm_dev(dp_ctx *ctx, uint64_t start, uint64_t end, const void *scalars_dev, size_t n_scalars, void *out_dev) {
@@ -1020,15 +1033,14 @@ static int commit_device(dp_ctx *ctx, const Fr *coeffs_dev, uint64_t n, G1Jacobi
     // into_repr + zero-pad to bases.len() (worker.rs:118-120)
     const uint64_t nb = ctx->n_bases;
     if (n > nb) return fail(ctx, DP_E_ARG, "commit: %llu coefficients > %llu bases", (unsigned long long)n, (unsigned long long)nb);
-    Fr *sc = (Fr *)ctx->pool.alloc((nb ? nb : 1) * sizeof(Fr));
+    Scratch tmp(ctx->pool);
+    Fr *sc = tmp.get<Fr>(nb);
     if (!sc) return fail(ctx, DP_E_OOM, "commit scalars");
     if (nb) {
         DP_LAUNCH(fr_into_repr_kernel, dim3(blocks_for(nb, 256)), dim3(256), 0, ctx->stream, coeffs_dev, sc, n, nb);
         ctx->launches++;
     }
-    int rc = msm_device(ctx, 0, (const uint4 *)sc, nb, out_dev, nullptr);
-    ctx->pool.release(sc);
-    return rc;
+    return msm_device(ctx, 0, (const uint4 *)sc, nb, out_dev, nullptr);  // synchronises before sc goes back
 }
 
 int dp_commit(dp_ctx *ctx, const void *coeffs, size_t n, void *out) {
@@ -1037,19 +1049,14 @@ int dp_commit(dp_ctx *ctx, const void *coeffs, size_t n, void *out) {
     if (n && !coeffs) return fail(ctx, DP_E_ARG, "dp_commit: coeffs is NULL");
     DP_CUDA(ctx, cudaSetDevice(ctx->device));
     call_begin(ctx);
-    Fr *cd = (Fr *)ctx->pool.alloc((n ? n : 1) * sizeof(Fr));
-    G1JacobianOut *od = (G1JacobianOut *)ctx->pool.alloc(sizeof(G1JacobianOut));
+    Scratch tmp(ctx->pool);
+    Fr *cd = tmp.get<Fr>(n);
+    G1JacobianOut *od = tmp.get<G1JacobianOut>(1);
     if (!cd || !od) return fail(ctx, DP_E_OOM, "dp_commit buffers");
     if (n) DP_CUDA(ctx, cudaMemcpyAsync(cd, coeffs, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
-    int rc = commit_device(ctx, cd, n, od);
-    if (rc == DP_OK) {
-        cudaError_t e = cudaMemcpyAsync(out, od, sizeof(G1JacobianOut), cudaMemcpyDeviceToHost, ctx->stream);
-        if (e != cudaSuccess) rc = fail(ctx, DP_E_CUDA, "dp_commit D2H: %s", cudaGetErrorString(e));
-    }
-    if (rc == DP_OK) rc = call_end(ctx, true);
-    ctx->pool.release(cd);
-    ctx->pool.release(od);
-    return rc;
+    DP_TRY(commit_device(ctx, cd, n, od));
+    DP_CUDA(ctx, cudaMemcpyAsync(out, od, sizeof(G1JacobianOut), cudaMemcpyDeviceToHost, ctx->stream));
+    return call_end(ctx, true);
 }
 
 int dp_fft_init(dp_ctx *ctx, uint64_t id, const dp_fft_workload *workloads, size_t n_workloads, int is_quot, int is_inv,
@@ -1199,16 +1206,14 @@ int dp_fft_dev(dp_ctx *ctx, const void *rows_dev, void *cols_dev, int is_quot, i
     const DomainDev &d = ctx->dom[is_quot ? 1 : 0];
     const uint64_t N = d.n();
     call_begin(ctx);
-    Fr *work = (Fr *)ctx->pool.alloc(N * sizeof(Fr));
+    Scratch tmp(ctx->pool);
+    Fr *work = tmp.get<Fr>(N);
     const bool need_scratch = d.log_c > ctx->max_contig_log_k;
-    Fr *scratch = need_scratch ? (Fr *)ctx->pool.alloc(N * sizeof(Fr)) : nullptr;
+    Fr *scratch = need_scratch ? tmp.get<Fr>(N) : nullptr;
     if (!work || (need_scratch && !scratch)) return fail(ctx, DP_E_OOM, "dp_fft_dev buffers");
-    int rc = plan_row_phase(ctx, d, (const Fr *)rows_dev, work, scratch, d.r(), 0, is_inv != 0, is_coset != 0, 1);
-    if (rc == DP_OK) rc = plan_col_phase(ctx, d, work, (Fr *)cols_dev, d.c(), 0, is_inv != 0, is_coset != 0);
-    ctx->pool.release(work);
-    ctx->pool.release(scratch);
-    if (rc != DP_OK) return rc;
-    return call_end(ctx, true);
+    DP_TRY(plan_row_phase(ctx, d, (const Fr *)rows_dev, work, scratch, d.r(), 0, is_inv != 0, is_coset != 0, 1));
+    DP_TRY(plan_col_phase(ctx, d, work, (Fr *)cols_dev, d.c(), 0, is_inv != 0, is_coset != 0));
+    return call_end(ctx, true);  // synchronises before the scratch goes back to the pool
 }
 
 int dp_fft_dev_rows(dp_ctx *ctx, const void *rows_dev, int is_quot, int is_inv, int is_coset, void **send_dev,
@@ -1224,11 +1229,10 @@ int dp_fft_dev_rows(dp_ctx *ctx, const void *rows_dev, int is_quot, int is_inv, 
     ctx->dev_send = (Fr *)ctx->pool.alloc(n_rows * c * sizeof(Fr));
     ctx->dev_recv = W > 1 ? (Fr *)ctx->pool.alloc(d.r() * n_cols * sizeof(Fr)) : nullptr;
     const bool need_scratch = d.log_c > ctx->max_contig_log_k;
-    Fr *scratch = need_scratch ? (Fr *)ctx->pool.alloc(n_rows * c * sizeof(Fr)) : nullptr;
+    Scratch tmp(ctx->pool);
+    Fr *scratch = need_scratch ? tmp.get<Fr>(n_rows * c) : nullptr;
     if (!ctx->dev_send || (W > 1 && !ctx->dev_recv) || (need_scratch && !scratch)) return fail(ctx, DP_E_OOM, "dp_fft_dev_rows buffers");
-    int rc = plan_row_phase(ctx, d, (const Fr *)rows_dev, ctx->dev_send, scratch, n_rows, ctx->me * n_rows, is_inv != 0, is_coset != 0, W);
-    ctx->pool.release(scratch);
-    if (rc != DP_OK) return rc;
+    DP_TRY(plan_row_phase(ctx, d, (const Fr *)rows_dev, ctx->dev_send, scratch, n_rows, ctx->me * n_rows, is_inv != 0, is_coset != 0, W));
     DP_TRY(call_end(ctx, true));
     ctx->dev_flags = (is_quot ? 4 : 0) | (is_inv ? 2 : 0) | (is_coset ? 1 : 0);
     *send_dev = ctx->dev_send;
@@ -1253,27 +1257,26 @@ int dp_fft_dev_cols(dp_ctx *ctx, void *cols_dev) {
 }
 
 static int ntt_device(dp_ctx *ctx, Fr *x, uint32_t log_n, bool is_inv, bool is_coset) {
-    // twiddles: reuse a resident domain table when it is at least as large, else build one
+    // twiddles: reuse a resident domain table when it is at least as large, else build one.
+    // Everything is queued on the compute stream, so handing the scratch back at scope exit is
+    // stream-ordered with respect to every later user of the pool.
     const DomainDev *d = nullptr;
     for (int k = 0; k < 2; k++)
         if (ctx->dom[k].H && ctx->dom[k].log_n >= log_n && (!d || ctx->dom[k].log_n < d->log_n)) d = &ctx->dom[k];
     const uint64_t N = (uint64_t)1 << log_n;
-    Fr *tmpH = nullptr;
+    Scratch tmp(ctx->pool);
     const Fr *H = d ? d->H : nullptr;
     uint32_t H_log = d ? d->log_n : log_n;
     const bool multi = log_n > ctx->max_contig_log_k;
     if (!H && multi) {
-        tmpH = (Fr *)ctx->pool.alloc((N / 2) * sizeof(Fr));
+        Fr *tmpH = tmp.get<Fr>(N / 2);
         if (!tmpH) return fail(ctx, DP_E_OOM, "dp_ntt twiddles");
         DP_TRY(gen_powers(ctx, tmpH, N / 2, fr_domain_gen(log_n), 0, 1, Fr::one()));
         H = tmpH;
     }
-    Fr *scratch = multi ? (Fr *)ctx->pool.alloc(N * sizeof(Fr)) : nullptr;
+    Fr *scratch = multi ? tmp.get<Fr>(N) : nullptr;
     if (multi && !scratch) return fail(ctx, DP_E_OOM, "dp_ntt scratch");
-    int rc = plan_whole_ntt(ctx, d, x, scratch, log_n, is_inv, is_coset, H, H_log);
-    ctx->pool.release(scratch);
-    ctx->pool.release(tmpH);
-    return rc;
+    return plan_whole_ntt(ctx, d, x, scratch, log_n, is_inv, is_coset, H, H_log);
 }
 
 int dp_ntt_dev(dp_ctx *ctx, void *data_dev, uint32_t log_n, int is_inv, int is_coset) {
@@ -1292,20 +1295,14 @@ int dp_ntt(dp_ctx *ctx, void *data, size_t n, uint32_t log_n, int is_inv, int is
     if (n > N) return fail(ctx, DP_E_ARG, "dp_ntt: %zu elements > domain 2^%u", n, log_n);
     DP_CUDA(ctx, cudaSetDevice(ctx->device));
     call_begin(ctx);
-    Fr *x = (Fr *)ctx->pool.alloc(N * sizeof(Fr));
+    Scratch tmp(ctx->pool);
+    Fr *x = tmp.get<Fr>(N);
     if (!x) return fail(ctx, DP_E_OOM, "dp_ntt buffer");
-    int rc = DP_OK;
-    cudaError_t e = cudaMemcpyAsync(x, data, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess && n < N) e = cudaMemsetAsync(x + n, 0, (N - n) * sizeof(Fr), ctx->stream);
-    if (e != cudaSuccess) rc = fail(ctx, DP_E_CUDA, "dp_ntt H2D: %s", cudaGetErrorString(e));
-    if (rc == DP_OK) rc = ntt_device(ctx, x, log_n, is_inv != 0, is_coset != 0);
-    if (rc == DP_OK) {
-        e = cudaMemcpyAsync(data, x, N * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream);
-        if (e != cudaSuccess) rc = fail(ctx, DP_E_CUDA, "dp_ntt D2H: %s", cudaGetErrorString(e));
-    }
-    if (rc == DP_OK) rc = call_end(ctx, true);
-    ctx->pool.release(x);
-    return rc;
+    DP_CUDA(ctx, cudaMemcpyAsync(x, data, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    if (n < N) DP_CUDA(ctx, cudaMemsetAsync(x + n, 0, (N - n) * sizeof(Fr), ctx->stream));
+    DP_TRY(ntt_device(ctx, x, log_n, is_inv != 0, is_coset != 0));
+    DP_CUDA(ctx, cudaMemcpyAsync(data, x, N * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    return call_end(ctx, true);
 }
 
 // wire = (b0 + b1*X) * (X^n - 1) + poly   (worker.rs:400-401)
@@ -1334,7 +1331,8 @@ int dp_round1(dp_ctx *ctx, const void *evals, size_t n, const void *blind, void 
     call_begin(ctx);
     ctx->pool.release(ctx->wire);
     ctx->wire = (Fr *)ctx->pool.alloc((N + 2) * sizeof(Fr));
-    G1JacobianOut *od = (G1JacobianOut *)ctx->pool.alloc(sizeof(G1JacobianOut));
+    Scratch tmp(ctx->pool);
+    G1JacobianOut *od = tmp.get<G1JacobianOut>(1);
     if (!ctx->wire || !od) return fail(ctx, DP_E_OOM, "dp_round1 buffers");
     ctx->wire_len = N + 2;
     DP_CUDA(ctx, cudaMemcpyAsync(ctx->wire, evals, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
@@ -1360,60 +1358,46 @@ int dp_round1(dp_ctx *ctx, const void *evals, size_t n, const void *blind, void 
     }
     DP_LAUNCH(round1_blind_kernel, dim3(1), dim3(32), 0, ctx->stream, ctx->wire, N, b[0], b[1]);
     ctx->launches++;
-    int rc = commit_device(ctx, ctx->wire, N + 2, od);
-    if (rc == DP_OK) {
-        cudaError_t e = cudaMemcpyAsync(out, od, sizeof(G1JacobianOut), cudaMemcpyDeviceToHost, ctx->stream);
-        if (e != cudaSuccess) rc = fail(ctx, DP_E_CUDA, "dp_round1 D2H: %s", cudaGetErrorString(e));
-    }
-    if (rc == DP_OK) rc = call_end(ctx, true);
-    ctx->pool.release(od);
-    return rc;
+    DP_TRY(commit_device(ctx, ctx->wire, N + 2, od));
+    DP_CUDA(ctx, cudaMemcpyAsync(out, od, sizeof(G1JacobianOut), cudaMemcpyDeviceToHost, ctx->stream));
+    return call_end(ctx, true);
 }
 
 // multiplicative scan of n Fr on the compute stream: out[i] = product of the logical elements before
 // (exclusive) or up to (inclusive) i, logical order reversed when `reverse`; *total_dev = whole product
 static int perm_scan(dp_ctx *ctx, const Fr *x, uint64_t n, bool reverse, bool inclusive, Fr *out, Fr *total_dev) {
     const uint32_t n_blocks = (uint32_t)((n + PERM_BLOCK - 1) / PERM_BLOCK);
-    Fr *block_tot = (Fr *)ctx->pool.alloc((size_t)n_blocks * sizeof(Fr));
+    Scratch tmp(ctx->pool);  // stream-ordered: only the compute stream touches it
+    Fr *block_tot = tmp.get<Fr>(n_blocks);
     if (!block_tot) return fail(ctx, DP_E_OOM, "perm scan scratch");
     DP_LAUNCH(perm_block_products_kernel, dim3(n_blocks), dim3(PERM_TPB), 0, ctx->stream, x, n, reverse ? 1u : 0u, block_tot);
     DP_LAUNCH(perm_block_offsets_kernel, dim3(1), dim3(PERM_TPB), 0, ctx->stream, block_tot, n_blocks, total_dev);
     DP_LAUNCH(perm_scan_write_kernel, dim3(n_blocks), dim3(PERM_TPB), 0, ctx->stream, x, n, reverse ? 1u : 0u, inclusive ? 1u : 0u,
               (const Fr *)block_tot, out);
     ctx->launches += 3;
-    ctx->pool.release(block_tot);
     DP_CUDA(ctx, cudaGetLastError());
     return DP_OK;
 }
 
 static int perm_product_device(dp_ctx *ctx, const Fr *wires, const Fr *id, const Fr *sigma, uint32_t n_types, uint64_t n,
                                const Fr &beta, const Fr &gamma, Fr *z_dev) {
-    Fr *a = (Fr *)ctx->pool.alloc(n * sizeof(Fr)), *b = (Fr *)ctx->pool.alloc(n * sizeof(Fr));
-    Fr *tot = (Fr *)ctx->pool.alloc(2 * sizeof(Fr));
-    int rc = DP_OK;
-    if (!a || !b || !tot) rc = fail(ctx, DP_E_OOM, "dp_perm_product scratch");
-    if (rc == DP_OK) {
-        DP_LAUNCH(perm_terms_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, ctx->stream, wires, id, sigma, n_types, n, beta, gamma, a, b);
-        ctx->launches++;
-        rc = perm_scan(ctx, a, n, false, false, a, tot);          // a <- exclusive prefix products (in place)
-    }
-    if (rc == DP_OK) rc = perm_scan(ctx, b, n, true, true, b, tot + 1);  // b <- inclusive suffix products; tot[1] = T
-    if (rc == DP_OK) {
-        DP_LAUNCH(perm_invert_kernel, dim3(1), dim3(32), 0, ctx->stream, tot + 1);
-        DP_LAUNCH(perm_finish_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, ctx->stream, (const Fr *)a, (const Fr *)b,
-                  (const Fr *)(tot + 1), n, z_dev);
-        ctx->launches += 2;
-        Fr t_inv;
-        cudaError_t e = cudaMemcpyAsync(&t_inv, tot + 1, sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e == cudaSuccess) e = cudaGetLastError();
-        if (e != cudaSuccess) rc = fail(ctx, DP_E_CUDA, "dp_perm_product: %s", cudaGetErrorString(e));
-        else if (t_inv.is_zero()) rc = fail(ctx, DP_E_ARG, "dp_perm_product: a denominator is zero (the reference's division panics)");
-    }
-    ctx->pool.release(a);
-    ctx->pool.release(b);
-    ctx->pool.release(tot);
-    return rc;
+    Scratch tmp(ctx->pool);
+    Fr *a = tmp.get<Fr>(n), *b = tmp.get<Fr>(n), *tot = tmp.get<Fr>(2);
+    if (!a || !b || !tot) return fail(ctx, DP_E_OOM, "dp_perm_product scratch");
+    DP_LAUNCH(perm_terms_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, ctx->stream, wires, id, sigma, n_types, n, beta, gamma, a, b);
+    ctx->launches++;
+    DP_TRY(perm_scan(ctx, a, n, false, false, a, tot));        // a <- exclusive prefix products (in place)
+    DP_TRY(perm_scan(ctx, b, n, true, true, b, tot + 1));      // b <- inclusive suffix products; tot[1] = T
+    DP_LAUNCH(perm_invert_kernel, dim3(1), dim3(32), 0, ctx->stream, tot + 1);
+    DP_LAUNCH(perm_finish_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, ctx->stream, (const Fr *)a, (const Fr *)b,
+              (const Fr *)(tot + 1), n, z_dev);
+    ctx->launches += 2;
+    Fr t_inv;
+    DP_CUDA(ctx, cudaMemcpyAsync(&t_inv, tot + 1, sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    DP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    DP_CUDA(ctx, cudaGetLastError());
+    if (t_inv.is_zero()) return fail(ctx, DP_E_ARG, "dp_perm_product: a denominator is zero (the reference's division panics)");
+    return DP_OK;
 }
 
 int dp_perm_product(dp_ctx *ctx, const void *wires, const void *id_perm, const void *sigma_perm, size_t num_wire_types, size_t n,
@@ -1422,31 +1406,19 @@ int dp_perm_product(dp_ctx *ctx, const void *wires, const void *id_perm, const v
     if (n == 0 || num_wire_types == 0 || num_wire_types > 16) return fail(ctx, DP_E_ARG, "dp_perm_product: n = %zu, %zu wire types", n, num_wire_types);
     DP_CUDA(ctx, cudaSetDevice(ctx->device));
     call_begin(ctx);
-    const size_t bytes = num_wire_types * n * sizeof(Fr);
-    Fr *w = (Fr *)ctx->pool.alloc(bytes), *i = (Fr *)ctx->pool.alloc(bytes), *s = (Fr *)ctx->pool.alloc(bytes);
-    Fr *z = (Fr *)ctx->pool.alloc(n * sizeof(Fr));
-    int rc = DP_OK;
-    if (!w || !i || !s || !z) rc = fail(ctx, DP_E_OOM, "dp_perm_product buffers");
-    if (rc == DP_OK) {
-        cudaError_t e = cudaMemcpyAsync(w, wires, bytes, cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(i, id_perm, bytes, cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(s, sigma_perm, bytes, cudaMemcpyHostToDevice, ctx->stream);
-        if (e != cudaSuccess) rc = fail(ctx, DP_E_CUDA, "dp_perm_product H2D: %s", cudaGetErrorString(e));
-    }
+    const size_t count = num_wire_types * n, bytes = count * sizeof(Fr);
+    Scratch tmp(ctx->pool);
+    Fr *w = tmp.get<Fr>(count), *i = tmp.get<Fr>(count), *s = tmp.get<Fr>(count), *z = tmp.get<Fr>(n);
+    if (!w || !i || !s || !z) return fail(ctx, DP_E_OOM, "dp_perm_product buffers");
+    DP_CUDA(ctx, cudaMemcpyAsync(w, wires, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    DP_CUDA(ctx, cudaMemcpyAsync(i, id_perm, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    DP_CUDA(ctx, cudaMemcpyAsync(s, sigma_perm, bytes, cudaMemcpyHostToDevice, ctx->stream));
     Fr be, ga;
     memcpy(&be, beta, sizeof be);
     memcpy(&ga, gamma, sizeof ga);
-    if (rc == DP_OK) rc = perm_product_device(ctx, w, i, s, (uint32_t)num_wire_types, n, be, ga, z);
-    if (rc == DP_OK) {
-        cudaError_t e = cudaMemcpyAsync(out, z, n * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream);
-        if (e != cudaSuccess) rc = fail(ctx, DP_E_CUDA, "dp_perm_product D2H: %s", cudaGetErrorString(e));
-    }
-    if (rc == DP_OK) rc = call_end(ctx, true);
-    ctx->pool.release(w);
-    ctx->pool.release(i);
-    ctx->pool.release(s);
-    ctx->pool.release(z);
-    return rc;
+    DP_TRY(perm_product_device(ctx, w, i, s, (uint32_t)num_wire_types, n, be, ga, z));
+    DP_CUDA(ctx, cudaMemcpyAsync(out, z, n * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    return call_end(ctx, true);
 }
 
 int dp_get_wire(dp_ctx *ctx, void *out, size_t out_bytes, size_t *n_coeffs) {
@@ -1548,11 +1520,10 @@ int dp_fft_dev_rows_p2p(dp_ctx *ctx, const void *rows_dev, int is_quot, int is_i
     Fr *slot = nullptr;
     DP_TRY(p2p_next_slot(ctx, d.r() * n_cols * sizeof(Fr), peers, slot, ctx->me * n_rows * n_cols));
     const bool need_scratch = d.log_c > ctx->max_contig_log_k;
-    Fr *scratch = need_scratch ? (Fr *)ctx->pool.alloc(n_rows * c * sizeof(Fr)) : nullptr;
+    Scratch tmp(ctx->pool);
+    Fr *scratch = need_scratch ? tmp.get<Fr>(n_rows * c) : nullptr;
     if (need_scratch && !scratch) return fail(ctx, DP_E_OOM, "dp_fft_dev_rows_p2p scratch");
-    int rc = plan_row_phase(ctx, d, (const Fr *)rows_dev, nullptr, scratch, n_rows, ctx->me * n_rows, is_inv != 0, is_coset != 0, W, &peers);
-    ctx->pool.release(scratch);
-    if (rc != DP_OK) return rc;
+    DP_TRY(plan_row_phase(ctx, d, (const Fr *)rows_dev, nullptr, scratch, n_rows, ctx->me * n_rows, is_inv != 0, is_coset != 0, W, &peers));
     DP_TRY(call_end(ctx, true));
     ctx->pool.release(ctx->dev_send);
     ctx->pool.release(ctx->dev_recv);

@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(NTT_TPB, 2) ntt_tile_kernel(NttPass p) {
 
     // ---- stage the butterfly twiddles (TMA bulk copy, overlaps the tile load below)
 #if defined(DP_EMUL)
+    (void)bar;
     if (tid == 0) {
         memcpy(wlo, p.w_lo, (size_t)K * 16);
         memcpy(whi, p.w_hi, (size_t)K * 16);

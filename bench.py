@@ -123,7 +123,7 @@ def cpu_sample(log_n: int, budget_s: float):
     from oracle import loader as orc
     threads = orc.lib().orc_num_threads()
     # MSM sample
-    log_m = min(log_n, 18)
+    log_m = min(log_n, 20)
     nb = (1 << log_m) + 32
     bases = orc.gen_bases(5, nb, 2048, True)
     sc = orc.gen_fr(6, nb, False)
@@ -132,7 +132,7 @@ def cpu_sample(log_n: int, budget_s: float):
     t_msm = time.perf_counter() - t0
     adds_rate = msm_work_adds(nb, nb) / t_msm
     # NTT sample
-    log_f = min(log_n + 3, 21)
+    log_f = min(log_n + 3, 23)
     x = orc.gen_fr(7, 1 << log_f)
     t0 = time.perf_counter()
     orc.distributed_fft(x, 1 << log_f, False, True, 1, True)
@@ -413,6 +413,17 @@ def main():
         e2e = {"value": e_steps / dt_e, "unit": "proofs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": dt_e / e_steps * 1e3, "steps": e_steps}
 
+    # ---- "next" row, measured beside the schedule (not part of the step): round-2 grand product
+    perm = None
+    if W == 1:
+        wt = [rand_fr(5 * n) for _ in range(3)]
+        zt = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+        bg = np.array([[3, 1, 4, 1], [5, 9, 2, 6]], dtype=np.uint64)
+        for _ in range(3):
+            ctx.perm_product_dev(wt[0].data_ptr(), wt[1].data_ptr(), wt[2].data_ptr(), 5, n, bg[0], bg[1], zt.data_ptr())
+        perm = {"n": n, "wire_types": 5, "gpu_ms": ctx.last_timing()[0], "gpu_rows_per_sec": n / (ctx.last_timing()[0] * 1e-3)}
+        del wt, zt
+
     if rank != 0:
         if W > 1:
             dist.destroy_process_group()
@@ -479,6 +490,7 @@ def main():
         "breakdown_ms": {"msm_total": msm_total, "msm_accumulate": acc_total, "intt_n_total": sum(stats["ntt_n_ms"]),
                          "coset_ntt_8n_total": ntt_m_total},
         "roofline": roofline, "roofline_ntt": ntt_hbm, "roofline_compute": compute, "e2e": e2e,
+        "next_row_perm_product": perm,
     }
     if not args.no_cpu and W == 1:
         from oracle import loader as orc
@@ -486,6 +498,13 @@ def main():
         cb = cpu_sample(log_n, 20.0)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         line["cpu_baseline"]["msm_g1_adds_per_sec"] = cb["msm_g1_adds_per_sec"]
+        if perm:   # the dispatcher's serial loop with one division per row (dispatcher2.rs:329-345), sampled
+            pn = 1 << 14
+            pw = [np.stack([orc.gen_fr(90 + 7 * k + i, pn) for i in range(5)]) for k in range(3)]
+            t0 = time.perf_counter()
+            orc.perm_product(pw[0], pw[1], pw[2], orc.gen_fr(98, 1)[0], orc.gen_fr(99, 1)[0])
+            perm["cpu_rows_per_sec"] = pn / (time.perf_counter() - t0)
+            perm["cpu_note"] = "oracle restatement, 1 thread (the reference loop is serial), 2^14-row sample"
     print(json.dumps(line), flush=True)
     if W > 1:
         dist.destroy_process_group()

@@ -13,7 +13,7 @@ EXPORTS = [
     "dp_fft1", "dp_fft1_rows", "dp_fft2_prepare", "dp_fft_exchange_begin", "dp_fft_exchange_end", "dp_fft2",
     "dp_ntt", "dp_round1", "dp_get_wire", "dp_peer_arena_create", "dp_peer_attach", "dp_last_timing",
     "dp_launch_count", "dp_sync", "dp_msm_dev", "dp_ntt_dev", "dp_fft_dev", "dp_debug_set_limits",
-    "dp_last_msm_breakdown", "dp_debug_gen_bases", "dp_fft_dev_rows", "dp_fft_dev_cols", "dp_peer_ready", "dp_fft_dev_rows_p2p", "dp_msm_dev_batch", "dp_perm_product", "dp_msm_batch",
+    "dp_last_msm_breakdown", "dp_debug_gen_bases", "dp_fft_dev_rows", "dp_fft_dev_cols", "dp_peer_ready", "dp_fft_dev_rows_p2p", "dp_msm_dev_batch", "dp_perm_product", "dp_msm_batch", "dp_perm_product_dev",
 ]
 
 
@@ -63,6 +63,7 @@ def bind(cdll: C.CDLL) -> C.CDLL:
         "dp_fft_dev_cols": (i, [vp, vp]),
         "dp_peer_ready": (i, [vp]),
         "dp_perm_product": (i, [vp, vp, vp, vp, sz, sz, vp, vp, vp]),
+        "dp_perm_product_dev": (i, [vp, vp, vp, vp, sz, sz, vp, vp, vp]),
         "dp_msm_batch": (i, [vp, sz, C.POINTER(u64), C.POINTER(u64), C.POINTER(vp), C.POINTER(sz), C.POINTER(vp)]),
         "dp_msm_dev_batch": (i, [vp, sz, C.POINTER(u64), C.POINTER(u64), C.POINTER(vp), C.POINTER(sz), C.POINTER(vp)]),
         "dp_fft_dev_rows_p2p": (i, [vp, vp, i, i, i]),
@@ -181,6 +182,10 @@ class Context:
         out = np.empty((n, 4), dtype=np.uint64)
         self._ck(self.lib.dp_perm_product(self.h, _addr(a[0]), _addr(a[1]), _addr(a[2]), n_types, n, _addr(a[3]), _addr(a[4]), _addr(out)))
         return out
+
+    def perm_product_dev(self, wires_ptr: int, id_ptr: int, sigma_ptr: int, n_types: int, n: int, beta: np.ndarray, gamma: np.ndarray, out_ptr: int):
+        b, g = np.ascontiguousarray(beta, dtype=np.uint64), np.ascontiguousarray(gamma, dtype=np.uint64)
+        self._ck(self.lib.dp_perm_product_dev(self.h, wires_ptr, id_ptr, sigma_ptr, n_types, n, _addr(b), _addr(g), out_ptr))
 
     def get_wire(self) -> np.ndarray:
         n = C.c_size_t()

@@ -1421,6 +1421,19 @@ int dp_perm_product(dp_ctx *ctx, const void *wires, const void *id_perm, const v
     return call_end(ctx, true);
 }
 
+int dp_perm_product_dev(dp_ctx *ctx, const void *wires_dev, const void *id_dev, const void *sigma_dev, size_t num_wire_types, size_t n,
+                        const void *beta, const void *gamma, void *out_dev) {
+    if (!ctx || !wires_dev || !id_dev || !sigma_dev || !beta || !gamma || !out_dev) return fail(ctx, DP_E_ARG, "dp_perm_product_dev: NULL argument");
+    if (n == 0 || num_wire_types == 0 || num_wire_types > 16) return fail(ctx, DP_E_ARG, "dp_perm_product_dev: n = %zu, %zu wire types", n, num_wire_types);
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    call_begin(ctx);
+    Fr be, ga;
+    memcpy(&be, beta, sizeof be);
+    memcpy(&ga, gamma, sizeof ga);
+    DP_TRY(perm_product_device(ctx, (const Fr *)wires_dev, (const Fr *)id_dev, (const Fr *)sigma_dev, (uint32_t)num_wire_types, n, be, ga, (Fr *)out_dev));
+    return call_end(ctx, true);
+}
+
 int dp_get_wire(dp_ctx *ctx, void *out, size_t out_bytes, size_t *n_coeffs) {
     if (!ctx) return DP_E_ARG;
     if (!ctx->wire) return fail(ctx, DP_E_STATE, "dp_get_wire before dp_round1");

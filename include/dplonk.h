@@ -139,6 +139,9 @@ int dp_get_wire(dp_ctx *ctx, void *out, size_t out_bytes, size_t *n_coeffs);
  * beta, gamma (one Fr each) and out (n Fr).  DP_E_ARG when a denominator is zero. */
 int dp_perm_product(dp_ctx *ctx, const void *wires, const void *id_perm, const void *sigma_perm, size_t num_wire_types, size_t n,
                     const void *beta, const void *gamma, void *out);
+/* same with device-resident inputs and output (beta, gamma stay host pointers to one Fr each) */
+int dp_perm_product_dev(dp_ctx *ctx, const void *wires_dev, const void *id_dev, const void *sigma_dev, size_t num_wire_types, size_t n,
+                        const void *beta, const void *gamma, void *out_dev);
 
 /* ---- peer transport for n_workers > 1 ---------------------------------------------------------
  * Exchange arena shared between the GPUs of one box through CUDA IPC: every rank exports a

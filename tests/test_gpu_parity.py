@@ -217,6 +217,13 @@ def test_commit_and_round1(orc, ctx, bases):
 def test_perm_product(orc, ctx, n):
     """next row §8(f)-3: round-2 grand product (dispatcher2.rs:329-345), 5 wire types"""
     common.check_perm_product(orc, ctx, n, 5, 500 + (n % 89))
+    if n == 1 << 12:   # device-resident variant
+        w, i_, s_ = (np.stack([orc.gen_fr(700 + 10 * k + t, n) for t in range(5)]) for k in range(3))
+        beta, gamma = orc.gen_fr(790, 1)[0], orc.gen_fr(791, 1)[0]
+        dev = [torch.from_numpy(a.view(np.int64)).cuda() for a in (w, i_, s_)]
+        out = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+        ctx.perm_product_dev(dev[0].data_ptr(), dev[1].data_ptr(), dev[2].data_ptr(), 5, n, beta, gamma, out.data_ptr())
+        assert np.array_equal(out.cpu().numpy().view(np.uint64), orc.perm_product(w, i_, s_, beta, gamma))
 
 
 # ---------------------------------------------------------------- full BASELINE sizes: properties

@@ -372,10 +372,10 @@ def main():
             ctx._ck(lib.dp_fft1_rows(ctx.h, tid[0], 0, n_rows, h_in.data_ptr()))
             if W == 1:
                 ctx.fft2_prepare(tid[0])
-            elif fused:
-                ctx.fft2_prepare(tid[0])
-                dist.barrier()
             else:
+                # host-buffer path: transfers dominate, so keep several tasks in flight; every task
+                # has its own send/recv buffers on the collective path (the fused arena holds one
+                # transform at a time per context)
                 s, r, blk = ctx.fft_exchange_begin(tid[0])
                 exchange(s, r, blk)
                 ctx.fft_exchange_end(tid[0])
@@ -386,7 +386,7 @@ def main():
             ctx._ck(lib.dp_fft2(ctx.h, t, h_out.data_ptr(), h_out.numel() * 8))
 
         msm_host_out = np.zeros(144, dtype=np.uint8)
-        LOOKAHEAD = 2 if W == 1 or not fused else 0    # the fused exchange has one transform in flight per context
+        LOOKAHEAD = 2
 
         def step_e2e():
             # the dispatcher issues its FFT tasks concurrently (join_all, dispatcher2.rs:294-306,

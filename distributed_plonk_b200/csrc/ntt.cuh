@@ -122,7 +122,7 @@ DP_D Fr tw_lookup(const Fr *H, uint64_t e, uint32_t log_n, uint32_t inverse) {
     const uint64_t n = (uint64_t)1 << log_n, half = n >> 1;
     e &= n - 1;
     if (inverse) e = (n - e) & (n - 1);
-    const bool neg = e >= half;
+    const bool neg = half != 0 && e >= half;  // (a one-element domain has no -1 half)
     if (neg) e -= half;
     Fr w = gmem_ld(H + e);
     return neg ? w.neg() : w;

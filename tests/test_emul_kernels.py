@@ -68,6 +68,15 @@ def test_distributed_fft_fused_peer_exchange(orc, emul_lib, W, limits):
         w.close()
 
 
+@pytest.mark.parametrize("logn,logq", [(0, 0), (0, 3), (1, 4), (2, 5)])
+def test_distributed_fft_tiny_domains(orc, emul_lib, logn, logq):
+    w = PlonkSlave(emul_lib, 0, 1)
+    w.init([b""], 1 << logn, 1 << logq)
+    common.check_distributed_fft(orc, [w], logn, False, 3, host_copy)
+    common.check_distributed_fft(orc, [w], logq, True, 4, host_copy)
+    w.close()
+
+
 def test_msm_distributions_and_geometries(orc, ctx):
     bases = orc.gen_bases(5, 600, 64, True)
     ctx.debug_set_limits(11, 9, 0)

@@ -284,9 +284,8 @@ def main():
         if W == 1:
             ctx.fft_dev(src.data_ptr(), dst.data_ptr(), is_quot, is_inv, is_coset)
         elif fused:
-            ctx.fft_dev_rows_p2p(src.data_ptr(), is_quot, is_inv, is_coset)
-            dist.barrier()                            # every rank's stores into my arena are complete
-            ctx.fft_dev_cols(dst.data_ptr())
+            # row kernels -> peer stores -> device-side barrier kernel -> column kernels, one stream
+            ctx.fft_dev_p2p(src.data_ptr(), dst.data_ptr(), is_quot, is_inv, is_coset)
         else:
             s, r, blk = ctx.fft_dev_rows(src.data_ptr(), is_quot, is_inv, is_coset)
             exchange(s, r, blk)

@@ -13,7 +13,7 @@ EXPORTS = [
     "dp_fft1", "dp_fft1_rows", "dp_fft2_prepare", "dp_fft_exchange_begin", "dp_fft_exchange_end", "dp_fft2",
     "dp_ntt", "dp_round1", "dp_get_wire", "dp_peer_arena_create", "dp_peer_attach", "dp_last_timing",
     "dp_launch_count", "dp_sync", "dp_msm_dev", "dp_ntt_dev", "dp_fft_dev", "dp_debug_set_limits",
-    "dp_last_msm_breakdown", "dp_debug_gen_bases", "dp_fft_dev_rows", "dp_fft_dev_cols", "dp_peer_ready", "dp_fft_dev_rows_p2p", "dp_msm_dev_batch", "dp_perm_product", "dp_msm_batch", "dp_perm_product_dev",
+    "dp_last_msm_breakdown", "dp_debug_gen_bases", "dp_fft_dev_rows", "dp_fft_dev_cols", "dp_peer_ready", "dp_fft_dev_rows_p2p", "dp_fft_dev_p2p", "dp_msm_dev_batch", "dp_perm_product", "dp_msm_batch", "dp_perm_product_dev",
 ]
 
 
@@ -67,6 +67,7 @@ def bind(cdll: C.CDLL) -> C.CDLL:
         "dp_msm_batch": (i, [vp, sz, C.POINTER(u64), C.POINTER(u64), C.POINTER(vp), C.POINTER(sz), C.POINTER(vp)]),
         "dp_msm_dev_batch": (i, [vp, sz, C.POINTER(u64), C.POINTER(u64), C.POINTER(vp), C.POINTER(sz), C.POINTER(vp)]),
         "dp_fft_dev_rows_p2p": (i, [vp, vp, i, i, i]),
+        "dp_fft_dev_p2p": (i, [vp, vp, vp, i, i, i]),
     }
     assert set(sig) == set(EXPORTS)
     for name, (res, args) in sig.items():
@@ -245,6 +246,9 @@ class Context:
 
     def fft_dev_rows_p2p(self, rows_ptr: int, is_quot: bool, is_inv: bool, is_coset: bool):
         self._ck(self.lib.dp_fft_dev_rows_p2p(self.h, rows_ptr, int(is_quot), int(is_inv), int(is_coset)))
+
+    def fft_dev_p2p(self, rows_ptr: int, cols_ptr: int, is_quot: bool, is_inv: bool, is_coset: bool):
+        self._ck(self.lib.dp_fft_dev_p2p(self.h, rows_ptr, cols_ptr, int(is_quot), int(is_inv), int(is_coset)))
 
     def fft_dev_cols(self, cols_ptr: int):
         self._ck(self.lib.dp_fft_dev_cols(self.h, cols_ptr))

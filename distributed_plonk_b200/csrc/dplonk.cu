@@ -148,6 +148,7 @@ struct dp_ctx {
     uint64_t arena_bytes = 0;
     Fr *peer_arena[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     uint64_t p2p_seq = 0;           // exchanges issued so far; must advance identically on every rank
+    uint32_t bar_seq = 0;           // device-side barriers issued so far (p2p_barrier_kernel)
     Fr *dev_send = nullptr, *dev_recv = nullptr;  // dp_fft_dev_rows / _cols staging (one transform in flight)
     Fr *dev_p2p_slot = nullptr;                   // receive slot of the last dp_fft_dev_rows_p2p
     int dev_flags = -1;
@@ -697,6 +698,8 @@ FftTask *find_task(dp_ctx *ctx, uint64_t id) {
     return it == ctx->tasks.end() ? nullptr : &it->second;
 }
 
+constexpr uint64_t ARENA_HEADER_BYTES = 1024;  // arrival counter of the device-side barrier, then the two slots
+
 bool p2p_ready(const dp_ctx *ctx) {
     if (ctx->W <= 1 || !ctx->arena) return false;
     for (uint64_t q = 0; q < ctx->W; q++)
@@ -706,9 +709,9 @@ bool p2p_ready(const dp_ctx *ctx) {
 
 // receive slot of the next exchange in every rank's arena (same sequence number on all ranks)
 int p2p_next_slot(dp_ctx *ctx, uint64_t recv_bytes, PeerDst &dst, Fr *&my_slot, uint64_t row_off) {
-    const uint64_t slot_bytes = ctx->arena_bytes / 2;
+    const uint64_t slot_bytes = (ctx->arena_bytes - ARENA_HEADER_BYTES) / 2;
     if (recv_bytes > slot_bytes) return fail(ctx, DP_E_COMM, "peer arena slot %llu B < receive matrix %llu B", (unsigned long long)slot_bytes, (unsigned long long)recv_bytes);
-    const uint64_t off = (ctx->p2p_seq++ & 1) * (slot_bytes / sizeof(Fr));
+    const uint64_t off = ARENA_HEADER_BYTES / sizeof(Fr) + (ctx->p2p_seq++ & 1) * (slot_bytes / sizeof(Fr));
     for (uint64_t q = 0; q < ctx->W; q++) dst.base[q] = ctx->peer_arena[q] + off;
     dst.row_off = row_off;
     my_slot = ctx->arena + off;
@@ -1485,10 +1488,11 @@ int dp_peer_arena_create(dp_ctx *ctx, uint64_t arena_bytes, void *handle_out) {
     if (ctx->arena) return fail(ctx, DP_E_STATE, "dp_peer_arena_create: arena already exists");
     if (arena_bytes < 2 * sizeof(Fr)) return fail(ctx, DP_E_ARG, "dp_peer_arena_create: arena too small");
     DP_CUDA(ctx, cudaSetDevice(ctx->device));
-    arena_bytes = (arena_bytes + 1023) & ~(uint64_t)1023;
+    arena_bytes = ((arena_bytes + 1023) & ~(uint64_t)1023) + ARENA_HEADER_BYTES;
     void *p = nullptr;
     // a dedicated cudaMalloc (not the pool): IPC handles cover whole allocations
     if (cudaMalloc(&p, arena_bytes) != cudaSuccess) return fail(ctx, DP_E_OOM, "peer arena of %llu bytes", (unsigned long long)arena_bytes);
+    cudaMemset(p, 0, ARENA_HEADER_BYTES);
     cudaIpcMemHandle_t h;
     static_assert(sizeof(cudaIpcMemHandle_t) == DP_IPC_HANDLE_BYTES, "IPC handle size");
     cudaError_t e = cudaIpcGetMemHandle(&h, p);
@@ -1545,6 +1549,32 @@ int dp_fft_dev_rows_p2p(dp_ctx *ctx, const void *rows_dev, int is_quot, int is_i
     ctx->dev_p2p_slot = slot;
     ctx->dev_flags = (is_quot ? 4 : 0) | (is_inv ? 2 : 0) | (is_coset ? 1 : 0);
     return DP_OK;
+}
+
+// rows -> peer memory -> device-side barrier -> columns, all queued on the compute stream
+int dp_fft_dev_p2p(dp_ctx *ctx, const void *rows_dev, void *cols_dev, int is_quot, int is_inv, int is_coset) {
+    if (!ctx || !rows_dev || !cols_dev) return fail(ctx, DP_E_ARG, "dp_fft_dev_p2p: NULL argument");
+    if (!ctx->inited) return fail(ctx, DP_E_STATE, "dp_fft_dev_p2p before dp_init");
+    if (!p2p_ready(ctx)) return fail(ctx, DP_E_COMM, "dp_fft_dev_p2p: peers not attached");
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const DomainDev &d = ctx->dom[is_quot ? 1 : 0];
+    const uint64_t W = ctx->W, n_rows = d.r() / W, n_cols = d.c() / W, c = d.c();
+    call_begin(ctx);
+    PeerDst peers;
+    Fr *slot = nullptr;
+    DP_TRY(p2p_next_slot(ctx, d.r() * n_cols * sizeof(Fr), peers, slot, ctx->me * n_rows * n_cols));
+    Scratch tmp(ctx->pool);
+    const bool need_scratch = d.log_c > ctx->max_contig_log_k;
+    Fr *scratch = need_scratch ? tmp.get<Fr>(n_rows * c) : nullptr;
+    if (need_scratch && !scratch) return fail(ctx, DP_E_OOM, "dp_fft_dev_p2p scratch");
+    DP_TRY(plan_row_phase(ctx, d, (const Fr *)rows_dev, nullptr, scratch, n_rows, ctx->me * n_rows, is_inv != 0, is_coset != 0, W, &peers));
+    PeerCounters pc;
+    for (uint64_t q = 0; q < 8; q++) pc.c[q] = q < W ? reinterpret_cast<uint32_t *>(ctx->peer_arena[q]) : nullptr;
+    ctx->bar_seq++;
+    DP_LAUNCH(p2p_barrier_kernel, dim3(1), dim3(32), 0, ctx->stream, pc, (uint32_t)W, (uint32_t)ctx->me, (uint32_t)(W * ctx->bar_seq));
+    ctx->launches++;
+    DP_TRY(plan_col_phase(ctx, d, slot, (Fr *)cols_dev, n_cols, ctx->me * n_cols, is_inv != 0, is_coset != 0));
+    return call_end(ctx, true);
 }
 
 }  // extern "C"

@@ -311,6 +311,32 @@ __global__ void __launch_bounds__(NTT_TPB, 2) ntt_tile_kernel(NttPass p) {
     }
 }
 
+// ------------------------------------------------------------------ device-side barrier across GPUs
+// Every rank owns a monotonically increasing arrival counter at the head of its peer arena.
+// Barrier number k: each rank adds 1 to EVERY rank's counter (system-scope atomics over NVLink)
+// after a system fence that orders the row kernel's peer stores before the arrival, then waits
+// until its own counter reaches W*k.  Launched between the row and the column kernels on the
+// same stream: the exchange needs no host synchronisation and no NCCL call at all.
+struct PeerCounters {
+    uint32_t *c[8];
+};
+__global__ void p2p_barrier_kernel(PeerCounters pc, uint32_t n_ranks, uint32_t me, uint32_t target) {
+    const uint32_t t = threadIdx.x;
+#if defined(DP_EMUL)
+    (void)me;
+    (void)target;
+    if (t < n_ranks) atomicAdd(pc.c[t], 1u);  // contexts run one after another in the emulator: no waiting
+#else
+    __threadfence_system();
+    if (t < n_ranks) atomicAdd_system(pc.c[t], 1u);
+    if (t == 0) {
+        volatile uint32_t *mine = pc.c[me];
+        while (*mine < target) __nanosleep(100);
+        __threadfence_system();
+    }
+#endif
+}
+
 // ------------------------------------------------------------------ table generation (init time)
 // stage-major butterfly twiddles: W[2^s + j] = omega_{2^(s+1)}^(+-j), j < 2^s, s < NTT_WTAB_LOG;
 // W[0] unused (= 1).  Plane-split (low / high 16 bytes) so one bulk copy per plane stages a prefix.

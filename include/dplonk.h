@@ -200,6 +200,11 @@ int dp_fft_dev_cols(dp_ctx *ctx, void *cols_dev);
 /* fused variant of _rows for attached peers: the row kernel stores into the owners' arenas; the
  * caller then only needs a barrier across ranks before dp_fft_dev_cols */
 int dp_fft_dev_rows_p2p(dp_ctx *ctx, const void *rows_dev, int is_quot, int is_inv, int is_coset);
+/* the whole distributed transform of one worker without host involvement: row kernels (stores into
+ * the owners' arenas), a device-side barrier kernel (system-scope arrival counters in the arenas,
+ * over NVLink), column kernels, queued back to back on the context stream; returns when done.
+ * Every rank must call it for the same transforms in the same order (it blocks like a collective). */
+int dp_fft_dev_p2p(dp_ctx *ctx, const void *rows_dev, void *cols_dev, int is_quot, int is_inv, int is_coset);
 
 #ifdef __cplusplus
 }

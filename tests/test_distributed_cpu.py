@@ -72,6 +72,19 @@ def _worker(rank, world, port, lib_path, out_dir, backend="gloo"):
         # CUDA IPC arenas need real GPUs (an emulated handle is a bare pointer of another process)
         ok &= bool(parallel.attach_peers(w.ctx, 2 * (1 << 9) * 32 // world))
         ok &= run_ffts("fused")           # row kernel stores straight into peer memory
+        # device-resident transform with the device-side barrier kernel (no host sync, no NCCL call)
+        for k, (inv, cos) in enumerate([(False, True), (True, True), (False, False)] * 2):
+            L = 9
+            r, c = 1 << (L >> 1), (1 << L) >> (L >> 1)
+            x = orc.gen_fr(300 + k, 1 << L)
+            rows = disp.dispatcher_rows(x, L)[rank * r // world:(rank + 1) * r // world]
+            rows_d = torch.from_numpy(np.ascontiguousarray(rows).view(np.int64)).cuda()
+            cols_d = torch.empty(((c // world) * r, 4), dtype=torch.int64, device="cuda")
+            w.ctx.fft_dev_p2p(rows_d.data_ptr(), cols_d.data_ptr(), True, inv, cos)
+            gathered = [torch.empty_like(cols_d) for _ in range(world)]
+            dist.all_gather(gathered, cols_d)
+            cols = torch.cat(gathered).cpu().numpy().view(np.uint64).reshape(c, r, 4)
+            ok &= bool(np.array_equal(disp.assemble(cols), orc.fft(x, inv, cos)))
     # sharded MSM: index-range split, partials summed by the dispatcher (rank 0 here)
     sc = orc.gen_fr(77, n_bases, False)
     lo, hi = parallel.msm_shard(n_bases, rank, world)

@@ -433,6 +433,32 @@ def main():
         perm = {"n": n, "wire_types": 5, "gpu_ms": ctx.last_timing()[0], "gpu_rows_per_sec": n / (ctx.last_timing()[0] * 1e-3)}
         del wt, zt
 
+    # ---- "next" row 8f-1, measured beside the schedule: rounds 3-5 on device-resident polynomials
+    rounds = None
+    if W == 1 and os.environ.get("DP_BENCH_SKIP_ROUNDS", "0") != "1":
+        try:
+            arrs = [rand_fr(m) for _ in range(25)]
+            qo = torch.empty((m, 4), dtype=torch.int64, device="cuda")
+            ch = np.array([[3, 1, 4, 1], [5, 9, 2, 6], [5, 3, 5, 8], [9, 7, 9, 3], [2, 3, 8, 4], [6, 2, 6, 4], [3, 3, 8, 3], [2, 7, 9, 5]], dtype=np.uint64)
+            ptr = [t.data_ptr() for t in arrs]
+            ms = {}
+            for _ in range(2):
+                ctx.quotient_evals_dev(ptr[:13], ptr[13:18], ptr[18:23], ptr[23], ptr[24], ch[:5], ch[5], ch[6], ch[7], qo.data_ptr())
+            ms["quotient_evals_8n"] = ctx.last_timing()[0]
+            for _ in range(2):
+                ctx.poly_eval(ptr[0], ch[5], n + 3)
+            ms["poly_eval_n"] = ctx.last_timing()[0]
+            for _ in range(2):
+                ctx.poly_div_linear(ptr[0], ch[5], n + 3, qo.data_ptr())
+            ms["poly_div_linear_n"] = ctx.last_timing()[0]
+            for _ in range(2):
+                ctx.poly_lincomb(ptr[:12], ch[[0, 1, 2, 3, 4, 5, 6, 7, 0, 1, 2, 3]], out_len=n + 3, lens=[n + 3] * 12, out_ptr=qo.data_ptr())
+            ms["poly_lincomb_12xn"] = ctx.last_timing()[0]
+            rounds = {"gpu_ms": ms, "note": "device-resident polynomials; quotient over the 8n coset domain (25 input arrays), the others over n+3 coefficients"}
+            del arrs, qo
+        except Exception as e:  # the headline numbers above must survive a failure of this extra
+            rounds = {"error": str(e)[:200]}
+
     if rank != 0:
         if W > 1:
             dist.destroy_process_group()
@@ -499,7 +525,7 @@ def main():
         "breakdown_ms": {"msm_total": msm_total, "msm_accumulate": acc_total, "intt_n_total": sum(stats["ntt_n_ms"]),
                          "coset_ntt_8n_total": ntt_m_total},
         "roofline": roofline, "roofline_ntt": ntt_hbm, "roofline_compute": compute, "e2e": e2e,
-        "next_row_perm_product": perm,
+        "next_row_perm_product": perm, "next_row_rounds_3_to_5": rounds,
     }
     if not args.no_cpu and W == 1:
         from oracle import loader as orc
@@ -514,6 +540,14 @@ def main():
             orc.perm_product(pw[0], pw[1], pw[2], orc.gen_fr(98, 1)[0], orc.gen_fr(99, 1)[0])
             perm["cpu_rows_per_sec"] = pn / (time.perf_counter() - t0)
             perm["cpu_note"] = "oracle restatement, 1 thread (the reference loop is serial), 2^14-row sample"
+        if rounds and "gpu_ms" in rounds:   # dispatcher2.rs:434-504 restated (all host threads), 2^17-point sample
+            qm, qn = 1 << 17, 1 << 14
+            qa = [np.stack([orc.gen_fr(200 + 20 * k + i, qm) for i in range(c)]) for k, c in enumerate((13, 5, 5))]
+            t0 = time.perf_counter()
+            orc.quotient_evals(qa[0], qa[1], qa[2], orc.gen_fr(290, qm), orc.gen_fr(291, qm), orc.gen_fr(292, 5), orc.gen_fr(293, 1)[0],
+                               orc.gen_fr(294, 1)[0], orc.gen_fr(295, 1)[0], qn)
+            rounds["cpu_quotient_points_per_sec"] = qm / (time.perf_counter() - t0)
+            rounds["gpu_quotient_points_per_sec"] = m / (rounds["gpu_ms"]["quotient_evals_8n"] * 1e-3)
     print(json.dumps(line), flush=True)
     if W > 1:
         dist.destroy_process_group()

@@ -14,6 +14,8 @@ EXPORTS = [
     "dp_ntt", "dp_round1", "dp_get_wire", "dp_peer_arena_create", "dp_peer_attach", "dp_last_timing",
     "dp_launch_count", "dp_sync", "dp_msm_dev", "dp_ntt_dev", "dp_fft_dev", "dp_debug_set_limits",
     "dp_last_msm_breakdown", "dp_debug_gen_bases", "dp_fft_dev_rows", "dp_fft_dev_cols", "dp_peer_ready", "dp_fft_dev_rows_p2p", "dp_fft_dev_p2p", "dp_msm_dev_batch", "dp_perm_product", "dp_msm_batch", "dp_perm_product_dev",
+    "dp_quotient_evals", "dp_quotient_evals_dev", "dp_poly_eval", "dp_poly_eval_dev", "dp_poly_lincomb", "dp_poly_lincomb_dev",
+    "dp_poly_div_linear", "dp_poly_div_linear_dev",
 ]
 
 
@@ -26,6 +28,12 @@ class DpError(RuntimeError):
 class FftWorkload(C.Structure):
     """utils.rs:3-19 / hello_world.capnp:8-13"""
     _fields_ = [("row_start", C.c_uint64), ("row_end", C.c_uint64), ("col_start", C.c_uint64), ("col_end", C.c_uint64)]
+
+
+class QuotientArgs(C.Structure):
+    """dp_quotient_args (include/dplonk.h): 25 polynomial-sized arrays + the challenges"""
+    _fields_ = [("selectors", C.c_void_p * 13), ("sigmas", C.c_void_p * 5), ("wires", C.c_void_p * 5), ("perm", C.c_void_p),
+                ("pub_input", C.c_void_p), ("k", C.c_void_p), ("alpha", C.c_void_p), ("beta", C.c_void_p), ("gamma", C.c_void_p)]
 
 
 def bind(cdll: C.CDLL) -> C.CDLL:
@@ -68,6 +76,14 @@ def bind(cdll: C.CDLL) -> C.CDLL:
         "dp_msm_dev_batch": (i, [vp, sz, C.POINTER(u64), C.POINTER(u64), C.POINTER(vp), C.POINTER(sz), C.POINTER(vp)]),
         "dp_fft_dev_rows_p2p": (i, [vp, vp, i, i, i]),
         "dp_fft_dev_p2p": (i, [vp, vp, vp, i, i, i]),
+        "dp_quotient_evals": (i, [vp, C.POINTER(QuotientArgs), vp]),
+        "dp_quotient_evals_dev": (i, [vp, C.POINTER(QuotientArgs), vp]),
+        "dp_poly_eval": (i, [vp, vp, sz, vp, vp]),
+        "dp_poly_eval_dev": (i, [vp, vp, sz, vp, vp]),
+        "dp_poly_lincomb": (i, [vp, C.POINTER(vp), C.POINTER(sz), vp, sz, vp, sz]),
+        "dp_poly_lincomb_dev": (i, [vp, C.POINTER(vp), C.POINTER(sz), vp, sz, vp, sz]),
+        "dp_poly_div_linear": (i, [vp, vp, sz, vp, vp, vp]),
+        "dp_poly_div_linear_dev": (i, [vp, vp, sz, vp, vp, vp]),
     }
     assert set(sig) == set(EXPORTS)
     for name, (res, args) in sig.items():
@@ -187,6 +203,76 @@ class Context:
     def perm_product_dev(self, wires_ptr: int, id_ptr: int, sigma_ptr: int, n_types: int, n: int, beta: np.ndarray, gamma: np.ndarray, out_ptr: int):
         b, g = np.ascontiguousarray(beta, dtype=np.uint64), np.ascontiguousarray(gamma, dtype=np.uint64)
         self._ck(self.lib.dp_perm_product_dev(self.h, wires_ptr, id_ptr, sigma_ptr, n_types, n, _addr(b), _addr(g), out_ptr))
+
+    # ---- rounds 3-5 ("next" row 1): plain = host arrays, *_dev = device pointers (ints)
+    @staticmethod
+    def _quotient_args(selectors, sigmas, wires, perm, pub_input, k, alpha, beta, gamma, keep):
+        """pointers may be ints (device) or numpy arrays (host; kept alive in `keep`)"""
+        def ptr(x):
+            if isinstance(x, int):
+                return x
+            a = np.ascontiguousarray(x, dtype=np.uint64)
+            keep.append(a)
+            return a.ctypes.data
+        q = QuotientArgs()
+        for j in range(13):
+            q.selectors[j] = ptr(selectors[j])
+        for j in range(5):
+            q.sigmas[j] = ptr(sigmas[j])
+            q.wires[j] = ptr(wires[j])
+        q.perm, q.pub_input = ptr(perm), ptr(pub_input)
+        q.k, q.alpha, q.beta, q.gamma = ptr(np.asarray(k)), ptr(np.asarray(alpha)), ptr(np.asarray(beta)), ptr(np.asarray(gamma))
+        return q
+
+    def quotient_evals(self, selectors, sigmas, wires, perm, pub_input, k, alpha, beta, gamma) -> np.ndarray:
+        """round 3 (dispatcher2.rs:434-504) on host arrays: selectors [13][m,4], sigmas / wires [5][m,4], ..."""
+        keep = []
+        q = self._quotient_args(selectors, sigmas, wires, perm, pub_input, k, alpha, beta, gamma, keep)
+        out = np.empty((np.asarray(perm).shape[0], 4), dtype=np.uint64)
+        self._ck(self.lib.dp_quotient_evals(self.h, C.byref(q), _addr(out)))
+        return out
+
+    def quotient_evals_dev(self, selectors, sigmas, wires, perm, pub_input, k, alpha, beta, gamma, out_ptr: int):
+        keep = []
+        q = self._quotient_args(selectors, sigmas, wires, perm, pub_input, k, alpha, beta, gamma, keep)
+        self._ck(self.lib.dp_quotient_evals_dev(self.h, C.byref(q), out_ptr))
+
+    def poly_eval(self, coeffs, point: np.ndarray, n: int | None = None) -> np.ndarray:
+        """round 4: p(point); coeffs = [n,4] host array, or a device pointer with n given"""
+        pt, out = np.ascontiguousarray(point, dtype=np.uint64), np.empty(4, dtype=np.uint64)
+        if isinstance(coeffs, int):
+            self._ck(self.lib.dp_poly_eval_dev(self.h, coeffs, n, _addr(pt), _addr(out)))
+        else:
+            c = np.ascontiguousarray(coeffs, dtype=np.uint64)
+            self._ck(self.lib.dp_poly_eval(self.h, _addr(c) if c.size else None, c.shape[0], _addr(pt), _addr(out)))
+        return out
+
+    def poly_div_linear(self, coeffs, point: np.ndarray, n: int | None = None, out_ptr: int | None = None):
+        """round 5: (quotient of p / (X - point), remainder p(point)); device form writes the quotient to out_ptr"""
+        pt, rem = np.ascontiguousarray(point, dtype=np.uint64), np.empty(4, dtype=np.uint64)
+        if isinstance(coeffs, int):
+            self._ck(self.lib.dp_poly_div_linear_dev(self.h, coeffs, n, _addr(pt), out_ptr, _addr(rem)))
+            return None, rem
+        c = np.ascontiguousarray(coeffs, dtype=np.uint64)
+        out = np.empty((max(c.shape[0] - 1, 0), 4), dtype=np.uint64)
+        self._ck(self.lib.dp_poly_div_linear(self.h, _addr(c) if c.size else None, c.shape[0], _addr(pt), _addr(out) if out.size else None, _addr(rem)))
+        return out, rem
+
+    def poly_lincomb(self, polys, coeffs: np.ndarray, out_len: int | None = None, lens=None, out_ptr: int | None = None):
+        """round 5: sum_i coeffs[i] * polys[i]; polys = host arrays, or device pointers with lens and out_ptr given"""
+        cf = np.ascontiguousarray(coeffs, dtype=np.uint64)
+        k = len(polys)
+        if out_ptr is not None:
+            ptrs, ln = (C.c_void_p * k)(*polys), (C.c_size_t * k)(*lens)
+            self._ck(self.lib.dp_poly_lincomb_dev(self.h, ptrs, ln, _addr(cf), k, out_ptr, out_len))
+            return None
+        ps = [np.ascontiguousarray(x, dtype=np.uint64) for x in polys]
+        ln = [x.shape[0] for x in ps]
+        n_out = max(ln) if out_len is None else out_len
+        out = np.empty((n_out, 4), dtype=np.uint64)
+        ptrs = (C.c_void_p * k)(*[x.ctypes.data if x.size else None for x in ps])
+        self._ck(self.lib.dp_poly_lincomb(self.h, ptrs, (C.c_size_t * k)(*ln), _addr(cf), k, _addr(out) if n_out else None, n_out))
+        return out
 
     def get_wire(self) -> np.ndarray:
         n = C.c_size_t()

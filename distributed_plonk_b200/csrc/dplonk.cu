@@ -14,6 +14,7 @@
 #include "msm.cuh"
 #include "ntt.cuh"
 #include "perm.cuh"
+#include "rounds.cuh"
 
 using namespace dp;
 
@@ -1575,6 +1576,269 @@ int dp_fft_dev_p2p(dp_ctx *ctx, const void *rows_dev, void *cols_dev, int is_quo
     ctx->launches++;
     DP_TRY(plan_col_phase(ctx, d, slot, (Fr *)cols_dev, n_cols, ctx->me * n_cols, is_inv != 0, is_coset != 0));
     return call_end(ctx, true);
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ rounds 3-5 ("next" row 1)
+namespace {
+
+// z^(2^j), j < RND_POW_TABLE, computed on the host and uploaded (80 squarings)
+int upload_pow_table(dp_ctx *ctx, const Fr &z, Fr *pw_dev) {
+    Fr host[RND_POW_TABLE];
+    host[0] = z;
+    for (int j = 1; j < RND_POW_TABLE; j++) host[j] = host[j - 1].sqr();
+    DP_CUDA(ctx, cudaMemcpyAsync(pw_dev, host, sizeof host, cudaMemcpyHostToDevice, ctx->stream));
+    DP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `host` is a stack buffer
+    return DP_OK;
+}
+
+// *out_dev = sum_k in[k] * (z^(2^e))^k
+int poly_fold_device(dp_ctx *ctx, const Fr *in, uint64_t n, const Fr *pw, uint32_t e, Fr *out_dev) {
+    Scratch tmp(ctx->pool);
+    while (true) {
+        const uint64_t nb = (n + RND_CHUNK - 1) / RND_CHUNK;
+        Fr *dst = nb == 1 ? out_dev : tmp.get<Fr>(nb);
+        if (!dst) return fail(ctx, DP_E_OOM, "poly fold scratch");
+        DP_LAUNCH(poly_fold_kernel, dim3((unsigned)nb), dim3(RND_TPB), 0, ctx->stream, in, n, pw, e, dst);
+        ctx->launches++;
+        if (nb == 1) break;
+        in = dst;
+        n = nb;
+        e += RND_LOG_CHUNK;
+    }
+    DP_CUDA(ctx, cudaGetLastError());
+    return DP_OK;
+}
+
+// E_j = sum_{k >= j} in[k] * y^(k-j), y = z^(2^e); stored at out[j - shift]; E_0 -> *rem when shift = 1
+int poly_suffix_device(dp_ctx *ctx, const Fr *in, uint64_t n, const Fr *pw, uint32_t e, Fr *out, uint32_t shift, Fr *rem) {
+    const uint64_t nb = (n + RND_CHUNK - 1) / RND_CHUNK;
+    Scratch tmp(ctx->pool);
+    Fr *carry = nullptr;
+    if (nb > 1) {
+        Fr *tot = tmp.get<Fr>(nb);
+        carry = tmp.get<Fr>(nb);
+        if (!tot || !carry) return fail(ctx, DP_E_OOM, "poly suffix scratch");
+        DP_LAUNCH(poly_fold_kernel, dim3((unsigned)nb), dim3(RND_TPB), 0, ctx->stream, in, n, pw, e, tot);
+        ctx->launches++;
+        DP_TRY(poly_suffix_device(ctx, tot, nb, pw, e + RND_LOG_CHUNK, carry, 0, nullptr));
+    }
+    DP_LAUNCH(poly_suffix_kernel, dim3((unsigned)nb), dim3(RND_TPB), 0, ctx->stream, in, n, pw, e, (const Fr *)carry, nb, out, shift, rem);
+    ctx->launches++;
+    DP_CUDA(ctx, cudaGetLastError());
+    return DP_OK;
+}
+
+int quotient_device(dp_ctx *ctx, const dp_quotient_args &a, const Fr *const *arrays /* 25 device arrays */, Fr *out_dev) {
+    const DomainDev &dq = ctx->dom[1], &dg = ctx->dom[0];
+    const uint64_t m = dq.n(), n = dg.n();
+    if (m < n || m / n > RND_MAX_RATIO) return fail(ctx, DP_E_ARG, "quotient domain / gate domain = %llu, supported: 1..%d", (unsigned long long)(m / n), RND_MAX_RATIO);
+    QuotientArgs q;
+    for (int i = 0; i < 13; i++) q.sel[i] = arrays[i];
+    for (int i = 0; i < 5; i++) q.sig[i] = arrays[13 + i];
+    for (int i = 0; i < 5; i++) q.w[i] = arrays[18 + i];
+    q.z = arrays[23];
+    q.pi = arrays[24];
+    Fr k[5];
+    memcpy(k, a.k, sizeof k);
+    memcpy(&q.alpha, a.alpha, sizeof(Fr));
+    memcpy(&q.beta, a.beta, sizeof(Fr));
+    memcpy(&q.gamma, a.gamma, sizeof(Fr));
+    for (int i = 0; i < 5; i++) q.k_beta[i] = k[i] * q.beta;
+    q.alpha_sq_div_n = q.alpha.sqr() * dg.n_inv;           // dispatcher2.rs:363
+    q.gen = fr_from_u64(7);
+    q.ratio = (uint32_t)(m / n);
+    // 1 / Z_H(x_i), x_i = g omega_m^i, i < m/n: x_i^n = g^n (omega_m^n)^i   (dispatcher2.rs:372-379)
+    const Fr gn = q.gen.pow(n), wn = fr_domain_gen(dq.log_n).pow(n);
+    Fr cur = gn;
+    for (uint32_t i = 0; i < q.ratio; i++) {
+        const Fr zh = cur - Fr::one();
+        if (zh.is_zero()) return fail(ctx, DP_E_ARG, "Z_H vanishes on the quotient coset (domains %llu / %llu)", (unsigned long long)n, (unsigned long long)m);
+        q.zh_inv[i] = zh.inverse();
+        cur = cur * wn;
+    }
+    for (uint32_t i = q.ratio; i < RND_MAX_RATIO; i++) q.zh_inv[i] = Fr::zero();
+    q.H = dq.H;
+    q.m = m;
+    q.log_m = dq.log_n;
+    q.out = out_dev;
+    // all blocks' 1 / prod(x_i - 1) up front, one thread per block, instead of one serial inversion inside each block
+    const unsigned n_blocks = blocks_for(m, QUO_TPB);
+    Scratch tmp(ctx->pool);
+    Fr *prod = tmp.get<Fr>(n_blocks);
+    if (!prod) return fail(ctx, DP_E_OOM, "quotient scratch");
+    DP_LAUNCH(quotient_xm1_products_kernel, dim3(n_blocks), dim3(QUO_TPB), 0, ctx->stream, q.gen, q.H, q.log_m, m, prod);
+    DP_LAUNCH(fr_invert_kernel, dim3(blocks_for(n_blocks, 128)), dim3(128), 0, ctx->stream, prod, (uint64_t)n_blocks);
+    q.prod_inv = prod;
+    DP_LAUNCH(quotient_kernel, dim3(n_blocks), dim3(QUO_TPB), 0, ctx->stream, q);
+    ctx->launches += 3;
+    DP_CUDA(ctx, cudaGetLastError());
+    return DP_OK;
+}
+
+const void *const *quotient_ptrs(const dp_quotient_args &a, const void *flat[25]) {
+    for (int i = 0; i < 13; i++) flat[i] = a.selectors[i];
+    for (int i = 0; i < 5; i++) flat[13 + i] = a.sigmas[i];
+    for (int i = 0; i < 5; i++) flat[18 + i] = a.wires[i];
+    flat[23] = a.perm;
+    flat[24] = a.pub_input;
+    return flat;
+}
+
+int quotient_check(dp_ctx *ctx, const dp_quotient_args *a, const void *out, const char *who) {
+    if (!ctx || !a || !out) return fail(ctx, DP_E_ARG, "%s: NULL argument", who);
+    if (!ctx->inited) return fail(ctx, DP_E_STATE, "%s before dp_init", who);
+    const void *flat[25];
+    quotient_ptrs(*a, flat);
+    for (int i = 0; i < 25; i++)
+        if (!flat[i]) return fail(ctx, DP_E_ARG, "%s: polynomial %d is NULL", who, i);
+    if (!a->k || !a->alpha || !a->beta || !a->gamma) return fail(ctx, DP_E_ARG, "%s: NULL challenge", who);
+    return DP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dp_quotient_evals(dp_ctx *ctx, const dp_quotient_args *a, void *out) {
+    DP_TRY(quotient_check(ctx, a, out, "dp_quotient_evals"));
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    call_begin(ctx);
+    const uint64_t m = ctx->dom[1].n();
+    const void *flat[25];
+    quotient_ptrs(*a, flat);
+    Scratch tmp(ctx->pool);
+    const Fr *dev[25];
+    for (int i = 0; i < 25; i++) {
+        Fr *d = tmp.get<Fr>(m);
+        if (!d) return fail(ctx, DP_E_OOM, "dp_quotient_evals: 26 x %llu B of device memory", (unsigned long long)(m * sizeof(Fr)));
+        DP_CUDA(ctx, cudaMemcpyAsync(d, flat[i], m * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+        dev[i] = d;
+    }
+    Fr *o = tmp.get<Fr>(m);
+    if (!o) return fail(ctx, DP_E_OOM, "dp_quotient_evals output");
+    DP_TRY(quotient_device(ctx, *a, dev, o));
+    DP_CUDA(ctx, cudaMemcpyAsync(out, o, m * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    return call_end(ctx, true);
+}
+
+int dp_quotient_evals_dev(dp_ctx *ctx, const dp_quotient_args *a, void *out_dev) {
+    DP_TRY(quotient_check(ctx, a, out_dev, "dp_quotient_evals_dev"));
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    call_begin(ctx);
+    const void *flat[25];
+    quotient_ptrs(*a, flat);
+    DP_TRY(quotient_device(ctx, *a, reinterpret_cast<const Fr *const *>(flat), (Fr *)out_dev));
+    return call_end(ctx, true);
+}
+
+static int poly_eval_any(dp_ctx *ctx, const void *coeffs, size_t n, const void *point, void *out32, bool on_device, const char *who) {
+    if (!ctx || !point || !out32 || (n && !coeffs)) return fail(ctx, DP_E_ARG, "%s: NULL argument", who);
+    if (n == 0) {  // the zero polynomial
+        memset(out32, 0, sizeof(Fr));
+        return DP_OK;
+    }
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    call_begin(ctx);
+    Scratch tmp(ctx->pool);
+    Fr *pw = tmp.get<Fr>(RND_POW_TABLE), *res = tmp.get<Fr>(1);
+    const Fr *src = (const Fr *)coeffs;
+    if (!on_device) {
+        Fr *c = tmp.get<Fr>(n);
+        if (!c) return fail(ctx, DP_E_OOM, "%s buffers", who);
+        DP_CUDA(ctx, cudaMemcpyAsync(c, coeffs, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+        src = c;
+    }
+    if (!pw || !res) return fail(ctx, DP_E_OOM, "%s buffers", who);
+    Fr z;
+    memcpy(&z, point, sizeof z);
+    DP_TRY(upload_pow_table(ctx, z, pw));
+    DP_TRY(poly_fold_device(ctx, src, n, pw, 0, res));
+    DP_CUDA(ctx, cudaMemcpyAsync(out32, res, sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    return call_end(ctx, true);
+}
+int dp_poly_eval(dp_ctx *ctx, const void *coeffs, size_t n, const void *point, void *out32) {
+    return poly_eval_any(ctx, coeffs, n, point, out32, false, "dp_poly_eval");
+}
+int dp_poly_eval_dev(dp_ctx *ctx, const void *coeffs_dev, size_t n, const void *point, void *out32) {
+    return poly_eval_any(ctx, coeffs_dev, n, point, out32, true, "dp_poly_eval_dev");
+}
+
+static int poly_div_any(dp_ctx *ctx, const void *coeffs, size_t n, const void *point, void *out, void *rem32, bool on_device, const char *who) {
+    if (!ctx || !point || (n && !coeffs) || (n > 1 && !out)) return fail(ctx, DP_E_ARG, "%s: NULL argument", who);
+    if (n == 0) {
+        if (rem32) memset(rem32, 0, sizeof(Fr));
+        return DP_OK;
+    }
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    call_begin(ctx);
+    Scratch tmp(ctx->pool);
+    Fr *pw = tmp.get<Fr>(RND_POW_TABLE), *rem = tmp.get<Fr>(1);
+    if (!pw || !rem) return fail(ctx, DP_E_OOM, "%s buffers", who);
+    const Fr *src = (const Fr *)coeffs;
+    Fr *dst = (Fr *)out;
+    if (!on_device) {
+        Fr *c = tmp.get<Fr>(n), *q = tmp.get<Fr>(n);
+        if (!c || !q) return fail(ctx, DP_E_OOM, "%s buffers", who);
+        DP_CUDA(ctx, cudaMemcpyAsync(c, coeffs, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+        src = c;
+        dst = q;
+    }
+    Fr z;
+    memcpy(&z, point, sizeof z);
+    DP_TRY(upload_pow_table(ctx, z, pw));
+    DP_TRY(poly_suffix_device(ctx, src, n, pw, 0, dst, 1, rem));
+    if (!on_device && n > 1) DP_CUDA(ctx, cudaMemcpyAsync(out, dst, (n - 1) * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    if (rem32) DP_CUDA(ctx, cudaMemcpyAsync(rem32, rem, sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    return call_end(ctx, true);
+}
+int dp_poly_div_linear(dp_ctx *ctx, const void *coeffs, size_t n, const void *point, void *out, void *rem32) {
+    return poly_div_any(ctx, coeffs, n, point, out, rem32, false, "dp_poly_div_linear");
+}
+int dp_poly_div_linear_dev(dp_ctx *ctx, const void *coeffs_dev, size_t n, const void *point, void *out_dev, void *rem32) {
+    return poly_div_any(ctx, coeffs_dev, n, point, out_dev, rem32, true, "dp_poly_div_linear_dev");
+}
+
+static int poly_lincomb_any(dp_ctx *ctx, const void *const *polys, const size_t *lens, const void *coeffs, size_t k, void *out, size_t out_len,
+                            bool on_device, const char *who) {
+    if (!ctx || !polys || !lens || !coeffs || (out_len && !out)) return fail(ctx, DP_E_ARG, "%s: NULL argument", who);
+    if (k == 0 || k > RND_MAX_POLYS) return fail(ctx, DP_E_ARG, "%s: %zu polynomials (1..%d)", who, k, RND_MAX_POLYS);
+    if (out_len == 0) return DP_OK;
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    call_begin(ctx);
+    Scratch tmp(ctx->pool);
+    LincombArgs a;
+    memset(&a, 0, sizeof a);
+    a.k = (uint32_t)k;
+    a.out_len = out_len;
+    memcpy(a.coeff, coeffs, k * sizeof(Fr));
+    for (size_t i = 0; i < k; i++) {
+        a.len[i] = lens[i] < out_len ? lens[i] : out_len;
+        if (a.len[i] && !polys[i]) return fail(ctx, DP_E_ARG, "%s: polynomial %zu is NULL", who, i);
+        if (on_device || a.len[i] == 0) {
+            a.poly[i] = (const Fr *)polys[i];
+        } else {
+            Fr *d = tmp.get<Fr>(a.len[i]);
+            if (!d) return fail(ctx, DP_E_OOM, "%s buffers", who);
+            DP_CUDA(ctx, cudaMemcpyAsync(d, polys[i], a.len[i] * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+            a.poly[i] = d;
+        }
+    }
+    Fr *dst = on_device ? (Fr *)out : tmp.get<Fr>(out_len);
+    if (!dst) return fail(ctx, DP_E_OOM, "%s buffers", who);
+    a.out = dst;
+    DP_LAUNCH(poly_lincomb_kernel, dim3(blocks_for(out_len, 256)), dim3(256), 0, ctx->stream, a);
+    ctx->launches++;
+    DP_CUDA(ctx, cudaGetLastError());
+    if (!on_device) DP_CUDA(ctx, cudaMemcpyAsync(out, dst, out_len * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    return call_end(ctx, true);
+}
+int dp_poly_lincomb(dp_ctx *ctx, const void *const *polys, const size_t *lens, const void *coeffs, size_t k, void *out, size_t out_len) {
+    return poly_lincomb_any(ctx, polys, lens, coeffs, k, out, out_len, false, "dp_poly_lincomb");
+}
+int dp_poly_lincomb_dev(dp_ctx *ctx, const void *const *polys_dev, const size_t *lens, const void *coeffs, size_t k, void *out_dev, size_t out_len) {
+    return poly_lincomb_any(ctx, polys_dev, lens, coeffs, k, out_dev, out_len, true, "dp_poly_lincomb_dev");
 }
 
 }  // extern "C"

@@ -143,6 +143,48 @@ int dp_perm_product(dp_ctx *ctx, const void *wires, const void *id_perm, const v
 int dp_perm_product_dev(dp_ctx *ctx, const void *wires_dev, const void *id_dev, const void *sigma_dev, size_t num_wire_types, size_t n,
                         const void *beta, const void *gamma, void *out_dev);
 
+/* ---- "next" row: rounds 3-5 of Prover::prove on polynomials resident on the worker
+ *
+ * The reference declares round3 / round4 / round5 RPCs (hello_world.capnp:26-44) but never implements
+ * them: the dispatcher pulls every polynomial back and does this arithmetic serially
+ * (src/dispatcher2.rs:363-690).  These entries are the bodies those RPCs would call.  The plain
+ * entries take host buffers (copied in and out); the *_dev entries take device pointers for the
+ * polynomial-sized arrays (challenges and points stay host-side, 32 B each).  All values raw
+ * Montgomery Fr; results byte-identical to the reference's sequential code.                        */
+
+typedef struct dp_quotient_args {
+    const void *selectors[13]; /* q_lc[4], q_mul[2], q_hash[4], q_o, q_c, q_ecc (dispatcher2.rs:437-450) */
+    const void *sigmas[5];
+    const void *wires[5];
+    const void *perm;      /* permutation product polynomial z                                          */
+    const void *pub_input;
+    /* ^ 25 arrays of quot_domain_size Fr: coset evaluations over the quotient domain (lines 381-432)  */
+    const void *k;         /* vk.k, 5 Fr, host                                                          */
+    const void *alpha, *beta, *gamma; /* 1 Fr each, host                                                */
+} dp_quotient_args;
+
+/* Round 3, src/dispatcher2.rs:434-504: out[i] = 1/Z_H(x_i) * (gate(i) + alpha * permutation(i)) +
+ * alpha^2/n * (z[i] - 1)/(x_i - 1), x_i = g * omega_m^i, over the quotient domain given to dp_init
+ * (GATE_WIDTH 4, five wire types); the input of the final coset iFFT (line 507, dp_ntt).          */
+int dp_quotient_evals(dp_ctx *ctx, const dp_quotient_args *host_arrays, void *out);
+int dp_quotient_evals_dev(dp_ctx *ctx, const dp_quotient_args *dev_arrays, void *out_dev);
+
+/* Round 4, DensePolynomial::evaluate (src/dispatcher2.rs:535-548): out32 = sum_j coeffs[j] * point^j */
+int dp_poly_eval(dp_ctx *ctx, const void *coeffs, size_t n, const void *point, void *out32);
+int dp_poly_eval_dev(dp_ctx *ctx, const void *coeffs_dev, size_t n, const void *point, void *out32);
+
+/* Round 5, the folds of src/dispatcher2.rs:566-649 (lin_poly, r_quot, batch_poly):
+ * out[j] = sum_{i<k} coeffs[i] * polys[i][j], polys[i] zero-extended past lens[i]; k <= 32.
+ * polys / lens / coeffs are host arrays; polys[i] points to host (plain) or device (_dev) memory.  */
+int dp_poly_lincomb(dp_ctx *ctx, const void *const *polys, const size_t *lens, const void *coeffs, size_t k, void *out, size_t out_len);
+int dp_poly_lincomb_dev(dp_ctx *ctx, const void *const *polys_dev, const size_t *lens, const void *coeffs, size_t k, void *out_dev,
+                        size_t out_len);
+
+/* Round 5, the opening witnesses (src/dispatcher2.rs:651-666, 672-688): the n-1 coefficients of
+ * p(X) / (X - point) into out, and the remainder p(point) into rem32 when it is not NULL.          */
+int dp_poly_div_linear(dp_ctx *ctx, const void *coeffs, size_t n, const void *point, void *out, void *rem32);
+int dp_poly_div_linear_dev(dp_ctx *ctx, const void *coeffs_dev, size_t n, const void *point, void *out_dev, void *rem32);
+
 /* ---- peer transport for n_workers > 1 ---------------------------------------------------------
  * Exchange arena shared between the GPUs of one box through CUDA IPC: every rank exports a
  * handle, the ranks swap them out of band (torch.distributed / the capnp control plane) and attach

@@ -482,6 +482,143 @@ int orc_perm_product(const u64 *wires, const u64 *id, const u64 *sigma, u64 n_ty
     return 0;
 }
 
+/* ------------------------------------------------------------------ rounds 3-5 of Prover::prove
+ * ("next" row 1 of SURVEY.md 8f: the arithmetic the dispatcher does between the transforms)        */
+
+/* Round 3: coset evaluations of the quotient polynomial over the quotient domain, before the final
+ * coset iFFT (src/dispatcher2.rs:363-504).  Same expression, same order of terms:
+ *   z_h_inv[i % (m/n)] * (gate(i) + alpha * (acc1 - acc2)) + alpha^2/n * (z[i] - 1) / (x_i - 1)
+ * with x_i = g * omega_m^i (lines 366-369), z_h_inv[i] = 1/(x_i^n - 1) (372-379), GATE_WIDTH = 4,
+ * selectors in the order q_lc[4], q_mul[2], q_hash[4], q_o, q_c, q_ecc (437-450), five wire types.
+ * selectors [13][m], sigmas [5][m], wires [5][m], perm [m], pub_input [m], k [5]; out [m].        */
+void orc_quotient_evals(const u64 *selectors, const u64 *sigmas, const u64 *wires, const u64 *perm,
+                        const u64 *pub_input, const u64 *k, const u64 *alpha_, const u64 *beta_,
+                        const u64 *gamma_, u64 n, u64 m, u64 *out) {
+    const fr_t *sel = (const fr_t *)selectors, *sg = (const fr_t *)sigmas, *w = (const fr_t *)wires;
+    const fr_t *z = (const fr_t *)perm, *pi = (const fr_t *)pub_input, *vk_k = (const fr_t *)k;
+    const fr_t alpha = *(const fr_t *)alpha_, beta = *(const fr_t *)beta_, gamma = *(const fr_t *)gamma_;
+    fr_t *q = (fr_t *)out;
+    const u64 ratio = m / n;
+    fr_t one, nf, ninv, alpha_sq_div_n, gen, omega;
+    fr_set_one(&one);
+    fr_from_u64(&nf, n);
+    fr_inv(&ninv, &nf);
+    fr_sqr(&alpha_sq_div_n, &alpha);
+    fr_mul(&alpha_sq_div_n, &alpha_sq_div_n, &ninv); /* alpha.square() / Fr::from(n), line 363 */
+    fr_from_u64(&gen, 7);
+    domain_gen(&omega, log2_ceil(m), 0);
+    fr_t *x = (fr_t *)malloc(m * sizeof(fr_t));
+    x[0] = gen;
+    for (u64 i = 1; i < m; i++) fr_mul(&x[i], &x[i - 1], &omega);
+    fr_t *z_h_inv = (fr_t *)malloc(ratio * sizeof(fr_t));
+    for (u64 i = 0; i < ratio; i++) {
+        fr_t t;
+        fr_pow_u64(&t, &x[i], n);
+        fr_sub(&t, &t, &one);
+        fr_inv(&z_h_inv[i], &t);
+    }
+#pragma omp parallel for schedule(static)
+    for (u64 i = 0; i < m; i++) {
+        const fr_t a = w[0 * m + i], b = w[1 * m + i], c = w[2 * m + i], d = w[3 * m + i], e = w[4 * m + i];
+        fr_t ab, cd, t, u, gate;
+        fr_mul(&ab, &a, &b);
+        fr_mul(&cd, &c, &d);
+        fr_add(&gate, &sel[11 * m + i], &pi[i]); /* q_c + pub_input */
+        const fr_t lc_in[4] = {a, b, c, d};
+        for (int j = 0; j < 4; j++) { /* q_lc[j] * wire_j */
+            fr_mul(&t, &sel[j * m + i], &lc_in[j]);
+            fr_add(&gate, &gate, &t);
+        }
+        fr_mul(&t, &sel[4 * m + i], &ab);
+        fr_add(&gate, &gate, &t);
+        fr_mul(&t, &sel[5 * m + i], &cd);
+        fr_add(&gate, &gate, &t);
+        fr_mul(&t, &sel[12 * m + i], &ab); /* q_ecc * ab * cd * e */
+        fr_mul(&t, &t, &cd);
+        fr_mul(&t, &t, &e);
+        fr_add(&gate, &gate, &t);
+        for (int j = 0; j < 4; j++) { /* q_hash[j] * wire_j^5 */
+            fr_sqr(&u, &lc_in[j]);
+            fr_sqr(&u, &u);
+            fr_mul(&u, &u, &lc_in[j]);
+            fr_mul(&t, &sel[(6 + j) * m + i], &u);
+            fr_add(&gate, &gate, &t);
+        }
+        fr_mul(&t, &sel[10 * m + i], &e); /* - q_o * e */
+        fr_sub(&gate, &gate, &t);
+        fr_t acc1 = z[i], acc2 = z[(i + ratio) % m];
+        for (int j = 0; j < 5; j++) {
+            fr_t wg;
+            fr_add(&wg, &w[j * m + i], &gamma);
+            fr_mul(&t, &vk_k[j], &x[i]);
+            fr_mul(&t, &t, &beta);
+            fr_add(&t, &t, &wg);
+            fr_mul(&acc1, &acc1, &t);
+            fr_mul(&t, &sg[j * m + i], &beta);
+            fr_add(&t, &t, &wg);
+            fr_mul(&acc2, &acc2, &t);
+        }
+        fr_sub(&t, &acc1, &acc2);
+        fr_mul(&t, &t, &alpha);
+        fr_add(&gate, &gate, &t);
+        fr_mul(&gate, &gate, &z_h_inv[i % ratio]);
+        fr_sub(&t, &z[i], &one); /* alpha^2/n * (z - 1) / (x - 1) */
+        fr_mul(&t, &t, &alpha_sq_div_n);
+        fr_sub(&u, &x[i], &one);
+        fr_inv(&u, &u);
+        fr_mul(&t, &t, &u);
+        fr_add(&q[i], &gate, &t);
+    }
+    free(x);
+    free(z_h_inv);
+}
+
+/* Round 4: DensePolynomial::evaluate (Horner), src/dispatcher2.rs:535-548 */
+void orc_poly_eval(const u64 *coeffs, u64 n, const u64 *point, u64 *out) {
+    const fr_t *c = (const fr_t *)coeffs, *zt = (const fr_t *)point;
+    fr_t acc;
+    memset(&acc, 0, sizeof acc);
+    for (u64 j = n; j-- > 0;) {
+        fr_mul(&acc, &acc, zt);
+        fr_add(&acc, &acc, &c[j]);
+    }
+    memcpy(out, &acc, sizeof acc);
+}
+
+/* Round 5: sum_k coeff_k * poly_k (the folds of src/dispatcher2.rs:566-633 and 646-649); polys of
+ * different lengths are zero-extended to out_len.  polys = k pointers to raw Fr arrays.          */
+void orc_poly_lincomb(const u64 *const *polys, const u64 *lens, const u64 *coeffs, u64 k, u64 *out, u64 out_len) {
+    const fr_t *cf = (const fr_t *)coeffs;
+    fr_t *o = (fr_t *)out;
+#pragma omp parallel for schedule(static)
+    for (u64 j = 0; j < out_len; j++) {
+        fr_t acc, t;
+        memset(&acc, 0, sizeof acc);
+        for (u64 i = 0; i < k; i++)
+            if (j < lens[i]) {
+                fr_mul(&t, &((const fr_t *)polys[i])[j], &cf[i]);
+                fr_add(&acc, &acc, &t);
+            }
+        o[j] = acc;
+    }
+}
+
+/* Round 5: witness polynomial = quotient of p(X) by (X - point), the long division of
+ * src/dispatcher2.rs:651-666 (and 672-688 with point = omega * zeta): top coefficient down,
+ * quotient[d-1] = remainder[d]; remainder[d-1] += remainder[d] * point.  out has n-1 coefficients. */
+void orc_poly_div_linear(const u64 *coeffs, u64 n, const u64 *point, u64 *out) {
+    const fr_t *c = (const fr_t *)coeffs, *zt = (const fr_t *)point;
+    fr_t *q = (fr_t *)out;
+    if (n < 2) return;
+    fr_t carry = c[n - 1];
+    for (u64 d = n - 1; d >= 1; d--) {
+        q[d - 1] = carry;
+        fr_t t;
+        fr_mul(&t, &carry, zt);
+        fr_add(&carry, &c[d - 1], &t);
+    }
+}
+
 /* ------------------------------------------------------------------ raw Fr utilities for tests */
 void orc_fr_mul(const u64 *a, const u64 *b, u64 *out) { fr_mul((fr_t *)out, (const fr_t *)a, (const fr_t *)b); }
 void orc_fr_add(const u64 *a, const u64 *b, u64 *out) { fr_add((fr_t *)out, (const fr_t *)a, (const fr_t *)b); }
@@ -489,6 +626,19 @@ void orc_fr_sub(const u64 *a, const u64 *b, u64 *out) { fr_sub((fr_t *)out, (con
 void orc_fq_mul(const u64 *a, const u64 *b, u64 *out) { fq_mul((fq_t *)out, (const fq_t *)a, (const fq_t *)b); }
 void orc_fq_add(const u64 *a, const u64 *b, u64 *out) { fq_add((fq_t *)out, (const fq_t *)a, (const fq_t *)b); }
 void orc_fq_sub(const u64 *a, const u64 *b, u64 *out) { fq_sub((fq_t *)out, (const fq_t *)a, (const fq_t *)b); }
+/* elementwise vector ops for building test instances: op 0 a+b, 1 a-b, 2 a*b, 3 1/a (0 -> 0) */
+void orc_fr_vec_op(const u64 *a, const u64 *b, u64 *out, u64 n, int op) {
+    const fr_t *x = (const fr_t *)a, *y = (const fr_t *)b;
+    fr_t *o = (fr_t *)out;
+#pragma omp parallel for schedule(static)
+    for (u64 i = 0; i < n; i++) {
+        if (op == 0) fr_add(&o[i], &x[i], &y[i]);
+        else if (op == 1) fr_sub(&o[i], &x[i], &y[i]);
+        else if (op == 2) fr_mul(&o[i], &x[i], &y[i]);
+        else if (fr_is_zero(&x[i])) memset(&o[i], 0, sizeof(fr_t));
+        else fr_inv(&o[i], &x[i]);
+    }
+}
 /* Fr::into_repr over a vector (worker.rs:118) */
 void orc_fr_into_repr(const u64 *in, u64 *out, u64 n) {
 #pragma omp parallel for schedule(static)

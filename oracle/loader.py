@@ -70,6 +70,11 @@ def lib():
             "orc_num_threads": (i, []),
             "orc_ntt_output_at": (None, [p, u64, u64, i, i, p]),
             "orc_perm_product": (i, [p, p, p, u64, u64, p, p, p]),
+            "orc_quotient_evals": (None, [p, p, p, p, p, p, p, p, p, u64, u64, p]),
+            "orc_fr_vec_op": (None, [p, p, p, u64, i]),
+            "orc_poly_eval": (None, [p, u64, p, p]),
+            "orc_poly_lincomb": (None, [p, p, p, u64, p, u64]),
+            "orc_poly_div_linear": (None, [p, u64, p, p]),
         }
         for name, (res, args) in sig.items():
             f = getattr(L, name)
@@ -140,6 +145,52 @@ def perm_product(wires: np.ndarray, idp: np.ndarray, sigma: np.ndarray, beta: np
     rc = lib().orc_perm_product(_ptr(args[0]), _ptr(args[1]), _ptr(args[2]), n_types, n, _ptr(args[3]), _ptr(args[4]), _ptr(out))
     if rc != 0:
         raise ZeroDivisionError("zero denominator in the permutation product")
+    return out
+
+
+def quotient_evals(selectors, sigmas, wires, perm, pub_input, k, alpha, beta, gamma, n: int) -> np.ndarray:
+    """dispatcher2.rs:363-504; selectors [13, m, 4], sigmas / wires [5, m, 4], perm / pub_input [m, 4], k [5, 4]"""
+    a = [np.ascontiguousarray(x, dtype=np.uint64) for x in (selectors, sigmas, wires, perm, pub_input, k, alpha, beta, gamma)]
+    m = a[3].shape[0]
+    out = np.zeros((m, 4), dtype=np.uint64)
+    lib().orc_quotient_evals(*[_ptr(x) for x in a], n, m, _ptr(out))
+    return out
+
+
+def poly_eval(coeffs: np.ndarray, point: np.ndarray) -> np.ndarray:
+    """DensePolynomial::evaluate (dispatcher2.rs:535-548)"""
+    c, z = np.ascontiguousarray(coeffs, dtype=np.uint64), np.ascontiguousarray(point, dtype=np.uint64)
+    out = np.zeros(4, dtype=np.uint64)
+    lib().orc_poly_eval(_ptr(c), c.shape[0], _ptr(z), _ptr(out))
+    return out
+
+
+def poly_lincomb(polys, coeffs: np.ndarray, out_len: int | None = None) -> np.ndarray:
+    """sum_k coeffs[k] * polys[k], shorter polynomials zero-extended (dispatcher2.rs:566-649)"""
+    ps = [np.ascontiguousarray(x, dtype=np.uint64) for x in polys]
+    cf = np.ascontiguousarray(coeffs, dtype=np.uint64)
+    lens = np.array([x.shape[0] for x in ps], dtype=np.uint64)
+    n_out = int(lens.max()) if out_len is None else out_len
+    ptrs = (C.c_void_p * len(ps))(*[x.ctypes.data for x in ps])
+    out = np.zeros((n_out, 4), dtype=np.uint64)
+    lib().orc_poly_lincomb(C.cast(ptrs, C.c_void_p), _ptr(lens), _ptr(cf), len(ps), _ptr(out), n_out)
+    return out
+
+
+def poly_div_linear(coeffs: np.ndarray, point: np.ndarray) -> np.ndarray:
+    """quotient of p(X) / (X - point): the witness polynomial of dispatcher2.rs:651-666"""
+    c, z = np.ascontiguousarray(coeffs, dtype=np.uint64), np.ascontiguousarray(point, dtype=np.uint64)
+    out = np.zeros((max(c.shape[0] - 1, 0), 4), dtype=np.uint64)
+    lib().orc_poly_div_linear(_ptr(c), c.shape[0], _ptr(z), _ptr(out))
+    return out
+
+
+def vec_op(op: str, a: np.ndarray, b: np.ndarray | None = None) -> np.ndarray:
+    """elementwise Fr add / sub / mul / inv over [n, 4] Montgomery arrays (test-instance construction)"""
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    b = a if b is None else np.ascontiguousarray(b, dtype=np.uint64)
+    out = np.empty_like(a)
+    lib().orc_fr_vec_op(_ptr(a), _ptr(b), _ptr(out), a.shape[0], {"add": 0, "sub": 1, "mul": 2, "inv": 3}[op])
     return out
 
 

@@ -20,6 +20,7 @@ Reference call sites this restates (file:line into /root/reference):
   * exchange scatter .......................... src/worker.rs:327-330, 432-435
   * dispatcher row/col <-> flat mapping ....... src/dispatcher2.rs:731-787
   * VariableBaseMSM::multi_scalar_mul ......... src/worker.rs:117-123, 177-182
+  * rounds 2-5 arithmetic of Prover::prove .... src/dispatcher2.rs:329-345, 363-504, 535-690
 """
 from __future__ import annotations
 
@@ -259,6 +260,60 @@ def distributed_fft(dom: Domain, coeffs, is_inv, is_coset, n_workers=1):
     cols = [fft2_helper(cols[k], k, is_coset, is_inv, dom) for k in range(c)]
     # dispatcher2.rs:780-786: transpose(u).concat()  -> out[j*c + i] = col_i[j]
     return [cols[i][j] for j in range(r) for i in range(c)]
+
+
+# ----------------------------------------------------------------------------- rounds 2-5 of Prover::prove
+def perm_product(wires, idp, sigma, beta, gamma):
+    """dispatcher2.rs:329-345: z[0] = 1, z[j+1] = z[j] * a_j / b_j.  wires/idp/sigma: [types][n] ints."""
+    n = len(wires[0])
+    z = [1]
+    for j in range(n - 1):
+        a = b = 1
+        for w, i_, s_ in zip(wires, idp, sigma):
+            a = a * (w[j] + gamma + beta * i_[j]) % FR_MOD
+            b = b * (w[j] + gamma + beta * s_[j]) % FR_MOD
+        z.append(z[-1] * a * pow(b, -1, FR_MOD) % FR_MOD)
+    return z
+
+
+def quotient_evals(sel, sig, w, z, pi, k, alpha, beta, gamma, n):
+    """dispatcher2.rs:363-504 by definition.  sel [13][m], sig / w [5][m], z / pi [m], k [5] (ints)."""
+    m = len(z)
+    ratio = m // n
+    omega = Domain(m).group_gen
+    x = [FR_GENERATOR * pow(omega, i, FR_MOD) % FR_MOD for i in range(m)]
+    zh_inv = [pow(pow(x[i], n, FR_MOD) - 1, -1, FR_MOD) for i in range(ratio)]
+    a2n = alpha * alpha * pow(n, -1, FR_MOD) % FR_MOD
+    out = []
+    for i in range(m):
+        a, b, c, d, e = (w[j][i] for j in range(5))
+        gate = (sel[11][i] + pi[i] + sel[0][i] * a + sel[1][i] * b + sel[2][i] * c + sel[3][i] * d
+                + sel[4][i] * a * b + sel[5][i] * c * d + sel[12][i] * a * b * c * d * e
+                + sel[6][i] * a**5 + sel[7][i] * b**5 + sel[8][i] * c**5 + sel[9][i] * d**5 - sel[10][i] * e)
+        acc1, acc2 = z[i], z[(i + ratio) % m]
+        for j in range(5):
+            acc1 = acc1 * (w[j][i] + gamma + k[j] * x[i] * beta) % FR_MOD
+            acc2 = acc2 * (w[j][i] + gamma + sig[j][i] * beta) % FR_MOD
+        t3 = a2n * (z[i] - 1) * pow(x[i] - 1, -1, FR_MOD)
+        out.append((zh_inv[i % ratio] * (gate + alpha * (acc1 - acc2)) + t3) % FR_MOD)
+    return out
+
+
+def poly_eval(coeffs, point):
+    """DensePolynomial::evaluate (dispatcher2.rs:535-548), by definition"""
+    return sum(c * pow(point, j, FR_MOD) for j, c in enumerate(coeffs)) % FR_MOD
+
+
+def poly_div_linear(coeffs, point):
+    """quotient q of p = q * (X - point) + p(point)  (dispatcher2.rs:651-666), by definition:
+    q_j = sum_{k > j} p_k * point^(k-j-1)"""
+    n = len(coeffs)
+    return [sum(coeffs[k] * pow(point, k - j - 1, FR_MOD) for k in range(j + 1, n)) % FR_MOD for j in range(n - 1)]
+
+
+def poly_lincomb(polys, coeffs):
+    n = max(len(p) for p in polys)
+    return [sum(c * p[j] for p, c in zip(polys, coeffs) if j < len(p)) % FR_MOD for j in range(n)]
 
 
 # ----------------------------------------------------------------------------- seeded PRNG shared with the C oracle

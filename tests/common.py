@@ -147,3 +147,109 @@ def check_perm_product(orc, ctx: Context, n: int, n_types: int, seed: int):
     assert np.array_equal(got, orc.perm_product(w, idp, sg, beta, gamma)), f"perm product n={n}"
     # a valid permutation (sigma = id re-ordered) closes the cycle: z[n-1] * a[n-1]/b[n-1] = 1
     return got
+
+
+def check_quotient(orc, ctx: Context, n: int, m: int, seed: int):
+    """round 3: one fused kernel vs the dispatcher's per-point loop (dispatcher2.rs:434-504)"""
+    sel = [orc.gen_fr(seed + i, m) for i in range(13)]
+    sig = [orc.gen_fr(seed + 20 + i, m) for i in range(5)]
+    w = [orc.gen_fr(seed + 30 + i, m) for i in range(5)]
+    z, pi = orc.gen_fr(seed + 40, m), orc.gen_fr(seed + 41, m)
+    k = orc.gen_fr(seed + 42, 5)
+    al, be, ga = (orc.gen_fr(seed + 43 + i, 1)[0] for i in range(3))
+    got = ctx.quotient_evals(sel, sig, w, z, pi, k, al, be, ga)
+    ref = orc.quotient_evals(np.stack(sel), np.stack(sig), np.stack(w), z, pi, k, al, be, ga, n)
+    assert np.array_equal(got, ref), f"quotient evaluations n={n} m={m}"
+
+
+def check_poly_ops(orc, ctx: Context, sizes, seed: int):
+    """rounds 4-5: evaluate, divide by (X - z), linear combination vs the sequential restatement"""
+    for n in sizes:
+        c, pt = orc.gen_fr(seed + n % 1000, n), orc.gen_fr(seed + 1, 1)[0]
+        ev = orc.poly_eval(c, pt)
+        assert np.array_equal(ctx.poly_eval(c, pt), ev), f"poly_eval n={n}"
+        q, rem = ctx.poly_div_linear(c, pt)
+        assert np.array_equal(rem, ev), f"poly_div_linear remainder n={n}"
+        assert np.array_equal(q, orc.poly_div_linear(c, pt)), f"poly_div_linear n={n}"
+    # special points: 0, 1, -1
+    c = orc.gen_fr(seed + 5, 300)
+    zero = np.zeros(4, dtype=np.uint64)
+    for pt in (zero, _fr_one(orc), _fr_neg_one(orc)):
+        assert np.array_equal(ctx.poly_eval(c, pt), orc.poly_eval(c, pt))
+        assert np.array_equal(ctx.poly_div_linear(c, pt)[0], orc.poly_div_linear(c, pt))
+    lens = [5, 2049, 1, 2049, 300, 0]
+    polys = [orc.gen_fr(seed + 70 + i, ln) for i, ln in enumerate(lens)]
+    cf = orc.gen_fr(seed + 80, len(lens))
+    assert np.array_equal(ctx.poly_lincomb(polys, cf), orc.poly_lincomb(polys, cf))
+    assert np.array_equal(ctx.poly_lincomb(polys, cf, out_len=100), orc.poly_lincomb(polys, cf)[:100])
+    assert np.array_equal(ctx.poly_lincomb(polys, cf, out_len=3000)[2049:], np.zeros((3000 - 2049, 4), dtype=np.uint64))
+
+
+def _fr_one(orc):
+    """Montgomery 1 = R mod r"""
+    a = np.array([1, 0, 0, 0], dtype=np.uint64)
+    return orc.from_repr(a[None])[0]
+
+
+def _fr_neg_one(orc):
+    out, zero = np.zeros(4, dtype=np.uint64), np.zeros(4, dtype=np.uint64)
+    one = _fr_one(orc)
+    orc.lib().orc_fr_sub(zero.ctypes.data, one.ctypes.data, out.ctypes.data)
+    return out
+
+
+def check_satisfied_circuit(orc, ctx: Context, log_n: int, seed: int):
+    """Size-independent property of rounds 2-3 (what the reference gets from its verifier, test_plonk):
+    for a witness that satisfies every gate and every copy constraint the quotient evaluations
+    interpolate to a polynomial of degree <= 5(n+1)+2, i.e. the division by Z_H is exact; with ONE
+    wire value corrupted it is not.  The instance is built with the oracle's elementwise vector ops;
+    perm product, iNTT, coset NTT, quotient kernel and coset iNTT all run through the library."""
+    n, m, log_m = 1 << log_n, 8 << log_n, log_n + 3
+    one = _fr_one(orc)
+    V = orc.vec_op
+    w = [orc.gen_fr(seed + i, n) for i in range(4)]
+    # copy constraints between equal-valued cells of different wire types / rows
+    pairs = [((0, 1), (2, 3)), ((1, 0), (3, n - 2)), ((0, 2), (0, n // 2 + 1)), ((3, 7 % n), (1, n - 1))]
+    for (i1, j1), (i2, j2) in pairs:
+        w[i2][j2] = w[i1][j1]
+    sel = [orc.gen_fr(seed + 10 + i, n) for i in range(13)]
+    pub = np.zeros((n, 4), dtype=np.uint64)
+    pub[:3] = orc.gen_fr(seed + 30, 3)                          # a few public inputs
+    a, b, c, d = w
+    ab, cd = V("mul", a, b), V("mul", c, d)
+    p5 = lambda v: V("mul", V("mul", V("mul", v, v), V("mul", v, v)), v)
+    rest = V("add", sel[11], pub)
+    for q, v in ((sel[0], a), (sel[1], b), (sel[2], c), (sel[3], d), (sel[4], ab), (sel[5], cd),
+                 (sel[6], p5(a)), (sel[7], p5(b)), (sel[8], p5(c)), (sel[9], p5(d))):
+        rest = V("add", rest, V("mul", q, v))
+    # q_c + pi + ... + q_ecc ab cd e - q_o e = 0   =>   e = rest / (q_o - q_ecc ab cd)
+    e = V("mul", rest, V("inv", V("sub", sel[10], V("mul", sel[12], V("mul", ab, cd)))))
+    w = w + [e]
+    k = orc.gen_fr(seed + 40, 5)
+    k[0] = one
+    x_poly = np.zeros((n, 4), dtype=np.uint64)
+    x_poly[1 % n] = one
+    omegas = ctx.ntt(x_poly, log_n, False, False)              # omega^j = evaluations of X over H
+    ident = [ctx.poly_lincomb([omegas], k[i][None]) for i in range(5)]
+    sigma = [v.copy() for v in ident]
+    for (i1, j1), (i2, j2) in pairs:
+        sigma[i1][j1], sigma[i2][j2] = sigma[i2][j2].copy(), sigma[i1][j1].copy()
+    beta, gamma, alpha = (orc.gen_fr(seed + 50 + i, 1)[0] for i in range(3))
+    z = ctx.perm_product(np.stack(w), np.stack(ident), np.stack(sigma), beta, gamma)
+
+    def to_coset(evals):                                       # dispatcher2.rs:381-432
+        return ctx.ntt(ctx.ntt(evals, log_n, True, False), log_m, False, True)
+
+    fixed = ([to_coset(v) for v in sel], [to_coset(v) for v in sigma], to_coset(z), to_coset(pub))
+
+    def degree(wires):
+        q = ctx.quotient_evals(fixed[0], fixed[1], [to_coset(v) for v in wires], fixed[2], fixed[3], k, alpha, beta, gamma)
+        coeffs = ctx.ntt(q, log_m, True, True)                 # dispatcher2.rs:507
+        nz = np.nonzero(coeffs.any(axis=1))[0]
+        return int(nz[-1]) if nz.size else -1
+
+    deg = degree(w)
+    assert 4 * n <= deg <= 5 * (n + 1) + 2, f"quotient degree {deg} for n={n}"
+    bad = [v.copy() for v in w]
+    bad[1][n // 3] = orc.gen_fr(seed + 60, 1)[0]
+    assert degree(bad) > 7 * n

@@ -188,6 +188,32 @@ def test_perm_product(orc, ctx):
     assert e.value.code == -1
 
 
+def test_rounds_3_to_5(orc, ctx):
+    common.check_quotient(orc, ctx, 1 << 6, 1 << 9, 900)
+    common.check_poly_ops(orc, ctx, (1, 2, 7, 8, 9, 255, 2047, 2048, 2049, 6145, 10000), 910)
+    # the zero polynomial and the constant polynomial
+    pt = orc.gen_fr(3, 1)[0]
+    assert not ctx.poly_eval(np.zeros((0, 4), dtype=np.uint64), pt).any()
+    q, rem = ctx.poly_div_linear(orc.gen_fr(4, 1), pt)
+    assert q.shape[0] == 0 and np.array_equal(rem, orc.gen_fr(4, 1)[0])
+    with pytest.raises(DpError) as e:
+        ctx.poly_lincomb([orc.gen_fr(1, 4)] * 33, orc.gen_fr(2, 33))
+    assert e.value.code == -1
+
+
+def test_satisfied_circuit_divides_exactly(orc, ctx):
+    common.check_satisfied_circuit(orc, ctx, 6, 1200)
+
+
+def test_rounds_quotient_domain_ratios(orc, emul_lib):
+    """quotient / gate domain ratios other than 8, and a quotient domain smaller than one block"""
+    for n, m in ((4, 32), (8, 16), (16, 16), (2, 32)):
+        c = Context(emul_lib, 0, 0, 1)
+        c.init(orc.gen_bases(5, 40, 8, False), n, m)
+        common.check_quotient(orc, c, n, m, 950 + n + m)
+        c.close()
+
+
 def test_error_behaviour(orc, emul_lib):
     c = Context(emul_lib, 0, 0, 1)
     with pytest.raises(DpError) as e:

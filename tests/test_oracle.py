@@ -126,3 +126,102 @@ def test_golden_vectors(orc):
     bases = orc.gen_bases(int(g["msm_seed"]), int(g["msm_n"]), 16, True)
     assert np.array_equal(bases, g["msm_bases"])
     assert np.array_equal(orc.normalize(orc.msm(bases, g["msm_scalars"])), g["msm_out_affine"])
+
+
+def _mont(vals):
+    """list of ints -> [len, 4] uint64 Montgomery Fr"""
+    return np.frombuffer(B.fr_vec_to_bytes(vals), dtype=np.uint64).reshape(-1, 4).copy()
+
+
+def satisfying_circuit(orc, n: int, seed: int):
+    """A random TurboPlonk instance whose gates and copy constraints HOLD (GATE_WIDTH 4, 5 wire types):
+    random a..d and selectors, q_o = 1, e = the gate output; a non-trivial wire permutation between
+    equal-valued cells.  Returns polynomials (coefficient form, ints) and the challenges."""
+    g = B.SplitMix64(seed)
+    dom, P = B.Domain(n), B.FR_MOD
+    w = [[g.fr() for _ in range(n)] for _ in range(4)]
+    # copy constraints: cell (i, j) == cell (i2, j2) for a few pairs; sigma swaps them
+    cells = [(i, j) for i in range(5) for j in range(n)]
+    pairs = [((0, 1), (2, 3)), ((1, 0), (3, n - 2)), ((0, 2), (0, 5))]
+    for (i1, j1), (i2, j2) in pairs:
+        w[i2][j2] = w[i1][j1]
+    sel = [[g.fr() for _ in range(n)] for _ in range(13)]
+    sel[10] = [1] * n                                    # q_o
+    sel[11] = [0] * n                                    # q_c (public input = 0)
+    e = []
+    for j in range(n):
+        a, b, c, d = (w[i][j] for i in range(4))
+        e.append((sel[0][j] * a + sel[1][j] * b + sel[2][j] * c + sel[3][j] * d + sel[4][j] * a * b + sel[5][j] * c * d
+                  + sel[6][j] * a**5 + sel[7][j] * b**5 + sel[8][j] * c**5 + sel[9][j] * d**5) % P)
+    sel[12] = [0] * n                                    # q_ecc would make e implicit; keep it off
+    w.append(e)
+    # permutation: extended identity k_i * omega^j; sigma = identity with the paired cells swapped
+    k = [1] + [g.fr() for _ in range(4)]
+    ident = [[k[i] * pow(dom.group_gen, j, P) % P for j in range(n)] for i in range(5)]
+    sigma = [row[:] for row in ident]
+    for (i1, j1), (i2, j2) in pairs:
+        sigma[i1][j1], sigma[i2][j2] = sigma[i2][j2], sigma[i1][j1]
+    beta, gamma, alpha = g.fr(), g.fr(), g.fr()
+    return dict(n=n, w=w, sel=sel, k=k, ident=ident, sigma=sigma, beta=beta, gamma=gamma, alpha=alpha, cells=cells)
+
+
+def test_rounds_tier1_vs_definition(orc):
+    """quotient evaluations, evaluate, linear combination and division by (X - z): C oracle == Python ints"""
+    g = B.SplitMix64(77)
+    n, m = 4, 32
+    sel = [[g.fr() for _ in range(m)] for _ in range(13)]
+    sig = [[g.fr() for _ in range(m)] for _ in range(5)]
+    w = [[g.fr() for _ in range(m)] for _ in range(5)]
+    z, pi, k = [g.fr() for _ in range(m)], [g.fr() for _ in range(m)], [g.fr() for _ in range(5)]
+    al, be, ga = g.fr(), g.fr(), g.fr()
+    got = orc.quotient_evals(np.stack([_mont(v) for v in sel]), np.stack([_mont(v) for v in sig]), np.stack([_mont(v) for v in w]),
+                             _mont(z), _mont(pi), _mont(k), _mont([al]), _mont([be]), _mont([ga]), n)
+    assert ints(got) == B.quotient_evals(sel, sig, w, z, pi, k, al, be, ga, n)
+    for ln in (1, 2, 3, 17, 64):
+        c, pt = [g.fr() for _ in range(ln)], g.fr()
+        assert ints(orc.poly_eval(_mont(c), _mont([pt]))[None]) == [B.poly_eval(c, pt)]
+        assert ints(orc.poly_div_linear(_mont(c), _mont([pt]))) == B.poly_div_linear(c, pt)
+    polys = [[g.fr() for _ in range(ln)] for ln in (5, 9, 1, 9, 3)]
+    cf = [g.fr() for _ in polys]
+    assert ints(orc.poly_lincomb([_mont(p) for p in polys], _mont(cf))) == B.poly_lincomb(polys, cf)
+
+
+def test_quotient_of_a_satisfied_circuit_is_a_polynomial(orc):
+    """The algebraic end-to-end check the reference gets from its verifier (test_plonk): for a witness that
+    satisfies every gate and copy constraint, the round-3 evaluations interpolate to a polynomial of degree
+    <= 5(n+1)+2 - with no blinding even lower - i.e. the division by Z_H is exact (dispatcher2.rs:506-517)."""
+    n = 16
+    m = 8 * n
+    c = satisfying_circuit(orc, n, 5)
+    P = B.FR_MOD
+    z = B.perm_product(c["w"], c["ident"], c["sigma"], c["beta"], c["gamma"])
+    assert ints(orc.perm_product(np.stack([_mont(v) for v in c["w"]]), np.stack([_mont(v) for v in c["ident"]]),
+                                 np.stack([_mont(v) for v in c["sigma"]]), _mont([c["beta"]]), _mont([c["gamma"]]))) == z
+    # the grand product closes: z[n-1] * a[n-1] / b[n-1] == 1
+    a = b = 1
+    for i in range(5):
+        a = a * (c["w"][i][n - 1] + c["gamma"] + c["beta"] * c["ident"][i][n - 1]) % P
+        b = b * (c["w"][i][n - 1] + c["gamma"] + c["beta"] * c["sigma"][i][n - 1]) % P
+    assert z[n - 1] * a % P == b
+
+    def to_coset(evals):     # evaluations over H -> coefficients -> evaluations over g*H_m (lines 386-388)
+        coeffs = orc.fft(_mont(evals), True, False)
+        pad = np.zeros((m, 4), dtype=np.uint64)
+        pad[:n] = coeffs
+        return orc.fft(pad, False, True)
+
+    sel = np.stack([to_coset(v) for v in c["sel"]])
+    sig = np.stack([to_coset(v) for v in c["sigma"]])
+    w = np.stack([to_coset(v) for v in c["w"]])
+    q = orc.quotient_evals(sel, sig, w, to_coset(z), to_coset([0] * n), _mont(c["k"]), _mont([c["alpha"]]), _mont([c["beta"]]),
+                           _mont([c["gamma"]]), n)
+    coeffs = ints(orc.fft(q, True, True))
+    deg = max(j for j, v in enumerate(coeffs) if v)
+    # unblinded degrees: gate 5(n-1)+ (n-1) ... bounded by the permutation term 6(n-1) - n
+    assert deg <= 5 * (n + 1) + 2 and deg >= 4 * n, deg
+    # and the same evaluations with ONE wire value corrupted do not divide: high coefficients appear
+    c["w"][0][3] = (c["w"][0][3] + 1) % P
+    w_bad = np.stack([to_coset(v) for v in c["w"]])
+    q_bad = orc.quotient_evals(sel, sig, w_bad, to_coset(z), to_coset([0] * n), _mont(c["k"]), _mont([c["alpha"]]),
+                               _mont([c["beta"]]), _mont([c["gamma"]]), n)
+    assert max(j for j, v in enumerate(ints(orc.fft(q_bad, True, True))) if v) > 7 * n

@@ -3,6 +3,8 @@ exactly like the reference's own tests drive the workers (dispatcher.rs:177-350,
 1088-1216) and compares with the oracle."""
 import ctypes as C
 
+import os
+
 import numpy as np
 
 from distributed_plonk_b200 import dispatcher as disp
@@ -253,3 +255,30 @@ def check_satisfied_circuit(orc, ctx: Context, log_n: int, seed: int):
     bad = [v.copy() for v in w]
     bad[1][n // 3] = orc.gen_fr(seed + 60, 1)[0]
     assert degree(bad) > 7 * n
+
+
+GOLDEN_ROUNDS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_rounds_v1.npz")
+
+
+def check_golden_rounds(make_ctx, impl=None):
+    """tests/golden/golden_rounds_v1.npz (written by make_golden_rounds.py, tier-0 verified there) against
+    `impl` (the oracle loader) or against the library (make_ctx(n, m) -> Context)"""
+    g = np.load(GOLDEN_ROUNDS)
+    n, m = int(g["n"]), int(g["m"])
+    if impl is not None:
+        assert np.array_equal(impl.quotient_evals(g["q_sel"], g["q_sig"], g["q_w"], g["q_z"], g["q_pi"], g["q_k"], g["q_alpha"],
+                                                  g["q_beta"], g["q_gamma"], n), g["q_out"])
+        assert np.array_equal(impl.perm_product(g["p_w"], g["p_id"], g["p_sigma"], g["q_beta"], g["q_gamma"]), g["p_out"])
+        assert np.array_equal(impl.poly_eval(g["e_coeffs"], g["e_point"]), g["e_out"])
+        assert np.array_equal(impl.poly_div_linear(g["e_coeffs"], g["e_point"]), g["d_out"])
+        assert np.array_equal(impl.poly_lincomb([g["l_p0"], g["l_p1"], g["l_p2"]], g["l_coeffs"]), g["l_out"])
+        return
+    ctx = make_ctx(n, m)
+    assert np.array_equal(ctx.quotient_evals(list(g["q_sel"]), list(g["q_sig"]), list(g["q_w"]), g["q_z"], g["q_pi"], g["q_k"],
+                                             g["q_alpha"], g["q_beta"], g["q_gamma"]), g["q_out"])
+    assert np.array_equal(ctx.perm_product(g["p_w"], g["p_id"], g["p_sigma"], g["q_beta"], g["q_gamma"]), g["p_out"])
+    assert np.array_equal(ctx.poly_eval(g["e_coeffs"], g["e_point"]), g["e_out"])
+    q, rem = ctx.poly_div_linear(g["e_coeffs"], g["e_point"])
+    assert np.array_equal(q, g["d_out"]) and np.array_equal(rem, g["e_out"])
+    assert np.array_equal(ctx.poly_lincomb([g["l_p0"], g["l_p1"], g["l_p2"]], g["l_coeffs"]), g["l_out"])
+    ctx.close()

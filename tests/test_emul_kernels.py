@@ -205,6 +205,14 @@ def test_satisfied_circuit_divides_exactly(orc, ctx):
     common.check_satisfied_circuit(orc, ctx, 6, 1200)
 
 
+def test_golden_rounds(orc, emul_lib):
+    def make(n, m):
+        c = Context(emul_lib, 0, 0, 1)
+        c.init(orc.gen_bases(5, 40, 8, False), n, m)
+        return c
+    common.check_golden_rounds(make)
+
+
 def test_rounds_quotient_domain_ratios(orc, emul_lib):
     """quotient / gate domain ratios other than 8, and a quotient domain smaller than one block"""
     for n, m in ((4, 32), (8, 16), (16, 16), (2, 32)):

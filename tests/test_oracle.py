@@ -225,3 +225,8 @@ def test_quotient_of_a_satisfied_circuit_is_a_polynomial(orc):
     q_bad = orc.quotient_evals(sel, sig, w_bad, to_coset(z), to_coset([0] * n), _mont(c["k"]), _mont([c["alpha"]]),
                                _mont([c["beta"]]), _mont([c["gamma"]]), n)
     assert max(j for j, v in enumerate(ints(orc.fft(q_bad, True, True))) if v) > 7 * n
+
+
+def test_golden_rounds(orc):
+    from tests import common
+    common.check_golden_rounds(None, impl=orc)

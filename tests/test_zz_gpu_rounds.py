@@ -30,6 +30,14 @@ def ctx(gpu_lib, orc):
     c.close()
 
 
+def test_golden_rounds_on_gpu(orc, gpu_lib):
+    def make(n, m):
+        c = Context(gpu_lib, 0, 0, 1)
+        c.init(orc.gen_bases(5, 40, 8, False), n, m)
+        return c
+    common.check_golden_rounds(make)
+
+
 def test_quotient_evals(orc, ctx):
     common.check_quotient(orc, ctx, 1 << 12, 1 << 15, 2000)
 

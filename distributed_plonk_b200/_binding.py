@@ -15,7 +15,7 @@ EXPORTS = [
     "dp_launch_count", "dp_sync", "dp_msm_dev", "dp_ntt_dev", "dp_fft_dev", "dp_debug_set_limits",
     "dp_last_msm_breakdown", "dp_debug_gen_bases", "dp_fft_dev_rows", "dp_fft_dev_cols", "dp_peer_ready", "dp_fft_dev_rows_p2p", "dp_fft_dev_p2p", "dp_msm_dev_batch", "dp_perm_product", "dp_msm_batch", "dp_perm_product_dev",
     "dp_quotient_evals", "dp_quotient_evals_dev", "dp_poly_eval", "dp_poly_eval_dev", "dp_poly_lincomb", "dp_poly_lincomb_dev",
-    "dp_poly_div_linear", "dp_poly_div_linear_dev",
+    "dp_poly_div_linear", "dp_poly_div_linear_dev", "dp_init_compressed", "dp_get_bases",
 ]
 
 
@@ -76,6 +76,8 @@ def bind(cdll: C.CDLL) -> C.CDLL:
         "dp_msm_dev_batch": (i, [vp, sz, C.POINTER(u64), C.POINTER(u64), C.POINTER(vp), C.POINTER(sz), C.POINTER(vp)]),
         "dp_fft_dev_rows_p2p": (i, [vp, vp, i, i, i]),
         "dp_fft_dev_p2p": (i, [vp, vp, vp, i, i, i]),
+        "dp_init_compressed": (i, [vp, vp, sz, u64, u64, i]),
+        "dp_get_bases": (i, [vp, u64, sz, vp]),
         "dp_quotient_evals": (i, [vp, C.POINTER(QuotientArgs), vp]),
         "dp_quotient_evals_dev": (i, [vp, C.POINTER(QuotientArgs), vp]),
         "dp_poly_eval": (i, [vp, vp, sz, vp, vp]),
@@ -203,6 +205,16 @@ class Context:
     def perm_product_dev(self, wires_ptr: int, id_ptr: int, sigma_ptr: int, n_types: int, n: int, beta: np.ndarray, gamma: np.ndarray, out_ptr: int):
         b, g = np.ascontiguousarray(beta, dtype=np.uint64), np.ascontiguousarray(gamma, dtype=np.uint64)
         self._ck(self.lib.dp_perm_product_dev(self.h, wires_ptr, id_ptr, sigma_ptr, n_types, n, _addr(b), _addr(g), out_ptr))
+
+    def init_compressed(self, bases48: np.ndarray, domain_size: int, quot_domain_size: int, check_subgroup: bool = True):
+        """dp_init from ark-serialize compressed points ([n, 48] uint8)"""
+        b = np.ascontiguousarray(bases48, dtype=np.uint8)
+        self._ck(self.lib.dp_init_compressed(self.h, _addr(b) if b.size else None, b.size // 48, domain_size, quot_domain_size, int(check_subgroup)))
+
+    def get_bases(self, start: int, n: int) -> np.ndarray:
+        out = np.zeros((n, 104), dtype=np.uint8)
+        self._ck(self.lib.dp_get_bases(self.h, start, n, _addr(out) if n else None))
+        return out
 
     # ---- rounds 3-5 ("next" row 1): plain = host arrays, *_dev = device pointers (ints)
     @staticmethod

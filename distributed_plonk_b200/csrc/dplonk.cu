@@ -873,7 +873,10 @@ int dp_last_timing(const dp_ctx *ctx, float *kernel_ms, uint64_t *launches) {
 
 uint64_t dp_launch_count(const dp_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
-int dp_init(dp_ctx *ctx, const void *bases, size_t n_bases, uint64_t domain_size, uint64_t quot_domain_size) {
+// format 0: raw ark GroupAffine structs (104 B, utils.rs:27-43) - what the reference's init RPC carries;
+// format 1: ark-serialize compressed points (48 B) - what SRS files hold ("next" row 4)
+static int init_impl(dp_ctx *ctx, const void *bases, size_t n_bases, uint64_t domain_size, uint64_t quot_domain_size, int format,
+                     int check_subgroup) {
     if (!ctx) return DP_E_ARG;
     if (n_bases && !bases) return fail(ctx, DP_E_ARG, "dp_init: bases is NULL");
     if (domain_size == 0 || quot_domain_size == 0) return fail(ctx, DP_E_ARG, "dp_init: domain sizes must be >= 1");
@@ -897,13 +900,32 @@ int dp_init(dp_ctx *ctx, const void *bases, size_t n_bases, uint64_t domain_size
     ctx->n_bases = n_bases;
     if (n_bases) {
         ctx->bases = (G1Affine *)ctx->pool.alloc(n_bases * sizeof(G1Affine));
-        void *staging = ctx->pool.alloc(n_bases * (size_t)DP_G1_AFFINE_BYTES);
+        const size_t in_bytes = n_bases * (size_t)(format == 0 ? DP_G1_AFFINE_BYTES : DP_G1_COMPRESSED_BYTES);
+        Scratch stage(ctx->pool);
+        void *staging = stage.get<uint8_t>(in_bytes);
         if (!ctx->bases || !staging) return fail(ctx, DP_E_OOM, "dp_init: %zu bases", n_bases);
-        DP_CUDA(ctx, cudaMemcpyAsync(staging, bases, n_bases * (size_t)DP_G1_AFFINE_BYTES, cudaMemcpyHostToDevice, ctx->stream));
-        DP_LAUNCH(g1_import_ark_kernel, dim3(blocks_for(n_bases, 256)), dim3(256), 0, ctx->stream,
-                  (const uint64_t *)staging, ctx->bases, (uint64_t)n_bases);
+        DP_CUDA(ctx, cudaMemcpyAsync(staging, bases, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        if (format == 0) {
+            DP_LAUNCH(g1_import_ark_kernel, dim3(blocks_for(n_bases, 256)), dim3(256), 0, ctx->stream,
+                      (const uint64_t *)staging, ctx->bases, (uint64_t)n_bases);
+        } else {
+            unsigned long long *err = stage.get<unsigned long long>(1), verdict = ~0ull;
+            if (!err) return fail(ctx, DP_E_OOM, "dp_init_compressed scratch");
+            DP_CUDA(ctx, cudaMemcpyAsync(err, &verdict, sizeof verdict, cudaMemcpyHostToDevice, ctx->stream));
+            DP_LAUNCH(g1_decompress_kernel, dim3(blocks_for(n_bases, 128)), dim3(128), 0, ctx->stream, (const uint32_t *)staging,
+                      ctx->bases, (uint64_t)n_bases, check_subgroup ? 1u : 0u, err);
+            DP_CUDA(ctx, cudaMemcpyAsync(&verdict, err, sizeof verdict, cudaMemcpyDeviceToHost, ctx->stream));
+            DP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (verdict != ~0ull) {
+                static const char *why[] = {"", "x is not a canonical field element", "both flag bits set", "x^3 + 4 is not a square: no such point",
+                                            "the point is not in the r-torsion subgroup"};
+                ctx->pool.release(ctx->bases);
+                ctx->bases = nullptr;
+                ctx->n_bases = 0;
+                return fail(ctx, DP_E_ARG, "dp_init_compressed: point %llu rejected: %s", (unsigned long long)((verdict >> 8) - 1), why[verdict & 7]);
+            }
+        }
         ctx->launches++;
-        ctx->pool.release(staging);
         // window multiples for the MSM (skipped for tiny SRS or when memory is short)
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
@@ -933,6 +955,30 @@ int dp_init(dp_ctx *ctx, const void *bases, size_t n_bases, uint64_t domain_size
     DP_TRY(call_end(ctx, true));
     ctx->inited = true;
     return DP_OK;
+}
+
+int dp_init(dp_ctx *ctx, const void *bases, size_t n_bases, uint64_t domain_size, uint64_t quot_domain_size) {
+    return init_impl(ctx, bases, n_bases, domain_size, quot_domain_size, 0, 0);
+}
+
+int dp_init_compressed(dp_ctx *ctx, const void *bases48, size_t n_bases, uint64_t domain_size, uint64_t quot_domain_size, int check_subgroup) {
+    return init_impl(ctx, bases48, n_bases, domain_size, quot_domain_size, 1, check_subgroup);
+}
+
+int dp_get_bases(dp_ctx *ctx, uint64_t start, size_t n, void *out104) {
+    if (!ctx || (n && !out104)) return fail(ctx, DP_E_ARG, "dp_get_bases: NULL argument");
+    if (!ctx->inited) return fail(ctx, DP_E_STATE, "dp_get_bases before dp_init");
+    if (start > ctx->n_bases || n > ctx->n_bases - start) return fail(ctx, DP_E_ARG, "dp_get_bases: range outside %llu bases", (unsigned long long)ctx->n_bases);
+    if (n == 0) return DP_OK;
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    call_begin(ctx);
+    Scratch tmp(ctx->pool);
+    uint64_t *ark = tmp.get<uint64_t>(n * 13);
+    if (!ark) return fail(ctx, DP_E_OOM, "dp_get_bases buffer");
+    DP_LAUNCH(g1_export_ark_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, ctx->stream, (const G1Affine *)(ctx->bases + start), ark, (uint64_t)n);
+    ctx->launches++;
+    DP_CUDA(ctx, cudaMemcpyAsync(out104, ark, n * (size_t)DP_G1_AFFINE_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+    return call_end(ctx, true);
 }
 
 int dp_msm(dp_ctx *ctx, uint64_t start, uint64_t end, const void *scalars, size_t n_scalars, void *out) {

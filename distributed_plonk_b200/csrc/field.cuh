@@ -241,6 +241,33 @@ struct Field : Limbs<P::N> {
         }
         return acc;
     }
+    // x^e, e = n_limbs 32-bit little-endian limbs
+    DP_HD Field pow_limbs(const uint32_t *e, int n_limbs) const {
+        Field acc = one();
+        bool started = false;
+        for (int i = n_limbs - 1; i >= 0; i--) {
+            for (int b = 31; b >= 0; b--) {
+                if (started) acc = acc.sqr();
+                if ((e[i] >> b) & 1) {
+                    acc = started ? acc * (*this) : *this;
+                    started = true;
+                }
+            }
+        }
+        return acc;
+    }
+    // canonical integers (NOT Montgomery form): a > b
+    DP_HD static bool canon_gt(const Field &a, const Field &b) {
+        for (int i = N - 1; i >= 0; i--)
+            if (a.l[i] != b.l[i]) return a.l[i] > b.l[i];
+        return false;
+    }
+    // canonical integer < modulus
+    DP_HD bool canon_is_reduced() const {
+        for (int i = N - 1; i >= 0; i--)
+            if (l[i] != P::mod(i)) return l[i] < P::mod(i);
+        return false;
+    }
     // x^(p-2) (Fermat); x != 0
     DP_HD Field inverse() const {
         uint32_t e[N];

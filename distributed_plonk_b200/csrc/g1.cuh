@@ -12,6 +12,12 @@
 
 namespace dp {
 
+DP_HD Fq fq_from_u32(uint32_t v) {
+    Fq x = Fq::zero();
+    x.l[0] = v;
+    return x.to_mont();
+}
+
 // affine point as stored on the device: 96 B, (0,0) encodes the point at infinity
 // ((0,0) is not on the curve since b = 4 != 0)
 struct alignas(16) G1Affine {

@@ -130,6 +130,79 @@ __global__ void g1_import_ark_kernel(const uint64_t *ark, G1Affine *out, uint64_
     out[i] = p;
 }
 
+// device affine -> raw ark GroupAffine (104 B; identity = (0, 1, true) like GroupAffine::zero())
+__global__ void g1_export_ark_kernel(const G1Affine *in, uint64_t *ark, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1Affine p = in[i];
+    const bool inf = p.is_inf();
+    if (inf) p.y = Fq::one();
+    uint64_t *dst = ark + i * 13;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        dst[k] = (uint64_t)p.x.l[2 * k] | ((uint64_t)p.x.l[2 * k + 1] << 32);
+        dst[6 + k] = (uint64_t)p.y.l[2 * k] | ((uint64_t)p.y.l[2 * k + 1] << 32);
+    }
+    dst[12] = inf ? 1 : 0;
+}
+
+// Canonical SRS ingest ("next" row 4 of SURVEY.md 8f): ark-serialize 0.3.0 compressed GroupAffine,
+// 48 B per point = canonical x little-endian, bit 7 of the last byte = (y > -y), bit 6 = infinity.
+// One thread per point: y = (x^3 + 4)^((p+1)/4) (p = 3 mod 4), the root whose order matches the flag;
+// optional r-torsion check by double-and-add with the scalar r.  *err = 1 + index of the first
+// rejected point, err[1] = why (1 x >= p, 2 both flags, 3 not on the curve, 4 not in the subgroup).
+__global__ void __launch_bounds__(128) g1_decompress_kernel(const uint32_t *in, G1Affine *out, uint64_t n, uint32_t check_subgroup,
+                                                            unsigned long long *err) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fq xc;
+#pragma unroll
+    for (int k = 0; k < 12; k++) xc.l[k] = in[i * 12 + k];
+    const bool positive = (xc.l[11] >> 31) & 1, infinity = (xc.l[11] >> 30) & 1;
+    xc.l[11] &= 0x3fffffffu;
+    uint32_t why = 0;
+    G1Affine p = G1Affine::inf();
+    if (positive && infinity) {
+        why = 2;
+    } else if (!infinity) {
+        if (!xc.canon_is_reduced()) {
+            why = 1;
+        } else {
+            const Fq x = xc.to_mont();
+            const Fq rhs = x.sqr() * x + fq_from_u32(4);
+            uint32_t e[12];  // (p + 1) / 4: the low limb ...aaab + 1 does not carry
+#pragma unroll
+            for (int k = 0; k < 12; k++) e[k] = FqParams::mod(k);
+            e[0] += 1;
+#pragma unroll
+            for (int k = 0; k < 12; k++) e[k] = (e[k] >> 2) | (k < 11 ? e[k + 1] << 30 : 0);
+            Fq y = rhs.pow_limbs(e, 12);
+            if (y.sqr() != rhs) {
+                why = 3;
+            } else {
+                const Fq ny = y.neg();
+                const bool y_is_larger = Fq::canon_gt(y.from_mont(), ny.from_mont());
+                p = G1Affine{x, y_is_larger == positive ? y : ny};
+                if (check_subgroup) {
+                    G1XYZZ acc = G1XYZZ::inf();
+                    for (int k = 7; k >= 0; k--)
+                        for (int b = 31; b >= 0; b--) {
+                            acc = acc.dbl();
+                            if ((FrParams::mod(k) >> b) & 1) acc = acc.add_mixed(p);
+                        }
+                    if (!acc.is_inf()) why = 4;
+                }
+            }
+        }
+    }
+    if (why) {
+        const unsigned long long mine = ((unsigned long long)(i + 1) << 8) | why;
+        atomicMin(err, mine);
+        p = G1Affine::inf();
+    }
+    out[i] = p;
+}
+
 // Synthetic SRS for benchmarks / tests: out[i] = k_i * G with k_i = SplitMix64(seed, i) (64-bit,
 // distinct points), written in the raw ark GroupAffine layout (104 B) that dp_init ingests.
 DP_HD G1Affine g1_generator() {

@@ -42,6 +42,7 @@ extern "C" {
 
 #define DP_FR_BYTES 32
 #define DP_G1_AFFINE_BYTES 104
+#define DP_G1_COMPRESSED_BYTES 48 /* ark-serialize 0.3.0 compressed GroupAffine */
 #define DP_G1_PROJECTIVE_BYTES 144
 
 typedef struct dp_ctx dp_ctx;
@@ -64,6 +65,18 @@ const char *dp_version(void);
  * `quot_domain_size` (Radix2EvaluationDomain::new rounds both up to powers of two).
  * bases: n_bases raw G1Affine (104 B each), the concatenation of the `bases` Data chunks. */
 int dp_init(dp_ctx *ctx, const void *bases, size_t n_bases, uint64_t domain_size, uint64_t quot_domain_size);
+
+/* "next" row: the same, from the canonical encoding SRS files hold - what the
+ * reference's dispatcher deserialises on the CPU before shipping raw structs (ark-serialize 0.3.0
+ * `GroupAffine::deserialize` / `deserialize_unchecked`; jellyfish `UnivariateUniversalParams`).
+ * bases48: n_bases x 48 B = canonical x little-endian, bit 7 of the last byte = (y > -y), bit 6 =
+ * infinity.  Decompression (a 381-bit square root per point) and, when check_subgroup != 0, the
+ * r-torsion check run on the GPU.  A rejected point (x >= p, both flags, no such point, outside the
+ * subgroup) returns DP_E_ARG naming the first bad index and leaves the context uninitialised.     */
+int dp_init_compressed(dp_ctx *ctx, const void *bases48, size_t n_bases, uint64_t domain_size, uint64_t quot_domain_size,
+                       int check_subgroup);
+/* bases [start, start + n) back as raw G1Affine (104 B each; identity = (0, 1, true))             */
+int dp_get_bases(dp_ctx *ctx, uint64_t start, size_t n, void *out104);
 
 /* ---- PlonkSlave.varMsm (src/worker.rs:159-185) -----------------------------------------------
  * out = sum_{k < min(end-start, n_scalars)} scalars[k] * bases[start + k]

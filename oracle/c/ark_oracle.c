@@ -845,6 +845,99 @@ void orc_g1_generator(uint8_t *out104) {
     memcpy(out104, &g, 104);
 }
 
+/* ------------------------------------------------------------------ canonical point encoding
+ * ark-serialize 0.3.0, `CanonicalSerialize for GroupAffine<P>` (short Weierstrass) [3P-recall: the
+ * crate is not vendored; "next" row 4 of SURVEY.md 8f, the format jellyfish SRS files use]:
+ *   compressed, 48 B: canonical x, little-endian; the two top bits of the last byte are SWFlags:
+ *   bit 7 = PositiveY (y > -y as canonical integers), bit 6 = Infinity (x written as 0).
+ * deserialize: x >= p, both flags set, x^3 + 4 not a square -> error; y = sqrt via (p+1)/4 (p = 3 mod 4),
+ * the root with (y > -y) == flag; the checked variant also requires r * P = 0.                      */
+static int fq_canon_gt(const fq_t *a, const fq_t *b) { /* canonical integers */
+    for (int i = 5; i >= 0; i--)
+        if (a->l[i] != b->l[i]) return a->l[i] > b->l[i];
+    return 0;
+}
+
+void orc_g1_compress(const uint8_t *aff104, uint8_t *out48) {
+    g1a_t p;
+    memcpy(&p, aff104, 104);
+    if (p.infinity) {
+        memset(out48, 0, 48);
+        out48[47] |= 1 << 6;
+        return;
+    }
+    fq_t xc, yc, ny, nyc;
+    fq_to_canonical(&xc, &p.x);
+    fq_to_canonical(&yc, &p.y);
+    fq_neg(&ny, &p.y);
+    fq_to_canonical(&nyc, &ny);
+    memcpy(out48, xc.l, 48);
+    if (fq_canon_gt(&yc, &nyc)) out48[47] |= 1 << 7;
+}
+
+/* 0 ok; -1 x not canonical; -2 bad flags; -3 not on the curve; -4 not in the r-torsion subgroup */
+int orc_g1_decompress(const uint8_t *in48, uint8_t *out104, int check_subgroup) {
+    uint8_t buf[48];
+    memcpy(buf, in48, 48);
+    const int positive = (buf[47] >> 7) & 1, infinity = (buf[47] >> 6) & 1;
+    buf[47] &= 0x3f;
+    g1a_t p;
+    memset(&p, 0, sizeof p);
+    if (positive && infinity) return -2;
+    if (infinity) { /* GroupAffine::zero() = (0, 1, true) */
+        fq_set_one(&p.y);
+        p.infinity = 1;
+        memcpy(out104, &p, 104);
+        return 0;
+    }
+    fq_t xc, mod;
+    memcpy(xc.l, buf, 48);
+    memcpy(mod.l, fq_MOD, 48);
+    if (!fq_canon_gt(&mod, &xc)) return -1;
+    fq_from_canonical(&p.x, &xc);
+    fq_t rhs, four, y, y2;
+    fq_t c4 = {{4, 0, 0, 0, 0, 0}};
+    fq_from_canonical(&four, &c4);
+    fq_sqr(&rhs, &p.x);
+    fq_mul(&rhs, &rhs, &p.x);
+    fq_add(&rhs, &rhs, &four);
+    u64 e[6]; /* (p + 1) / 4 */
+    memcpy(e, fq_MOD, 48);
+    e[0] += 1; /* low limb ...aaab + 1 does not carry */
+    for (int i = 0; i < 6; i++) e[i] = (e[i] >> 2) | (i < 5 ? e[i + 1] << 62 : 0);
+    fq_pow_limbs(&y, &rhs, e, 6);
+    fq_sqr(&y2, &y);
+    if (memcmp(&y2, &rhs, sizeof y2) != 0) return -3;
+    fq_t ny, yc, nyc;
+    fq_neg(&ny, &y);
+    fq_to_canonical(&yc, &y);
+    fq_to_canonical(&nyc, &ny);
+    const int y_is_larger = fq_canon_gt(&yc, &nyc);
+    p.y = (y_is_larger == positive) ? y : ny;
+    if (check_subgroup) {
+        g1j_t q;
+        g1_scalar_mul(&q, &p, fr_MOD);
+        if (!g1j_is_zero(&q)) return -4;
+    }
+    memcpy(out104, &p, 104);
+    return 0;
+}
+
+/* a point of the curve outside the r-torsion subgroup (for the negative test): the first x = 1, 2, ...
+ * with x^3 + 4 a square, NOT multiplied by the cofactor */
+int orc_g1_point_outside_subgroup(uint8_t *out48) {
+    for (u64 x = 1; x < 1000; x++) {
+        uint8_t buf[48] = {0};
+        uint8_t tmp[104];
+        memcpy(buf, &x, 8);
+        if (orc_g1_decompress(buf, tmp, 0) == 0 && orc_g1_decompress(buf, tmp, 1) == -4) {
+            memcpy(out48, buf, 48);
+            return 0;
+        }
+    }
+    return -1;
+}
+
 /* ------------------------------------------------------------------ seeded inputs */
 typedef struct { u64 s; } splitmix_t;
 static u64 splitmix_next(splitmix_t *g) {

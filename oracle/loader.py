@@ -72,6 +72,9 @@ def lib():
             "orc_perm_product": (i, [p, p, p, u64, u64, p, p, p]),
             "orc_quotient_evals": (None, [p, p, p, p, p, p, p, p, p, u64, u64, p]),
             "orc_fr_vec_op": (None, [p, p, p, u64, i]),
+            "orc_g1_compress": (None, [p, p]),
+            "orc_g1_decompress": (i, [p, p, i]),
+            "orc_g1_point_outside_subgroup": (i, [p]),
             "orc_poly_eval": (None, [p, u64, p, p]),
             "orc_poly_lincomb": (None, [p, p, p, u64, p, u64]),
             "orc_poly_div_linear": (None, [p, u64, p, p]),
@@ -182,6 +185,29 @@ def poly_div_linear(coeffs: np.ndarray, point: np.ndarray) -> np.ndarray:
     c, z = np.ascontiguousarray(coeffs, dtype=np.uint64), np.ascontiguousarray(point, dtype=np.uint64)
     out = np.zeros((max(c.shape[0] - 1, 0), 4), dtype=np.uint64)
     lib().orc_poly_div_linear(_ptr(c), c.shape[0], _ptr(z), _ptr(out))
+    return out
+
+
+def g1_compress(bases104: np.ndarray) -> np.ndarray:
+    """[n, 104] raw GroupAffine -> [n, 48] ark-serialize compressed"""
+    b = np.ascontiguousarray(bases104, dtype=np.uint8).reshape(-1, 104)
+    out = np.zeros((b.shape[0], 48), dtype=np.uint8)
+    for k in range(b.shape[0]):
+        lib().orc_g1_compress(b[k].ctypes.data, out[k].ctypes.data)
+    return out
+
+
+def g1_decompress(comp48: np.ndarray, check_subgroup: bool = True):
+    """[n, 48] -> ([n, 104], rc list); rc != 0 marks an invalid encoding (see orc_g1_decompress)"""
+    c = np.ascontiguousarray(comp48, dtype=np.uint8).reshape(-1, 48)
+    out = np.zeros((c.shape[0], 104), dtype=np.uint8)
+    rcs = [lib().orc_g1_decompress(c[k].ctypes.data, out[k].ctypes.data, int(check_subgroup)) for k in range(c.shape[0])]
+    return out, rcs
+
+
+def g1_point_outside_subgroup() -> np.ndarray:
+    out = np.zeros(48, dtype=np.uint8)
+    assert lib().orc_g1_point_outside_subgroup(out.ctypes.data) == 0
     return out
 
 

@@ -262,6 +262,40 @@ def distributed_fft(dom: Domain, coeffs, is_inv, is_coset, n_workers=1):
     return [cols[i][j] for j in range(r) for i in range(c)]
 
 
+# ----------------------------------------------------------------------------- canonical point encoding
+def g1_compress(pt) -> bytes:
+    """ark-serialize 0.3.0 compressed GroupAffine (48 B): x little-endian, bit 7 of the last byte =
+    (y > -y), bit 6 = infinity.  pt = (x, y) ints or None."""
+    if pt is None:
+        return bytes(47) + bytes([1 << 6])
+    x, y = pt
+    b = bytearray(x.to_bytes(48, "little"))
+    if y > FQ_MOD - y:
+        b[47] |= 1 << 7
+    return bytes(b)
+
+
+def g1_decompress(b: bytes, check_subgroup: bool = True):
+    """inverse of g1_compress; raises ValueError like ark's deserialize returns Err"""
+    positive, infinity = b[47] >> 7 & 1, b[47] >> 6 & 1
+    if positive and infinity:
+        raise ValueError("bad flags")
+    if infinity:
+        return None
+    x = int.from_bytes(b[:47] + bytes([b[47] & 0x3F]), "little")
+    if x >= FQ_MOD:
+        raise ValueError("x not canonical")
+    rhs = (x * x * x + G1_B) % FQ_MOD
+    y = pow(rhs, (FQ_MOD + 1) // 4, FQ_MOD)
+    if y * y % FQ_MOD != rhs:
+        raise ValueError("not on the curve")
+    if (y > FQ_MOD - y) != bool(positive):
+        y = FQ_MOD - y
+    if check_subgroup and g1_mul((x, y), FR_MOD) is not None:
+        raise ValueError("not in the subgroup")
+    return (x, y)
+
+
 # ----------------------------------------------------------------------------- rounds 2-5 of Prover::prove
 def perm_product(wires, idp, sigma, beta, gamma):
     """dispatcher2.rs:329-345: z[0] = 1, z[j+1] = z[j] * a_j / b_j.  wires/idp/sigma: [types][n] ints."""

@@ -282,3 +282,42 @@ def check_golden_rounds(make_ctx, impl=None):
     assert np.array_equal(q, g["d_out"]) and np.array_equal(rem, g["e_out"])
     assert np.array_equal(ctx.poly_lincomb([g["l_p0"], g["l_p1"], g["l_p2"]], g["l_coeffs"]), g["l_out"])
     ctx.close()
+
+
+def check_compressed_init(orc, make_ctx, n: int, seed: int):
+    """"next" row 4: SRS ingest from ark-serialize compressed points == ingest of the raw structs"""
+    bases = orc.gen_bases(seed, n, min(n, 64), True)
+    comp = orc.g1_compress(bases)
+    ctx = make_ctx()
+    for check in (False, True):
+        ctx.init_compressed(comp, 1 << 4, 1 << 7, check)
+        assert np.array_equal(ctx.get_bases(0, n), bases), f"decompressed bases differ (check_subgroup={check})"
+    sc = orc.gen_fr(seed + 1, n, False)
+    assert_point_eq(orc, ctx.msm(0, n, sc), orc.msm(bases, sc), "msm over decompressed bases")
+    # rejected encodings name the first bad index and leave the context uninitialised
+    bad = comp.copy()
+    bad[n // 2] = np.frombuffer((B_FQ_MOD + 1).to_bytes(48, "little"), dtype=np.uint8)
+    both = comp.copy()
+    both[3, 47] |= 0xC0
+    nosq = comp.copy()
+    no_point = next(x for x in range(1, 50) if pow((x**3 + 4) % B_FQ_MOD, (B_FQ_MOD - 1) // 2, B_FQ_MOD) != 1)
+    nosq[n - 1] = np.frombuffer(no_point.to_bytes(48, "little"), dtype=np.uint8)
+    nosq[1] = nosq[n - 1]
+    outside = comp.copy()
+    outside[5] = orc.g1_point_outside_subgroup()
+    for arr, idx, word in ((bad, n // 2, "canonical"), (both, 3, "flag"), (nosq, 1, "square"), (outside, 5, "subgroup")):
+        try:
+            ctx.init_compressed(arr, 1 << 4, 1 << 7, True)
+            raise AssertionError(f"accepted an invalid encoding ({word})")
+        except DpError as e:
+            assert e.code == -1 and f"point {idx} " in str(e) and word in str(e), str(e)
+        try:
+            ctx.msm(0, 1, sc[:1])
+            raise AssertionError("context usable after a failed init")
+        except DpError as e:
+            assert e.code == -2
+    ctx.init_compressed(outside, 1 << 4, 1 << 7, False)       # the unchecked variant accepts it (deserialize_unchecked)
+    ctx.close()
+
+
+B_FQ_MOD = 0x1A0111EA397FE69A4B1BA7B6434BACD764774B84F38512BF6730D2A0F6B0F6241EABFFFEB153FFFFB9FEFFFFFFFFAAAB

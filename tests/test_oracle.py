@@ -230,3 +230,36 @@ def test_quotient_of_a_satisfied_circuit_is_a_polynomial(orc):
 def test_golden_rounds(orc):
     from tests import common
     common.check_golden_rounds(None, impl=orc)
+
+
+def test_point_encoding_tier1_vs_tier0(orc):
+    """ark-serialize compressed G1 ("next" row 4): C oracle == Python ints; round trip; error cases"""
+    bases = orc.gen_bases(11, 24, 24, True)
+    comp = orc.g1_compress(bases)
+    for k in range(bases.shape[0]):
+        pt = B.g1_affine_from_bytes(bases[k].tobytes())
+        assert comp[k].tobytes() == B.g1_compress(pt)
+        assert B.g1_decompress(comp[k].tobytes()) == pt
+    back, rcs = orc.g1_decompress(comp)
+    assert rcs == [0] * len(rcs) and np.array_equal(back, bases)
+    # the generator: y is the smaller root, so the encoding is x little-endian with no flag bits
+    gen = np.zeros(104, dtype=np.uint8)
+    orc.lib().orc_g1_generator(gen.ctypes.data)
+    assert orc.g1_compress(gen[None])[0].tobytes() == B.G1_GEN[0].to_bytes(48, "little")
+    neg = B.g1_compress(B.g1_neg(B.G1_GEN))
+    assert neg[47] >> 7 == 1 and neg[:47] == B.G1_GEN[0].to_bytes(48, "little")[:47]
+    # errors: x >= p, both flags, x with no point, a curve point outside the subgroup
+    bad_x = np.frombuffer((B.FQ_MOD + 1).to_bytes(48, "little"), dtype=np.uint8)
+    both = comp[0].copy()
+    both[47] |= 0xC0
+    outside = orc.g1_point_outside_subgroup()
+    assert orc.g1_decompress(np.stack([bad_x, both, outside]))[1] == [-1, -2, -4]
+    assert orc.g1_decompress(outside[None], check_subgroup=False)[1] == [0]
+    no_point = next(x for x in range(1, 50) if pow((x**3 + 4) % B.FQ_MOD, (B.FQ_MOD - 1) // 2, B.FQ_MOD) != 1)
+    assert orc.g1_decompress(np.frombuffer(no_point.to_bytes(48, "little"), dtype=np.uint8)[None])[1] == [-3]
+    for raw, exc in ((bad_x, "canonical"), (both, "flags"), (outside, "subgroup")):
+        try:
+            B.g1_decompress(raw.tobytes())
+            assert False
+        except ValueError as e:
+            assert exc in str(e)

@@ -110,3 +110,9 @@ def test_satisfied_circuit_divides_exactly(orc, gpu_lib, log_n):
     c.init(orc.gen_bases(5, 40, 8, False), 1 << log_n, 8 << log_n)
     common.check_satisfied_circuit(orc, c, log_n, 2500 + log_n)
     c.close()
+
+
+@pytest.mark.parametrize("n", [40, 5000])
+def test_compressed_srs_ingest(orc, gpu_lib, n):
+    """"next" row §8(f)-4: ark-serialize compressed points decompressed (and subgroup-checked) on the GPU"""
+    common.check_compressed_init(orc, lambda: Context(gpu_lib, 0, 0, 1), n, 2600 + n)

@@ -845,6 +845,31 @@ void orc_g1_generator(uint8_t *out104) {
     memcpy(out104, &g, 104);
 }
 
+/* KZG SRS with a KNOWN trapdoor, for tests only: out[i] = tau^i * G (tau canonical, 4 limbs).
+ * With tau known, commit(p) = p(tau) * G, so opening proofs can be checked in the group without a
+ * pairing: (tau - z) * commit(q) + p(z) * G == commit(p)  for q = (p - p(z)) / (X - z).            */
+void orc_gen_srs(const u64 *tau, u64 n, uint8_t *out104) {
+    fr_t t, cur;
+    fr_from_canonical(&t, (const fr_t *)tau);
+    fr_t *pw = (fr_t *)malloc((n ? n : 1) * sizeof(fr_t));
+    fr_set_one(&cur);
+    for (u64 i = 0; i < n; i++) {
+        fr_to_canonical(&pw[i], &cur);
+        fr_mul(&cur, &cur, &t);
+    }
+    g1a_t g;
+    g1_generator(&g);
+#pragma omp parallel for schedule(dynamic, 16)
+    for (u64 i = 0; i < n; i++) {
+        g1j_t q;
+        g1a_t a;
+        g1_scalar_mul(&q, &g, pw[i].l);
+        g1j_to_affine(&a, &q);
+        memcpy(out104 + 104 * i, &a, 104);
+    }
+    free(pw);
+}
+
 /* ------------------------------------------------------------------ canonical point encoding
  * ark-serialize 0.3.0, `CanonicalSerialize for GroupAffine<P>` (short Weierstrass) [3P-recall: the
  * crate is not vendored; "next" row 4 of SURVEY.md 8f, the format jellyfish SRS files use]:

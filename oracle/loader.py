@@ -72,6 +72,7 @@ def lib():
             "orc_perm_product": (i, [p, p, p, u64, u64, p, p, p]),
             "orc_quotient_evals": (None, [p, p, p, p, p, p, p, p, p, u64, u64, p]),
             "orc_fr_vec_op": (None, [p, p, p, u64, i]),
+            "orc_gen_srs": (None, [p, u64, p]),
             "orc_g1_compress": (None, [p, p]),
             "orc_g1_decompress": (i, [p, p, i]),
             "orc_g1_point_outside_subgroup": (i, [p]),
@@ -186,6 +187,37 @@ def poly_div_linear(coeffs: np.ndarray, point: np.ndarray) -> np.ndarray:
     out = np.zeros((max(c.shape[0] - 1, 0), 4), dtype=np.uint64)
     lib().orc_poly_div_linear(_ptr(c), c.shape[0], _ptr(z), _ptr(out))
     return out
+
+
+def gen_srs(tau_canonical: np.ndarray, n: int) -> np.ndarray:
+    """[tau^i] G, i < n, as raw GroupAffine structs (tests only: the trapdoor is known)"""
+    t = np.ascontiguousarray(tau_canonical, dtype=np.uint64)
+    out = np.zeros((n, 104), dtype=np.uint8)
+    lib().orc_gen_srs(_ptr(t), n, _ptr(out))
+    return out
+
+
+def g1_mul(aff104: np.ndarray, k_canonical: np.ndarray) -> np.ndarray:
+    out = np.zeros(104, dtype=np.uint8)
+    lib().orc_g1_mul(_ptr(np.ascontiguousarray(aff104, dtype=np.uint8)), _ptr(np.ascontiguousarray(k_canonical, dtype=np.uint64)), _ptr(out))
+    return out
+
+
+def affine_to_jacobian(aff104: np.ndarray) -> np.ndarray:
+    """raw GroupAffine -> raw GroupProjective with z = 1 (identity: (0, 1, 0))"""
+    a = np.ascontiguousarray(aff104, dtype=np.uint8)
+    out = np.zeros(144, dtype=np.uint8)
+    out[:96] = a[:96]
+    if a[96]:
+        out[:96] = 0
+        out[48:96] = _FQ_ONE
+    else:
+        out[96:144] = _FQ_ONE
+    return out
+
+
+_FQ_ONE = np.array([0x760900000002fffd, 0xebf4000bc40c0002, 0x5f48985753c758ba, 0x77ce585370525745, 0x5c071a97a256ec6d,
+                    0x15f65ec3fa80e493], dtype=np.uint64).view(np.uint8)
 
 
 def g1_compress(bases104: np.ndarray) -> np.ndarray:

@@ -321,3 +321,31 @@ def check_compressed_init(orc, make_ctx, n: int, seed: int):
 
 
 B_FQ_MOD = 0x1A0111EA397FE69A4B1BA7B6434BACD764774B84F38512BF6730D2A0F6B0F6241EABFFFEB153FFFFB9FEFFFFFFFFAAAB
+
+
+def check_kzg_opening(orc, make_ctx, n: int, seed: int):
+    """Protocol-level property of round 5 (what the reference's verifier checks with a pairing in
+    test_plonk): over an SRS with a KNOWN trapdoor tau, commit(p) = p(tau) G, so for the witness
+    q = (p - p(z)) / (X - z) computed by the library   (tau - z) commit(q) + p(z) G == commit(p).
+    MSM (dp_commit), evaluation and division kernels all take part; the oracle only does group algebra."""
+    from oracle.py import bls12_381 as B
+    tau = orc.gen_fr(seed, 1, False)[0]
+    srs = orc.gen_srs(tau, n)
+    ctx = make_ctx()
+    ctx.init(srs, 1 << 4, 1 << 7)
+    p, z = orc.gen_fr(seed + 1, n), orc.gen_fr(seed + 2, 1)[0]
+    q, rem = ctx.poly_div_linear(p, z)
+    assert np.array_equal(rem, ctx.poly_eval(p, z))
+    c_p, c_q = ctx.commit(p), ctx.commit(q)
+    tau_i = int.from_bytes(tau.tobytes(), "little")
+    z_i, rem_i = B.fr_from_mont_bytes(z.tobytes()), B.fr_from_mont_bytes(rem.tobytes())
+    as_k = lambda v: np.frombuffer((v % B.FR_MOD).to_bytes(32, "little"), dtype=np.uint64)
+    gen = np.zeros(104, dtype=np.uint8)
+    orc.lib().orc_g1_generator(gen.ctypes.data)
+    lhs = orc.g1_add(orc.affine_to_jacobian(orc.g1_mul(orc.normalize(c_q), as_k(tau_i - z_i))),
+                     orc.affine_to_jacobian(orc.g1_mul(gen, as_k(rem_i))))
+    assert np.array_equal(orc.normalize(lhs), orc.normalize(c_p)), "KZG opening identity"
+    # and commit(p) really is p(tau) G
+    p_tau = B.fr_from_mont_bytes(ctx.poly_eval(p, orc.from_repr(tau[None])[0]).tobytes())
+    assert np.array_equal(orc.g1_mul(gen, as_k(p_tau)), orc.normalize(c_p))
+    ctx.close()

@@ -209,6 +209,10 @@ def test_compressed_srs_ingest(orc, emul_lib):
     common.check_compressed_init(orc, lambda: Context(emul_lib, 0, 0, 1), 40, 1300)
 
 
+def test_kzg_opening_identity(orc, emul_lib):
+    common.check_kzg_opening(orc, lambda: Context(emul_lib, 0, 0, 1), 100, 1400)
+
+
 def test_golden_rounds(orc, emul_lib):
     def make(n, m):
         c = Context(emul_lib, 0, 0, 1)

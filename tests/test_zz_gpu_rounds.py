@@ -116,3 +116,8 @@ def test_satisfied_circuit_divides_exactly(orc, gpu_lib, log_n):
 def test_compressed_srs_ingest(orc, gpu_lib, n):
     """"next" row §8(f)-4: ark-serialize compressed points decompressed (and subgroup-checked) on the GPU"""
     common.check_compressed_init(orc, lambda: Context(gpu_lib, 0, 0, 1), n, 2600 + n)
+
+
+def test_kzg_opening_identity(orc, gpu_lib):
+    """round 5 end to end over an SRS with a known trapdoor: (tau - z) commit(q) + p(z) G == commit(p)"""
+    common.check_kzg_opening(orc, lambda: Context(gpu_lib, 0, 0, 1), 3000, 2700)

@@ -16,6 +16,7 @@ EXPORTS = [
     "dp_last_msm_breakdown", "dp_debug_gen_bases", "dp_fft_dev_rows", "dp_fft_dev_cols", "dp_peer_ready", "dp_fft_dev_rows_p2p", "dp_fft_dev_p2p", "dp_msm_dev_batch", "dp_perm_product", "dp_msm_batch", "dp_perm_product_dev",
     "dp_quotient_evals", "dp_quotient_evals_dev", "dp_poly_eval", "dp_poly_eval_dev", "dp_poly_lincomb", "dp_poly_lincomb_dev",
     "dp_poly_div_linear", "dp_poly_div_linear_dev", "dp_init_compressed", "dp_get_bases",
+    "dp_msm_submit", "dp_msm_collect",
 ]
 
 
@@ -76,6 +77,8 @@ def bind(cdll: C.CDLL) -> C.CDLL:
         "dp_msm_dev_batch": (i, [vp, sz, C.POINTER(u64), C.POINTER(u64), C.POINTER(vp), C.POINTER(sz), C.POINTER(vp)]),
         "dp_fft_dev_rows_p2p": (i, [vp, vp, i, i, i]),
         "dp_fft_dev_p2p": (i, [vp, vp, vp, i, i, i]),
+        "dp_msm_submit": (i, [vp, u64, u64, u64, vp, sz]),
+        "dp_msm_collect": (i, [vp, u64, vp]),
         "dp_init_compressed": (i, [vp, vp, sz, u64, u64, i]),
         "dp_get_bases": (i, [vp, u64, sz, vp]),
         "dp_quotient_evals": (i, [vp, C.POINTER(QuotientArgs), vp]),
@@ -205,6 +208,24 @@ class Context:
     def perm_product_dev(self, wires_ptr: int, id_ptr: int, sigma_ptr: int, n_types: int, n: int, beta: np.ndarray, gamma: np.ndarray, out_ptr: int):
         b, g = np.ascontiguousarray(beta, dtype=np.uint64), np.ascontiguousarray(gamma, dtype=np.uint64)
         self._ck(self.lib.dp_perm_product_dev(self.h, wires_ptr, id_ptr, sigma_ptr, n_types, n, _addr(b), _addr(g), out_ptr))
+
+    def msm_submit(self, job_id: int, start: int, end: int, scalars, n: int | None = None):
+        """asynchronous varMsm: scalars = [n,4] host array (kept alive by the caller) or a host pointer + n"""
+        if isinstance(scalars, int):
+            self._ck(self.lib.dp_msm_submit(self.h, job_id, start, end, scalars, n))
+        else:
+            a = np.ascontiguousarray(scalars)
+            self._keep = getattr(self, "_keep", {})
+            self._keep[job_id] = a
+            self._ck(self.lib.dp_msm_submit(self.h, job_id, start, end, _addr(a) if a.size else None, a.nbytes // 32))
+
+    def msm_collect(self, job_id: int) -> np.ndarray:
+        out = np.zeros(G1_PROJECTIVE_BYTES, dtype=np.uint8)
+        try:
+            self._ck(self.lib.dp_msm_collect(self.h, job_id, _addr(out)))
+        finally:
+            getattr(self, "_keep", {}).pop(job_id, None)
+        return out
 
     def init_compressed(self, bases48: np.ndarray, domain_size: int, quot_domain_size: int, check_subgroup: bool = True):
         """dp_init from ark-serialize compressed points ([n, 48] uint8)"""

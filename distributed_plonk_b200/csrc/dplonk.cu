@@ -116,6 +116,10 @@ struct FftTask {
 
 }  // namespace
 
+namespace {
+struct MsmPending;  // defined with the MSM driver below
+}
+
 struct dp_ctx {
     int device = 0;
     uint64_t me = 0, W = 1;
@@ -150,6 +154,10 @@ struct dp_ctx {
     Fr *peer_arena[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     uint64_t p2p_seq = 0;           // exchanges issued so far; must advance identically on every rank
     uint32_t bar_seq = 0;           // device-side barriers issued so far (p2p_barrier_kernel)
+    // MSMs submitted with dp_msm_submit and not collected yet (keyed by the caller's id)
+    std::map<uint64_t, MsmPending *> msm_pending;
+    uint8_t *msm_pinned = nullptr;  // MSM_SLOTS x MSM_SLOT_BYTES of pinned host memory: result + error flag per job
+    uint64_t msm_slots_used = 0;    // bit mask
     Fr *dev_send = nullptr, *dev_recv = nullptr;  // dp_fft_dev_rows / _cols staging (one transform in flight)
     Fr *dev_p2p_slot = nullptr;                   // receive slot of the last dp_fft_dev_rows_p2p
     int dev_flags = -1;
@@ -591,6 +599,16 @@ struct MsmJob {
     cudaEvent_t ev_head = nullptr;
 };
 
+// an MSM between dp_msm_submit and dp_msm_collect
+constexpr uint32_t MSM_SLOTS = 64, MSM_SLOT_BYTES = 256;  // pinned: 144 B result at 0, error flag at 192
+struct MsmPending {
+    MsmJob job;
+    uint4 *scalars = nullptr;         // pool_io
+    G1JacobianOut *out = nullptr;     // pool
+    cudaEvent_t ev_in = nullptr, ev_done = nullptr;
+    uint32_t slot = 0;
+};
+
 int msm_enqueue(dp_ctx *ctx, uint64_t start, const uint4 *scalars_dev, uint64_t n, G1JacobianOut *out_dev, MsmJob &job,
                 bool record_breakdown) {
     cudaStream_t st = ctx->stream, tl = ctx->s_tail;
@@ -692,6 +710,24 @@ int msm_device(dp_ctx *ctx, uint64_t start, const uint4 *scalars_dev, uint64_t n
     int rc = msm_enqueue(ctx, start, scalars_dev, n, out_dev, jobs[0], n != 0);
     int rc2 = msm_finish(ctx, jobs, rc == DP_OK && n != 0);
     return rc != DP_OK ? rc : rc2;
+}
+
+// give back everything a pending MSM holds; the caller has made sure its kernels are done
+void release_pending(dp_ctx *ctx, MsmPending *p) {
+    for (void *q : p->job.scratch) ctx->pool.release(q);
+    if (p->job.ev_head) cudaEventDestroy(p->job.ev_head);
+    ctx->pool_io.release(p->scalars);
+    ctx->pool.release(p->out);
+    if (p->ev_in) cudaEventDestroy(p->ev_in);
+    if (p->ev_done) cudaEventDestroy(p->ev_done);
+    ctx->msm_slots_used &= ~(1ull << p->slot);
+    delete p;
+}
+
+// dp_init / dp_destroy: every stream has been synchronised
+void drop_pending_msms(dp_ctx *ctx) {
+    for (auto &kv : ctx->msm_pending) release_pending(ctx, kv.second);
+    ctx->msm_pending.clear();
 }
 
 FftTask *find_task(dp_ctx *ctx, uint64_t id) {
@@ -838,6 +874,9 @@ int dp_destroy(dp_ctx *ctx) {
         if (kv.second.ev_in) cudaEventDestroy(kv.second.ev_in);
         if (kv.second.ev_c) cudaEventDestroy(kv.second.ev_c);
     }
+    cudaStreamSynchronize(ctx->s_tail);
+    drop_pending_msms(ctx);
+    if (ctx->msm_pinned) cudaFreeHost(ctx->msm_pinned);
     ctx->pool.destroy();
     ctx->pool_io.destroy();
     for (uint64_t q = 0; q < 8; q++)
@@ -888,6 +927,8 @@ static int init_impl(dp_ctx *ctx, const void *bases, size_t n_bases, uint64_t do
     cudaStreamSynchronize(ctx->s_out);
     for (auto &kv : ctx->tasks) free_task(ctx, kv.second);
     ctx->tasks.clear();
+    cudaStreamSynchronize(ctx->s_tail);
+    drop_pending_msms(ctx);
     ctx->pool.release(ctx->bases);
     ctx->pool.release(ctx->pre_table);
     ctx->bases = nullptr;
@@ -1077,6 +1118,79 @@ int dp_msm_batch(dp_ctx *ctx, size_t n_jobs, const uint64_t *starts, const uint6
     ctx->pool.release(od);
     if (rc != DP_OK) return rc;
     return call_end(ctx, true);
+}
+
+// varMsm without blocking the caller: the Rust worker answers the RPC from a Promise (like fft2Prepare,
+// worker.rs:293), so that transforms and commitments of concurrent requests share the GPU: the copy-in
+// runs on s_in, the kernels queue behind whatever the compute stream holds, the 144-byte result lands in
+// pinned host memory.  dp_msm_collect waits for that one job only.
+int dp_msm_submit(dp_ctx *ctx, uint64_t id, uint64_t start, uint64_t end, const void *scalars, size_t n_scalars) {
+    if (!ctx) return DP_E_ARG;
+    if (!ctx->inited) return fail(ctx, DP_E_STATE, "dp_msm_submit before dp_init");
+    if (start > end || end > ctx->n_bases) return fail(ctx, DP_E_ARG, "dp_msm_submit: range [%llu,%llu) outside %llu bases", (unsigned long long)start, (unsigned long long)end, (unsigned long long)ctx->n_bases);
+    if (n_scalars && !scalars) return fail(ctx, DP_E_ARG, "dp_msm_submit: scalars is NULL");
+    if (ctx->msm_pending.count(id)) return fail(ctx, DP_E_STATE, "dp_msm_submit: id %llu is already pending", (unsigned long long)id);
+    if (ctx->msm_slots_used == ~0ull) return fail(ctx, DP_E_STATE, "dp_msm_submit: %u jobs pending, collect some first", MSM_SLOTS);
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->msm_pinned) DP_CUDA(ctx, cudaMallocHost((void **)&ctx->msm_pinned, (size_t)MSM_SLOTS * MSM_SLOT_BYTES));
+    const uint64_t n = (end - start) < n_scalars ? (end - start) : n_scalars;
+    MsmPending *p = new MsmPending();
+    while (ctx->msm_slots_used & (1ull << p->slot)) p->slot++;
+    ctx->msm_slots_used |= 1ull << p->slot;
+    uint8_t *pin = ctx->msm_pinned + (size_t)p->slot * MSM_SLOT_BYTES;
+    memset(pin, 0, MSM_SLOT_BYTES);
+    p->scalars = (uint4 *)ctx->pool_io.alloc((n ? n : 1) * 32);
+    p->out = (G1JacobianOut *)ctx->pool.alloc(sizeof(G1JacobianOut));
+    int rc = DP_OK;
+    cudaError_t e = cudaSuccess;
+    if (!p->scalars || !p->out) rc = fail(ctx, DP_E_OOM, "dp_msm_submit buffers");
+    if (rc == DP_OK) e = cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming);
+    if (rc == DP_OK && e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_done, cudaEventDisableTiming);
+    if (rc == DP_OK && e == cudaSuccess && n) e = cudaMemcpyAsync(p->scalars, scalars, n * 32, cudaMemcpyHostToDevice, ctx->s_in);
+    if (rc == DP_OK && e == cudaSuccess) e = cudaEventRecord(p->ev_in, ctx->s_in);
+    if (rc == DP_OK && e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, p->ev_in, 0);
+    if (rc == DP_OK && e == cudaSuccess) rc = msm_enqueue(ctx, start, p->scalars, n, p->out, p->job, false);
+    if (rc == DP_OK && e == cudaSuccess && n == 0) {  // the identity was written on the compute stream: order the tail stream after it
+        e = cudaEventCreateWithFlags(&p->job.ev_head, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(p->job.ev_head, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->s_tail, p->job.ev_head, 0);
+    }
+    if (rc == DP_OK && e == cudaSuccess) e = cudaMemcpyAsync(pin, p->out, sizeof(G1JacobianOut), cudaMemcpyDeviceToHost, ctx->s_tail);
+    if (rc == DP_OK && e == cudaSuccess && p->job.err) e = cudaMemcpyAsync(pin + 192, p->job.err, 4, cudaMemcpyDeviceToHost, ctx->s_tail);
+    if (rc == DP_OK && e == cudaSuccess) e = cudaEventRecord(p->ev_done, ctx->s_tail);
+    if (rc == DP_OK && e != cudaSuccess) rc = fail(ctx, DP_E_CUDA, "dp_msm_submit: %s", cudaGetErrorString(e));
+    if (rc != DP_OK) {  // nothing of this job may still be running when its buffers go back
+        cudaStreamSynchronize(ctx->s_in);
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->s_tail);
+        release_pending(ctx, p);
+        return rc;
+    }
+    ctx->msm_pending[id] = p;
+    return DP_OK;
+}
+
+int dp_msm_collect(dp_ctx *ctx, uint64_t id, void *out) {
+    if (!ctx || !out) return fail(ctx, DP_E_ARG, "dp_msm_collect: NULL argument");
+    auto it = ctx->msm_pending.find(id);
+    if (it == ctx->msm_pending.end()) return fail(ctx, DP_E_STATE, "dp_msm_collect: no pending job %llu", (unsigned long long)id);
+    MsmPending *p = it->second;
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaError_t e = cudaEventSynchronize(p->ev_done);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    const uint8_t *pin = ctx->msm_pinned + (size_t)p->slot * MSM_SLOT_BYTES;
+    uint32_t bad = 0;
+    memcpy(out, pin, sizeof(G1JacobianOut));
+    memcpy(&bad, pin + 192, 4);
+    if (e != cudaSuccess) {  // make sure nothing is running before the buffers go back
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->s_tail);
+    }
+    release_pending(ctx, p);
+    ctx->msm_pending.erase(it);
+    if (e != cudaSuccess) return fail(ctx, DP_E_CUDA, "msm kernels: %s", cudaGetErrorString(e));
+    if (bad) return fail(ctx, DP_E_ARG, "msm: a scalar is not a canonical Fr integer (>= 2^255)");
+    return DP_OK;
 }
 
 static int commit_device(dp_ctx *ctx, const Fr *coeffs_dev, uint64_t n, G1JacobianOut *out_dev) {

@@ -91,6 +91,15 @@ int dp_msm(dp_ctx *ctx, uint64_t start, uint64_t end, const void *scalars, size_
 int dp_msm_batch(dp_ctx *ctx, size_t n_jobs, const uint64_t *starts, const uint64_t *ends, const void *const *scalars,
                  const size_t *n_scalars, void *const *outs);
 
+/* varMsm answered asynchronously (the Rust worker returns a Promise, as it already does for
+ * fft2Prepare, src/worker.rs:293): dp_msm_submit queues the copy-in and the kernels behind whatever
+ * the context is doing and returns; dp_msm_collect blocks until THAT job is done and writes the
+ * 144-byte G1Projective.  `id` is the caller's (unique among pending jobs; at most 64 pending).
+ * `scalars` must stay valid until the copy-in has run (dp_msm_collect, or dp_sync).  Lets
+ * commitments share the GPU with transforms whose time goes into PCIe transfers.                 */
+int dp_msm_submit(dp_ctx *ctx, uint64_t id, uint64_t start, uint64_t end, const void *scalars, size_t n_scalars);
+int dp_msm_collect(dp_ctx *ctx, uint64_t id, void *out144);
+
 /* ---- commit_polynomial (src/worker.rs:117-123) -----------------------------------------------
  * Fr::into_repr on every coefficient, zero-pad to bases.len(), MSM over all bases.
  * coeffs: n raw Fr (Montgomery), n <= n_bases. */

@@ -349,3 +349,103 @@ def check_kzg_opening(orc, make_ctx, n: int, seed: int):
     p_tau = B.fr_from_mont_bytes(ctx.poly_eval(p, orc.from_repr(tau[None])[0]).tobytes())
     assert np.array_equal(orc.g1_mul(gen, as_k(p_tau)), orc.normalize(c_p))
     ctx.close()
+
+
+def check_async_msm(orc, ctx: Context, bases, n: int, seed: int):
+    """dp_msm_submit / dp_msm_collect: several commitments in flight, interleaved with a transform and
+    collected out of order, equal the blocking dp_msm; error behaviour of the job table"""
+    sets = [orc.gen_fr(seed + k, n - 3 * k, False) for k in range(4)]
+    sets[2][::3] = 0
+    ranges = [(0, n), (3, n), (0, n - 6), (5, n - 4)]
+    for k, (sc, (lo, hi)) in enumerate(zip(sets, ranges)):
+        ctx.msm_submit(100 + k, lo, hi, sc)
+        if k == 1:   # a whole transform goes through the context while jobs are pending
+            x = orc.gen_fr(seed + 9, 64)
+            assert np.array_equal(ctx.ntt(x, 6, False, True), orc.fft(x, False, True))
+    ctx.msm_submit(200, 7, 7, np.zeros((0, 4), dtype=np.uint64))          # empty range -> identity
+    for k in (2, 0, 3, 1):
+        sc, (lo, hi) = sets[k], ranges[k]
+        m = min(hi - lo, sc.shape[0])
+        assert_point_eq(orc, ctx.msm_collect(100 + k), orc.msm(bases[lo:lo + m], sc[:m]), f"async msm job {k}")
+    assert np.array_equal(orc.normalize(ctx.msm_collect(200))[96:97], np.array([1], dtype=np.uint8))
+    # job table errors
+    ctx.msm_submit(1, 0, n, sets[0])
+    for call, code in ((lambda: ctx.msm_submit(1, 0, n, sets[0]), -2), (lambda: ctx.msm_collect(999), -2),
+                       (lambda: ctx.msm_submit(2, 0, n + 10**6, sets[0]), -1)):
+        try:
+            call()
+            raise AssertionError("expected a DpError")
+        except DpError as e:
+            assert e.code == code, str(e)
+    assert_point_eq(orc, ctx.msm_collect(1), orc.msm(bases[:n], sets[0]), "job 1 after the rejected calls")
+    # a scalar >= 2^255 (not a canonical Fr): whatever the blocking call does with it - an error when the
+    # top window overflows, the plain 256-bit multiple otherwise - the asynchronous one does too
+    bad = sets[0].copy()
+    bad[5] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    outcome = []
+    for call in (lambda: ctx.msm(0, n, bad), lambda: (ctx.msm_submit(3, 0, n, bad), ctx.msm_collect(3))[1]):
+        try:
+            outcome.append(orc.normalize(call()).tobytes())
+        except DpError as e:
+            outcome.append(e.code)
+    assert outcome[0] == outcome[1], outcome
+    # 64 jobs may be pending, the 65th is refused; all of them still complete (empty jobs: the identity)
+    empty = np.zeros((0, 4), dtype=np.uint64)
+    for k in range(63):
+        ctx.msm_submit(1000 + k, 7, 7, empty)
+    ctx.msm_submit(1063, 0, 8, sets[0][:8])
+    try:
+        ctx.msm_submit(2000, 0, 8, sets[0][:8])
+        raise AssertionError("65 pending jobs accepted")
+    except DpError as e:
+        assert e.code == -2
+    assert_point_eq(orc, ctx.msm_collect(1063), orc.msm(bases[:8], sets[0][:8]), "the 64th job")
+    for k in range(63):
+        assert orc.normalize(ctx.msm_collect(1000 + k))[96] == 1
+
+
+def check_schedule(orc, ctx: Context, bases, log_n: int, log_m: int, seed: int, rank: int = 0, world: int = 1, exchange=None, gather=None):
+    """distributed_plonk_b200/schedule.py: the serial and the overlapped host schedules (transforms with
+    look-ahead, commitments batched or queued between transforms) give every transform and every
+    commitment of the job list exactly as the oracle does.  Distinct inputs per transform.
+    gather(array) -> concatenation over ranks (identity for one worker)."""
+    from distributed_plonk_b200 import schedule
+    gather = gather or (lambda a: a)
+    specs = [(log_n, False, True, False), (log_m, True, False, True), (log_m, True, False, True), (log_m, True, True, True),
+             (log_n, False, False, False), (log_m, True, False, True), (log_n, False, True, True)]
+    transforms, expect, keep = [], {}, []
+    for k, (L, is_quot, inv, cos) in enumerate(specs):
+        x = orc.gen_fr(seed + k, 1 << L)
+        wl = disp.fft_workloads(L, world)
+        r, c = 1 << (L >> 1), (1 << L) >> (L >> 1)
+        rows = np.ascontiguousarray(disp.dispatcher_rows(x, L)[wl[rank][0]:wl[rank][1]])
+        out = np.zeros(((wl[rank][3] - wl[rank][2]) * r, 4), dtype=np.uint64)
+        keep += [rows, out]
+        t = schedule.Transform(rows.ctypes.data, out.ctypes.data, out.nbytes, wl, wl[rank][1] - wl[rank][0], is_quot, inv, cos)
+        transforms.append(t)
+        expect[id(t)] = (out, orc.fft(x, inv, cos), c, r)
+    n_b = bases.shape[0]
+    lo, hi = rank * n_b // world, (rank + 1) * n_b // world
+    sc = np.ascontiguousarray(orc.gen_fr(seed + 50, n_b, False)[lo:hi])
+    com = schedule.Commitment(lo, hi, sc.ctypes.data, hi - lo)
+    ref_msm = orc.normalize(orc.msm(bases[lo:hi], sc))
+    seen = {"fft": 0, "msm": 0}
+
+    def on_fft(t):
+        out, ref, c, r = expect[id(t)]
+        cols = gather(out.copy()).reshape(c, r, 4)
+        assert np.array_equal(disp.assemble(cols), ref), "transform result"
+        out[:] = 0
+        seen["fft"] += 1
+
+    def on_msm(o):
+        assert np.array_equal(orc.normalize(o), ref_msm), "commitment result"
+        seen["msm"] += 1
+
+    run = schedule.Runner(ctx, exchange, first_id=7000)
+    run.run_serial(transforms, com, (2, 1), 2, on_fft, on_msm)
+    assert seen == {"fft": len(specs), "msm": 3}
+    run.run_overlapped(transforms, com, 5, 4, on_fft, on_msm)          # more commitments than pairs of transforms
+    assert seen == {"fft": 2 * len(specs), "msm": 8}
+    run.run_overlapped(transforms[:2], com, 0, 1, on_fft, on_msm)
+    assert seen == {"fft": 2 * len(specs) + 2, "msm": 8}

@@ -68,6 +68,21 @@ def _worker(rank, world, port, lib_path, out_dir, backend="gloo"):
         return good
 
     ok &= run_ffts("collective")          # one all_to_all_single per transform
+
+    # the host schedules of bench.py's end-to-end leg (serial / commitments queued between transforms)
+    def gather(a):
+        mine = torch.from_numpy(a.view(np.int64))
+        if cuda:
+            mine = mine.cuda()
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        return torch.cat(parts).cpu().numpy().view(np.uint64)
+    from tests import common
+    try:
+        common.check_schedule(orc, w.ctx, bases, 6, 9, 1700, rank, world, exchange, gather)
+    except AssertionError as e:
+        print("schedule check failed:", e, flush=True)
+        ok = False
     if cuda:
         # CUDA IPC arenas need real GPUs (an emulated handle is a bare pointer of another process)
         ok &= bool(parallel.attach_peers(w.ctx, 2 * (1 << 9) * 32 // world))

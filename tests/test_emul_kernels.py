@@ -209,6 +209,27 @@ def test_compressed_srs_ingest(orc, emul_lib):
     common.check_compressed_init(orc, lambda: Context(emul_lib, 0, 0, 1), 40, 1300)
 
 
+def test_async_msm(orc, emul_lib):
+    bases = orc.gen_bases(5, 600, 64, True)
+    c = Context(emul_lib, 0, 0, 1)
+    c.init(bases, 1 << 6, 1 << 9)
+    common.check_async_msm(orc, c, bases, 300, 1500)
+    c.msm_submit(7, 0, 100, orc.gen_fr(1, 100, False))      # a job still pending at re-init / close is dropped
+    c.init(bases, 1 << 6, 1 << 9)
+    with pytest.raises(DpError):
+        c.msm_collect(7)
+    c.msm_submit(8, 0, 100, orc.gen_fr(1, 100, False))
+    c.close()
+
+
+def test_host_schedules(orc, emul_lib):
+    bases = orc.gen_bases(5, 200, 64, True)
+    c = Context(emul_lib, 0, 0, 1)
+    c.init(bases, 1 << 6, 1 << 9)
+    common.check_schedule(orc, c, bases, 6, 9, 1600)
+    c.close()
+
+
 def test_kzg_opening_identity(orc, emul_lib):
     common.check_kzg_opening(orc, lambda: Context(emul_lib, 0, 0, 1), 100, 1400)
 

@@ -121,3 +121,22 @@ def test_compressed_srs_ingest(orc, gpu_lib, n):
 def test_kzg_opening_identity(orc, gpu_lib):
     """round 5 end to end over an SRS with a known trapdoor: (tau - z) commit(q) + p(z) G == commit(p)"""
     common.check_kzg_opening(orc, lambda: Context(gpu_lib, 0, 0, 1), 3000, 2700)
+
+
+def test_async_msm(orc, gpu_lib):
+    """dp_msm_submit / dp_msm_collect (commitments queued behind transforms) == blocking dp_msm"""
+    n = 5000
+    bases = orc.gen_bases(5, n, 2048, True)
+    c = Context(gpu_lib, 0, 0, 1)
+    c.init(bases, 1 << 6, 1 << 9)
+    common.check_async_msm(orc, c, bases, n, 2800)
+    c.close()
+
+
+def test_host_schedules(orc, gpu_lib):
+    """serial and overlapped end-to-end schedules of bench.py (schedule.py) against the oracle, host buffers"""
+    bases = orc.gen_bases(5, 3000, 2048, True)
+    c = Context(gpu_lib, 0, 0, 1)
+    c.init(bases, 1 << 12, 1 << 15)
+    common.check_schedule(orc, c, bases, 12, 15, 2900)
+    c.close()

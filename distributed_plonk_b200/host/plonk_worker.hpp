@@ -8,6 +8,9 @@
 //                                     (worker.rs:125-439; methods of hello_world.capnp:15-52)
 //   dplonk::Prover::fft          <->  Prover::fft                  (dispatcher2.rs:731-787)
 //   dplonk::Prover::commit_polynomial <-> Prover::commit_polynomial (dispatcher2.rs:834-893)
+//   PlonkImpl::quotient_evals / evaluate / lin_comb / witness_poly  <->  the round 3-5 arithmetic of
+//                                     Prover::prove (dispatcher2.rs:363-690), i.e. the bodies of the
+//                                     round3*/round4*/round5* RPCs the schema declares
 //
 // `ListData` is the in-memory form of a capnp `List(Data)`: byte chunks cut at 2^28 bytes
 // (dispatcher.rs:61-63).  Where the reference `unwrap()`s (panics -> capnp error to the caller)
@@ -126,6 +129,79 @@ class PlonkImpl {
         check(dp_round1(ctx_, e.data(), e.size() / DP_FR_BYTES, blind_2fr, out.data()));
         return out;
     }
+    // varMsm answered from a Promise (the way fft2Prepare is, worker.rs:293): begin in the RPC body,
+    // end when the reply is built; other requests are served - and their kernels queued - in between
+    void var_msm_begin(uint64_t id, const MsmWorkload &w, const ListData &scalars) {
+        Bytes &s = pending_scalars_[id];   // the copy-in is asynchronous: keep the bytes until the job is collected
+        s = concat(scalars);
+        check(dp_msm_submit(ctx_, id, w.start, w.end, s.data(), s.size() / DP_FR_BYTES));
+    }
+    Bytes var_msm_end(uint64_t id) {
+        Bytes out(DP_G1_PROJECTIVE_BYTES);
+        int rc = dp_msm_collect(ctx_, id, out.data());
+        pending_scalars_.erase(id);
+        check(rc);
+        return out;
+    }
+    // init from the canonical encoding of the SRS (ark-serialize compressed G1, 48 B per point)
+    void init_compressed(const ListData &bases48, uint64_t domain_size, uint64_t quot_domain_size, bool check_subgroup = true) {
+        Bytes b = concat(bases48);
+        check(dp_init_compressed(ctx_, b.data(), b.size() / DP_G1_COMPRESSED_BYTES, domain_size, quot_domain_size, check_subgroup));
+        log_[0] = log2_ceil(domain_size);
+        log_[1] = log2_ceil(quot_domain_size);
+    }
+
+    // ---- the bodies of the declared-but-unimplemented round3* / round4* / round5* RPCs
+    // (hello_world.capnp:26-44); the arithmetic is the dispatcher's, src/dispatcher2.rs:363-690.
+    // Polynomials are raw Fr vectors (32 B per coefficient / evaluation).
+    // round 3: quotient evaluations over the quotient coset (434-504); every array quot_domain_size long
+    Bytes quotient_evals(const std::vector<Bytes> &selectors /*13*/, const std::vector<Bytes> &sigmas /*5*/,
+                         const std::vector<Bytes> &wires /*5*/, const Bytes &perm, const Bytes &pub_input, const Bytes &k /*5 Fr*/,
+                         const Bytes &alpha, const Bytes &beta, const Bytes &gamma) {
+        if (selectors.size() != 13 || sigmas.size() != 5 || wires.size() != 5) throw Error(DP_E_ARG, "quotient_evals: 13 selectors, 5 sigmas, 5 wires");
+        dp_quotient_args a;
+        for (int i = 0; i < 13; i++) a.selectors[i] = selectors[i].data();
+        for (int i = 0; i < 5; i++) {
+            a.sigmas[i] = sigmas[i].data();
+            a.wires[i] = wires[i].data();
+        }
+        a.perm = perm.data();
+        a.pub_input = pub_input.data();
+        a.k = k.data();
+        a.alpha = alpha.data();
+        a.beta = beta.data();
+        a.gamma = gamma.data();
+        Bytes out(perm.size());
+        check(dp_quotient_evals(ctx_, &a, out.data()));
+        return out;
+    }
+    // round 4: poly.evaluate(&point) (535-548)
+    Bytes evaluate(const Bytes &coeffs, const Bytes &point) {
+        Bytes out(DP_FR_BYTES);
+        check(dp_poly_eval(ctx_, coeffs.data(), coeffs.size() / DP_FR_BYTES, point.data(), out.data()));
+        return out;
+    }
+    // round 5: sum_i coeffs[i] * polys[i] (566-649)
+    Bytes lin_comb(const std::vector<Bytes> &polys, const Bytes &coeffs) {
+        std::vector<const void *> ptr;
+        std::vector<size_t> len;
+        size_t longest = 0;
+        for (const Bytes &p : polys) {
+            ptr.push_back(p.data());
+            len.push_back(p.size() / DP_FR_BYTES);
+            longest = len.back() > longest ? len.back() : longest;
+        }
+        Bytes out(longest * DP_FR_BYTES);
+        check(dp_poly_lincomb(ctx_, ptr.data(), len.data(), coeffs.data(), polys.size(), out.data(), longest));
+        return out;
+    }
+    // round 5: witness polynomial p(X) / (X - point) (651-666, 672-688)
+    Bytes witness_poly(const Bytes &coeffs, const Bytes &point) {
+        const size_t n = coeffs.size() / DP_FR_BYTES;
+        Bytes out(n ? (n - 1) * DP_FR_BYTES : 0);
+        check(dp_poly_div_linear(ctx_, coeffs.data(), n, point.data(), out.data(), nullptr));
+        return out;
+    }
     dp_ctx *raw() { return ctx_; }
     uint64_t me() const { return me_; }
 
@@ -143,6 +219,7 @@ class PlonkImpl {
     uint64_t me_, n_workers_;
     uint32_t log_[2] = {0, 0};
     std::map<uint64_t, Dims> dims_;
+    std::map<uint64_t, Bytes> pending_scalars_;
 };
 
 // The dispatcher's side of the path, against in-process workers instead of capnp connections.

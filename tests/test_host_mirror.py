@@ -33,11 +33,16 @@ def run_case(orc, exe, tmp_path, n_bases, log_n, log_q, flags, n_coeffs):
     subprocess.check_call([exe, str(req), str(rep)])
     raw = np.fromfile(rep, dtype=np.uint8)
     L = log_q if flags & 1 else log_n
-    part, out = raw[:144], raw[144:].view(np.uint64).reshape(1 << L, 4)
+    part, rest = raw[:144], raw[144:].view(np.uint64).reshape(-1, 4)
+    out, pz, q, lc = rest[:1 << L], rest[1 << L], rest[(1 << L) + 1:(1 << L) + n_coeffs], rest[(1 << L) + n_coeffs:]
     assert np.array_equal(orc.normalize(part), orc.normalize(orc.msm(bases, sc)))
     pad = np.zeros((1 << L, 4), dtype=np.uint64)
     pad[:n_coeffs] = co
     assert np.array_equal(out, orc.fft(pad, bool(flags & 2), bool(flags & 4)))
+    # rounds 4-5 through the C++ mirror: p(z), p / (X - z), z p + z p[:n/2]   (z = p[0])
+    assert np.array_equal(pz, orc.poly_eval(co, co[0]))
+    assert np.array_equal(q, orc.poly_div_linear(co, co[0]))
+    assert np.array_equal(lc, orc.poly_lincomb([co, co[:n_coeffs // 2]], np.stack([co[0], co[0]])))
 
 
 def test_cpp_host_mirror_on_emulator(orc, tmp_path):

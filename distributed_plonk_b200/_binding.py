@@ -16,7 +16,7 @@ EXPORTS = [
     "dp_last_msm_breakdown", "dp_debug_gen_bases", "dp_fft_dev_rows", "dp_fft_dev_cols", "dp_peer_ready", "dp_fft_dev_rows_p2p", "dp_fft_dev_p2p", "dp_msm_dev_batch", "dp_perm_product", "dp_msm_batch", "dp_perm_product_dev",
     "dp_quotient_evals", "dp_quotient_evals_dev", "dp_poly_eval", "dp_poly_eval_dev", "dp_poly_lincomb", "dp_poly_lincomb_dev",
     "dp_poly_div_linear", "dp_poly_div_linear_dev", "dp_init_compressed", "dp_get_bases",
-    "dp_msm_submit", "dp_msm_collect",
+    "dp_msm_submit", "dp_msm_collect", "dp_poly_put", "dp_poly_ptr", "dp_poly_get", "dp_poly_free", "dp_commit_dev",
 ]
 
 
@@ -77,6 +77,11 @@ def bind(cdll: C.CDLL) -> C.CDLL:
         "dp_msm_dev_batch": (i, [vp, sz, C.POINTER(u64), C.POINTER(u64), C.POINTER(vp), C.POINTER(sz), C.POINTER(vp)]),
         "dp_fft_dev_rows_p2p": (i, [vp, vp, i, i, i]),
         "dp_fft_dev_p2p": (i, [vp, vp, vp, i, i, i]),
+        "dp_poly_put": (i, [vp, u64, vp, sz, sz]),
+        "dp_poly_ptr": (i, [vp, u64, C.POINTER(vp), C.POINTER(sz)]),
+        "dp_poly_get": (i, [vp, u64, sz, sz, vp]),
+        "dp_poly_free": (i, [vp, u64]),
+        "dp_commit_dev": (i, [vp, vp, sz, vp]),
         "dp_msm_submit": (i, [vp, u64, u64, u64, vp, sz]),
         "dp_msm_collect": (i, [vp, u64, vp]),
         "dp_init_compressed": (i, [vp, vp, sz, u64, u64, i]),
@@ -208,6 +213,33 @@ class Context:
     def perm_product_dev(self, wires_ptr: int, id_ptr: int, sigma_ptr: int, n_types: int, n: int, beta: np.ndarray, gamma: np.ndarray, out_ptr: int):
         b, g = np.ascontiguousarray(beta, dtype=np.uint64), np.ascontiguousarray(gamma, dtype=np.uint64)
         self._ck(self.lib.dp_perm_product_dev(self.h, wires_ptr, id_ptr, sigma_ptr, n_types, n, _addr(b), _addr(g), out_ptr))
+
+    # ---- worker-resident polynomials
+    def poly_put(self, poly_id: int, coeffs: np.ndarray, capacity: int = 0) -> int:
+        """store [n,4] raw Fr under poly_id (zero-extended to `capacity`); returns the device address"""
+        a = np.ascontiguousarray(coeffs, dtype=np.uint64)
+        self._ck(self.lib.dp_poly_put(self.h, poly_id, _addr(a) if a.size else None, a.size // 4, capacity))
+        return self.poly_ptr(poly_id)[0]
+
+    def poly_ptr(self, poly_id: int):
+        d, cap = C.c_void_p(), C.c_size_t()
+        self._ck(self.lib.dp_poly_ptr(self.h, poly_id, C.byref(d), C.byref(cap)))
+        return d.value, cap.value
+
+    def poly_get(self, poly_id: int, n: int | None = None, offset: int = 0) -> np.ndarray:
+        if n is None:
+            n = self.poly_ptr(poly_id)[1] - offset
+        out = np.empty((n, 4), dtype=np.uint64)
+        self._ck(self.lib.dp_poly_get(self.h, poly_id, offset, n, _addr(out) if n else None))
+        return out
+
+    def poly_free(self, poly_id: int):
+        self._ck(self.lib.dp_poly_free(self.h, poly_id))
+
+    def commit_dev(self, coeffs_ptr: int, n: int) -> np.ndarray:
+        out = np.zeros(G1_PROJECTIVE_BYTES, dtype=np.uint8)
+        self._ck(self.lib.dp_commit_dev(self.h, coeffs_ptr, n, _addr(out)))
+        return out
 
     def msm_submit(self, job_id: int, start: int, end: int, scalars, n: int | None = None):
         """asynchronous varMsm: scalars = [n,4] host array (kept alive by the caller) or a host pointer + n"""

@@ -154,6 +154,12 @@ struct dp_ctx {
     Fr *peer_arena[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     uint64_t p2p_seq = 0;           // exchanges issued so far; must advance identically on every rank
     uint32_t bar_seq = 0;           // device-side barriers issued so far (p2p_barrier_kernel)
+    // worker-resident polynomials (dp_poly_*): id -> device buffer of `cap` Fr, zero beyond what was written
+    struct Poly {
+        Fr *dev = nullptr;
+        size_t cap = 0;
+    };
+    std::map<uint64_t, Poly> polys;
     // MSMs submitted with dp_msm_submit and not collected yet (keyed by the caller's id)
     std::map<uint64_t, MsmPending *> msm_pending;
     uint8_t *msm_pinned = nullptr;  // MSM_SLOTS x MSM_SLOT_BYTES of pinned host memory: result + error flag per job
@@ -1999,6 +2005,75 @@ int dp_poly_lincomb(dp_ctx *ctx, const void *const *polys, const size_t *lens, c
 }
 int dp_poly_lincomb_dev(dp_ctx *ctx, const void *const *polys_dev, const size_t *lens, const void *coeffs, size_t k, void *out_dev, size_t out_len) {
     return poly_lincomb_any(ctx, polys_dev, lens, coeffs, k, out_dev, out_len, true, "dp_poly_lincomb_dev");
+}
+
+// ------------------------------------------------------------------ worker-resident polynomials
+// What `state.wire` is in the reference (worker.rs:58,400-405), generalised: named device buffers
+// that the *_dev entries of rounds 2-5, dp_ntt_dev and dp_commit_dev work on, so that a polynomial
+// crosses PCIe once (or never).  All copies and kernels touching them run on the compute stream.
+int dp_poly_put(dp_ctx *ctx, uint64_t poly_id, const void *coeffs, size_t n, size_t capacity) {
+    if (!ctx || (n && !coeffs)) return fail(ctx, DP_E_ARG, "dp_poly_put: NULL argument");
+    if (capacity < n) capacity = n;
+    if (capacity == 0) return fail(ctx, DP_E_ARG, "dp_poly_put: empty polynomial");
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    dp_ctx::Poly &p = ctx->polys[poly_id];
+    if (p.cap != capacity) {  // (re)allocate; stream-ordered pool: earlier kernels on the old buffer are ordered before its reuse
+        ctx->pool.release(p.dev);
+        p.dev = (Fr *)ctx->pool.alloc(capacity * sizeof(Fr));
+        p.cap = p.dev ? capacity : 0;
+        if (!p.dev) {
+            ctx->polys.erase(poly_id);
+            return fail(ctx, DP_E_OOM, "dp_poly_put: %zu coefficients", capacity);
+        }
+    }
+    if (n) DP_CUDA(ctx, cudaMemcpyAsync(p.dev, coeffs, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    if (capacity > n) DP_CUDA(ctx, cudaMemsetAsync(p.dev + n, 0, (capacity - n) * sizeof(Fr), ctx->stream));
+    DP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `coeffs` is the caller's again
+    return DP_OK;
+}
+
+int dp_poly_ptr(dp_ctx *ctx, uint64_t poly_id, void **dev, size_t *capacity) {
+    if (!ctx) return DP_E_ARG;
+    auto it = ctx->polys.find(poly_id);
+    if (it == ctx->polys.end()) return fail(ctx, DP_E_ARG, "dp_poly_ptr: unknown polynomial %llu", (unsigned long long)poly_id);
+    if (dev) *dev = it->second.dev;
+    if (capacity) *capacity = it->second.cap;
+    return DP_OK;
+}
+
+int dp_poly_get(dp_ctx *ctx, uint64_t poly_id, size_t offset, size_t n, void *out) {
+    if (!ctx || (n && !out)) return fail(ctx, DP_E_ARG, "dp_poly_get: NULL argument");
+    auto it = ctx->polys.find(poly_id);
+    if (it == ctx->polys.end()) return fail(ctx, DP_E_ARG, "dp_poly_get: unknown polynomial %llu", (unsigned long long)poly_id);
+    if (offset > it->second.cap || n > it->second.cap - offset) return fail(ctx, DP_E_ARG, "dp_poly_get: [%zu, +%zu) outside %zu coefficients", offset, n, it->second.cap);
+    if (n == 0) return DP_OK;
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    DP_CUDA(ctx, cudaMemcpyAsync(out, it->second.dev + offset, n * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    DP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DP_OK;
+}
+
+int dp_poly_free(dp_ctx *ctx, uint64_t poly_id) {
+    if (!ctx) return DP_E_ARG;
+    auto it = ctx->polys.find(poly_id);
+    if (it == ctx->polys.end()) return fail(ctx, DP_E_ARG, "dp_poly_free: unknown polynomial %llu", (unsigned long long)poly_id);
+    ctx->pool.release(it->second.dev);
+    ctx->polys.erase(it);
+    return DP_OK;
+}
+
+// commit_polynomial (worker.rs:117-123) of coefficients that already live on the device
+int dp_commit_dev(dp_ctx *ctx, const void *coeffs_dev, size_t n, void *out144) {
+    if (!ctx || !out144 || (n && !coeffs_dev)) return fail(ctx, DP_E_ARG, "dp_commit_dev: NULL argument");
+    if (!ctx->inited) return fail(ctx, DP_E_STATE, "dp_commit_dev before dp_init");
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    call_begin(ctx);
+    Scratch tmp(ctx->pool);
+    G1JacobianOut *od = tmp.get<G1JacobianOut>(1);
+    if (!od) return fail(ctx, DP_E_OOM, "dp_commit_dev buffers");
+    DP_TRY(commit_device(ctx, (const Fr *)coeffs_dev, n, od));
+    DP_CUDA(ctx, cudaMemcpyAsync(out144, od, sizeof(G1JacobianOut), cudaMemcpyDeviceToHost, ctx->stream));
+    return call_end(ctx, true);
 }
 
 }  // extern "C"

@@ -207,6 +207,21 @@ int dp_poly_lincomb_dev(dp_ctx *ctx, const void *const *polys_dev, const size_t 
 int dp_poly_div_linear(dp_ctx *ctx, const void *coeffs, size_t n, const void *point, void *out, void *rem32);
 int dp_poly_div_linear_dev(dp_ctx *ctx, const void *coeffs_dev, size_t n, const void *point, void *out_dev, void *rem32);
 
+/* ---- worker-resident polynomials ---------------------------------------------------------------
+ * `state.wire` of the reference (src/worker.rs:58,400-405) generalised: named device buffers the
+ * *_dev entries above, dp_ntt_dev, dp_perm_product_dev and dp_commit_dev work on, so a polynomial
+ * crosses PCIe once (or never: outputs of one step are inputs of the next).  A Rust worker has no
+ * device allocator of its own; this is it.                                                          */
+/* create / overwrite polynomial `poly_id`: `capacity` Fr on the device (>= n; e.g. the quotient domain
+ * size for a polynomial that will be transformed in place), coefficients [0, n) copied from the host,
+ * the rest zero.  Re-putting with the same capacity reuses the buffer.                              */
+int dp_poly_put(dp_ctx *ctx, uint64_t poly_id, const void *coeffs, size_t n, size_t capacity);
+int dp_poly_ptr(dp_ctx *ctx, uint64_t poly_id, void **dev, size_t *capacity); /* the device address         */
+int dp_poly_get(dp_ctx *ctx, uint64_t poly_id, size_t offset, size_t n, void *out);    /* copy back        */
+int dp_poly_free(dp_ctx *ctx, uint64_t poly_id);
+/* commit_polynomial (src/worker.rs:117-123) of n coefficients already on the device -> 144 B        */
+int dp_commit_dev(dp_ctx *ctx, const void *coeffs_dev, size_t n, void *out144);
+
 /* ---- peer transport for n_workers > 1 ---------------------------------------------------------
  * Exchange arena shared between the GPUs of one box through CUDA IPC: every rank exports a
  * handle, the ranks swap them out of band (torch.distributed / the capnp control plane) and attach

@@ -200,13 +200,11 @@ def _fr_neg_one(orc):
     return out
 
 
-def check_satisfied_circuit(orc, ctx: Context, log_n: int, seed: int):
-    """Size-independent property of rounds 2-3 (what the reference gets from its verifier, test_plonk):
-    for a witness that satisfies every gate and every copy constraint the quotient evaluations
-    interpolate to a polynomial of degree <= 5(n+1)+2, i.e. the division by Z_H is exact; with ONE
-    wire value corrupted it is not.  The instance is built with the oracle's elementwise vector ops;
-    perm product, iNTT, coset NTT, quotient kernel and coset iNTT all run through the library."""
-    n, m, log_m = 1 << log_n, 8 << log_n, log_n + 3
+def make_satisfied_instance(orc, ctx: Context, log_n: int, seed: int):
+    """A random TurboPlonk instance (GATE_WIDTH 4, five wire types) whose gates and copy constraints
+    hold, as evaluations over H: wires w[5], selectors sel[13], public input, identity / sigma
+    permutation values, challenges, and the round-2 product z (computed by the library)."""
+    n = 1 << log_n
     one = _fr_one(orc)
     V = orc.vec_op
     w = [orc.gen_fr(seed + i, n) for i in range(4)]
@@ -238,6 +236,19 @@ def check_satisfied_circuit(orc, ctx: Context, log_n: int, seed: int):
         sigma[i1][j1], sigma[i2][j2] = sigma[i2][j2].copy(), sigma[i1][j1].copy()
     beta, gamma, alpha = (orc.gen_fr(seed + 50 + i, 1)[0] for i in range(3))
     z = ctx.perm_product(np.stack(w), np.stack(ident), np.stack(sigma), beta, gamma)
+    return dict(n=n, w=w, sel=sel, pub=pub, k=k, ident=ident, sigma=sigma, beta=beta, gamma=gamma, alpha=alpha, z=z)
+
+
+def check_satisfied_circuit(orc, ctx: Context, log_n: int, seed: int):
+    """Size-independent property of rounds 2-3 (what the reference gets from its verifier, test_plonk):
+    for a witness that satisfies every gate and every copy constraint the quotient evaluations
+    interpolate to a polynomial of degree <= 5(n+1)+2, i.e. the division by Z_H is exact; with ONE
+    wire value corrupted it is not.  The instance is built with the oracle's elementwise vector ops;
+    perm product, iNTT, coset NTT, quotient kernel and coset iNTT all run through the library."""
+    n, log_m = 1 << log_n, log_n + 3
+    c = make_satisfied_instance(orc, ctx, log_n, seed)
+    w, sel, sigma, z, pub, k = c["w"], c["sel"], c["sigma"], c["z"], c["pub"], c["k"]
+    alpha, beta, gamma = c["alpha"], c["beta"], c["gamma"]
 
     def to_coset(evals):                                       # dispatcher2.rs:381-432
         return ctx.ntt(ctx.ntt(evals, log_n, True, False), log_m, False, True)
@@ -255,6 +266,69 @@ def check_satisfied_circuit(orc, ctx: Context, log_n: int, seed: int):
     bad = [v.copy() for v in w]
     bad[1][n // 3] = orc.gen_fr(seed + 60, 1)[0]
     assert degree(bad) > 7 * n
+
+
+def check_resident_rounds(orc, ctx: Context, bases, log_n: int, seed: int):
+    """Rounds 2-5 with every polynomial RESIDENT on the worker (dp_poly_* store + the *_dev entries +
+    dp_ntt_dev + dp_commit_dev): each polynomial crosses PCIe once on the way in; only commitments,
+    evaluations and the final witness commitments come back.  Checked against the host-buffer entries /
+    the oracle at every step, and by the protocol's own invariants (exact division, opening identity)."""
+    n, m, log_m = 1 << log_n, 8 << log_n, log_n + 3
+    c = make_satisfied_instance(orc, ctx, log_n, seed)
+    alpha, beta, gamma, k = c["alpha"], c["beta"], c["gamma"], c["k"]
+    ids = {}
+
+    def put(name, evals):
+        ids[name] = len(ids) + 100
+        return ctx.poly_put(ids[name], evals, m)
+
+    # round 1-2: evaluations over H in, coefficient form by an in-place iNTT of the first n entries
+    names = [f"sel{i}" for i in range(13)] + [f"sig{i}" for i in range(5)] + [f"w{i}" for i in range(5)] + ["z", "pub"]
+    evals = c["sel"] + c["sigma"] + c["w"] + [c["z"], c["pub"]]
+    ptr = {}
+    for name, ev in zip(names, evals):
+        ptr[name] = put(name, ev)
+        ctx.ntt_dev(ptr[name], log_n, True, False)
+    coeff = {name: ctx.poly_get(ids[name], n) for name in ("w0", "w4", "z", "sig1")}
+    assert np.array_equal(coeff["w0"], orc.fft(c["w"][0], True, False))
+    assert not ctx.poly_get(ids["w0"], m - n, n).any(), "zero padding of a resident polynomial"
+    com_w0 = ctx.commit_dev(ptr["w0"], n)                                     # wire commitment from device memory
+    assert_point_eq(orc, com_w0, orc.commit(bases, coeff["w0"]), "commit_dev")
+    # round 4 evaluations before the buffers are transformed in place
+    zeta = orc.gen_fr(seed + 70, 1)[0]
+    ev_w4 = ctx.poly_eval(ptr["w4"], zeta, n)
+    assert np.array_equal(ev_w4, orc.poly_eval(coeff["w4"], zeta))
+    # round 5 witness of z at zeta, straight into another resident polynomial, then committed
+    wit = ctx.poly_put(999, np.zeros((1, 4), dtype=np.uint64), n)
+    _, rem = ctx.poly_div_linear(ptr["z"], zeta, n, wit)
+    assert np.array_equal(rem, orc.poly_eval(coeff["z"], zeta))
+    assert np.array_equal(ctx.poly_get(999, n - 1), orc.poly_div_linear(coeff["z"], zeta))
+    assert_point_eq(orc, ctx.commit_dev(wit, n - 1), orc.commit(bases, orc.poly_div_linear(coeff["z"], zeta)), "witness commitment")
+    # round 3: coset evaluations in place, quotient kernel, coset iNTT in place, split commitments
+    for name in names:
+        ctx.ntt_dev(ptr[name], log_m, False, True)
+    q_ptr = ctx.poly_put(998, np.zeros((1, 4), dtype=np.uint64), m)
+    ctx.quotient_evals_dev([ptr[f"sel{i}"] for i in range(13)], [ptr[f"sig{i}"] for i in range(5)], [ptr[f"w{i}"] for i in range(5)],
+                           ptr["z"], ptr["pub"], k, alpha, beta, gamma, q_ptr)
+    host_q = ctx.quotient_evals([ctx.poly_get(ids[f"sel{i}"]) for i in range(13)], [ctx.poly_get(ids[f"sig{i}"]) for i in range(5)],
+                                [ctx.poly_get(ids[f"w{i}"]) for i in range(5)], ctx.poly_get(ids["z"]), ctx.poly_get(ids["pub"]),
+                                k, alpha, beta, gamma)
+    assert np.array_equal(ctx.poly_get(998), host_q), "resident quotient == host-buffer quotient"
+    ctx.ntt_dev(q_ptr, log_m, True, True)
+    quot = ctx.poly_get(998)
+    nz = np.nonzero(quot.any(axis=1))[0]
+    assert 4 * n <= int(nz[-1]) <= 5 * (n + 1) + 2, "exact division by Z_H"
+    for j in range(0, int(nz[-1]) + 1, n + 2):                                # split_quot_polys (dispatcher2.rs:509-524)
+        ln = min(n + 2, m - j)
+        if n + 2 <= bases.shape[0]:
+            assert_point_eq(orc, ctx.commit_dev(q_ptr + 32 * j, ln), orc.commit(bases, quot[j:j + ln]), f"split quotient commitment at {j}")
+    for pid in list(ids.values()) + [998, 999]:
+        ctx.poly_free(pid)
+    try:
+        ctx.poly_ptr(998)
+        raise AssertionError("freed polynomial still known")
+    except DpError as e:
+        assert e.code == -1
 
 
 GOLDEN_ROUNDS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_rounds_v1.npz")

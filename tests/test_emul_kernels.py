@@ -222,6 +222,14 @@ def test_async_msm(orc, emul_lib):
     c.close()
 
 
+def test_resident_rounds(orc, emul_lib):
+    bases = orc.gen_bases(5, 80, 64, True)
+    c = Context(emul_lib, 0, 0, 1)
+    c.init(bases, 1 << 6, 1 << 9)
+    common.check_resident_rounds(orc, c, bases, 6, 1800)
+    c.close()
+
+
 def test_host_schedules(orc, emul_lib):
     bases = orc.gen_bases(5, 200, 64, True)
     c = Context(emul_lib, 0, 0, 1)

@@ -140,3 +140,13 @@ def test_host_schedules(orc, gpu_lib):
     c.init(bases, 1 << 12, 1 << 15)
     common.check_schedule(orc, c, bases, 12, 15, 2900)
     c.close()
+
+
+@pytest.mark.parametrize("log_n", [6, 12])
+def test_resident_rounds(orc, gpu_lib, log_n):
+    """rounds 2-5 on worker-resident polynomials (dp_poly_* + *_dev entries + dp_ntt_dev + dp_commit_dev)"""
+    bases = orc.gen_bases(5, (1 << log_n) + 32, 2048, True)
+    c = Context(gpu_lib, 0, 0, 1)
+    c.init(bases, 1 << log_n, 8 << log_n)
+    common.check_resident_rounds(orc, c, bases, log_n, 3000 + log_n)
+    c.close()

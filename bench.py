@@ -385,55 +385,25 @@ def main():
         com = schedule.Commitment(lo, hi, h_scal.data_ptr(), hi - lo)
         host_of = {h_out_n.data_ptr(): h_out_n, h_out_m.data_ptr(): h_out_m}
 
-        def observers(check):
-            if check is None:
-                return None, None
-            return (lambda t: check["fft"].append(int(host_of[t.out_ptr].sum()))), (lambda o: check["msm"].append(o.tobytes()))
+        # Two host schedules over the same work (distributed_plonk_b200/schedule.py).  serial: the
+        # commitments of each prover round as one batch, then the transforms with two tasks of look-ahead
+        # (the dispatcher issues its FFT tasks concurrently, dispatcher2.rs:294-306, 382-414).
+        # overlapped: the transforms are bound by PCIe (1 GiB in and out per 10 ms of kernels), the
+        # commitments by the multiplier (24 ms of kernels per 128 MiB in), so a commitment is queued
+        # (dp_msm_submit) after every second transform and fills the compute stream while the copy
+        # engines work on the transforms around it; across a stream of proofs this is round 1-2 of
+        # proof k+1 under round 3 of proof k.  The overlapped schedule is timed only if it first
+        # reproduces the serial one bit for bit on this box and is not slower in a one-step trial.
+        def all_agree(ok):
+            if W == 1:
+                return ok
+            flag = torch.tensor([1 if ok else 0], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            return bool(flag.item())
 
-        def step_e2e_serial(check=None):
-            # the dispatcher issues its FFT tasks concurrently (join_all, dispatcher2.rs:294-306,
-            # 382-414: up to 25 in flight); two tasks of look-ahead keep the copy-in stream, the
-            # kernels and the copy-out stream busy at the same time (PCIe is full duplex)
-            on_fft, on_msm = observers(check)
-            runner.run_serial(jobs, com, ROUNDS, 2, on_fft, on_msm)
-
-        # Overlapped schedule: the transforms are bound by PCIe (1 GiB in and out per 10 ms of kernels),
-        # the commitments by the multiplier (24 ms of kernels per 128 MiB in), so a commitment is
-        # queued (dp_msm_submit) after every second transform and fills the compute stream while
-        # the copy engines work on the transforms around it.  Same work per step as the serial
-        # schedule; across a stream of proofs this is round 1-2 of proof k+1 under round 3 of proof k.
-        def step_e2e_overlap(check=None):
-            on_fft, on_msm = observers(check)
-            runner.run_overlapped(jobs, com, N_MSM, 4, on_fft, on_msm)
-
-        # the overlapped schedule must reproduce the serial one bit for bit (every commitment, a
-        # checksum of every transform's output) on this box before it is timed; otherwise the serial
-        # schedule is timed and the reason is reported
-        e2e_mode, step_e2e = "serial", step_e2e_serial
-        if os.environ.get("DP_BENCH_E2E_SERIAL", "0") != "1":
-            same, why = False, "gave different results"
-            try:
-                ref, got = {"msm": [], "fft": []}, {"msm": [], "fft": []}
-                step_e2e_serial(ref)
-                step_e2e_overlap(got)
-                same = sorted(ref["msm"]) == sorted(got["msm"]) and ref["fft"] == got["fft"] and len(got["msm"]) == N_MSM
-            except Exception as exc:
-                why = f"failed: {str(exc)[:120]}"
-                ctx.sync()
-            if W > 1:   # every rank takes the same decision
-                flag = torch.tensor([1 if same else 0], device="cuda")
-                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-                same = bool(flag.item())
-            if same:
-                # both schedules are valid: time one step of each and keep the faster
-                t_ser, _ = timed(step_e2e_serial, 1, 0)
-                t_ovl, _ = timed(step_e2e_overlap, 1, 0)
-                if t_ovl <= t_ser:
-                    e2e_mode, step_e2e = "overlapped (commitments queued between transforms; verified against the serial schedule)", step_e2e_overlap
-                else:
-                    e2e_mode = f"serial (overlapped schedule verified but slower in a one-step trial: {t_ovl * 1e3:.0f} vs {t_ser * 1e3:.0f} ms)"
-            else:
-                e2e_mode = f"serial (overlapped schedule {why}: disabled)"
+        step_e2e, e2e_mode = schedule.pick_schedule(
+            runner, jobs, com, ROUNDS, checksum=lambda t: int(host_of[t.out_ptr].sum()), timed=lambda f: timed(f, 1, 0)[0],
+            all_agree=all_agree, allow_overlap=os.environ.get("DP_BENCH_E2E_SERIAL", "0") != "1")
 
         e_steps = max(1, min(args.steps, 2))
         dt_e, _ = timed(step_e2e, e_steps, 1)

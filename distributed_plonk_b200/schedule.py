@@ -119,3 +119,45 @@ class Runner:
                 finish(pending.pop(0))
         while pending:
             finish(pending.pop(0))
+
+
+def pick_schedule(runner: Runner, transforms: Sequence[Transform], commitment: Commitment, rounds: Sequence[int],
+                  checksum: Callable, timed: Callable, all_agree: Callable = lambda ok: ok, allow_overlap: bool = True):
+    """Decide which schedule the end-to-end measurement times.  The overlapped schedule is used only if,
+    on this machine, it reproduces the serial one bit for bit - every commitment and `checksum(t)` of every
+    transform's output, in order - and is not slower in a one-step trial.
+      checksum(transform) -> hashable digest of the transform's host output buffer
+      timed(step) -> seconds for one call of step() (the caller's clock, max over ranks)
+      all_agree(ok) -> ok on every rank (identity for one worker)
+    Returns (step, description): step() runs one pass of the chosen schedule."""
+    n_msm = sum(rounds)
+
+    def serial(check=None):
+        runner.run_serial(transforms, commitment, rounds, 2, *_observers(check, checksum))
+
+    def overlapped(check=None):
+        runner.run_overlapped(transforms, commitment, n_msm, 4, *_observers(check, checksum))
+
+    if not allow_overlap:
+        return serial, "serial"
+    same, why = False, "gave different results"
+    try:
+        ref, got = {"msm": [], "fft": []}, {"msm": [], "fft": []}
+        serial(ref)
+        overlapped(got)
+        same = sorted(ref["msm"]) == sorted(got["msm"]) and ref["fft"] == got["fft"] and len(got["msm"]) == n_msm
+    except Exception as exc:   # the serial schedule stays available whatever happened to the other one
+        why = f"failed: {str(exc)[:120]}"
+        runner.ctx.sync()
+    if not all_agree(same):
+        return serial, f"serial (overlapped schedule {why}: disabled)"
+    t_ser, t_ovl = timed(serial), timed(overlapped)
+    if t_ovl <= t_ser:
+        return overlapped, "overlapped (commitments queued between transforms; verified against the serial schedule)"
+    return serial, f"serial (overlapped schedule verified but slower in a one-step trial: {t_ovl * 1e3:.0f} vs {t_ser * 1e3:.0f} ms)"
+
+
+def _observers(check, checksum):
+    if check is None:
+        return None, None
+    return (lambda t: check["fft"].append(checksum(t))), (lambda o: check["msm"].append(o.tobytes()))

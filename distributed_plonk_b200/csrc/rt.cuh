@@ -4,7 +4,7 @@
 #if defined(DP_EMUL)
 #include "../../tests/emul/cuda_emul.h"
 #define DP_LAUNCH(kernel, grid, block, smem, stream, ...) \
-    dp_emul::launch(grid, block, smem, [&] { kernel(__VA_ARGS__); })
+    dp_emul::launch_on(stream, grid, block, smem, [=] { kernel(__VA_ARGS__); })
 #define DP_DYN_SMEM(name) unsigned char *name = dp_emul::t_dyn_smem
 #else
 #if !defined(__CUDACC__)

@@ -26,7 +26,9 @@ def emul_lib():
     """CPU kernel-logic emulator build of the library (tests/emul; NOT a product backend)"""
     from tests.emul import build as emul_build
     from distributed_plonk_b200._binding import bind
-    return bind(ctypes.CDLL(emul_build.build()))
+    # DP_TEST_EMUL_ASYNC=1 runs every emulator test on the asynchronous-stream build (streams are threads,
+    # random delays): slower, used to hunt missing stream / event dependencies
+    return bind(ctypes.CDLL(emul_build.build(async_streams=os.environ.get("DP_TEST_EMUL_ASYNC", "0") == "1")))
 
 
 @pytest.fixture(scope="session")

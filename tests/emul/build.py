@@ -11,20 +11,28 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 SRC = os.path.join(ROOT, "distributed_plonk_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libdplonk_emul.so")
+OUT_ASYNC = os.path.join(HERE, "_build", "libdplonk_emul_async.so")
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
 
-def build(force=False):
+def build(force=False, async_streams=False):
+    """async_streams: streams are worker threads, events are real, operations get random delays
+    (cuda_emul.h, DP_EMUL_ASYNC) - catches missing stream / event dependencies on a CPU"""
+    out = OUT_ASYNC if async_streams else OUT
+    return _build(out, ["-DDP_EMUL_ASYNC"] if async_streams else [], force)
+
+
+def _build(OUT, extra, force):
     deps = [os.path.join(SRC, f) for f in os.listdir(SRC)] + [os.path.join(HERE, "cuda_emul.h"),
                                                              os.path.join(ROOT, "include", "dplonk.h")]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = [CXX, "-O2", "-g", "-std=c++20", "-fPIC", "-shared", "-pthread", "-DDP_EMUL", "-Wall", "-Wno-unknown-pragmas",
+    cmd = [CXX, "-O2", "-g", "-std=c++20", "-fPIC", "-shared", "-pthread", "-DDP_EMUL", *extra, "-Wall", "-Wno-unknown-pragmas",
            "-x", "c++", os.path.join(SRC, "dplonk.cu"), "-o", OUT]
     subprocess.check_call(cmd)
     return OUT
 
 
 if __name__ == "__main__":
-    print(build(force="-f" in sys.argv))
+    print(build(force="-f" in sys.argv, async_streams="--async" in sys.argv))

@@ -168,12 +168,136 @@ template <class T> inline T __ldg(const T *p) { return *p; }
 // ------------------------------------------------------------------ runtime API subset
 typedef int cudaError_t;
 typedef struct dp_emul_stream *cudaStream_t;
-typedef struct dp_emul_event { std::chrono::steady_clock::time_point t; } *cudaEvent_t;
+typedef struct dp_emul_event *cudaEvent_t;
 enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
 enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocDefault = 0 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 struct cudaDeviceProp { int multiProcessorCount; size_t totalGlobalMem; char name[256]; int major, minor; };
+
+#if defined(DP_EMUL_ASYNC)
+// ---- asynchronous streams (tests/emul/build.py --async): every stream is a worker thread with a FIFO
+// of closures, events carry record / completion generations, kernels of all streams run one at a time
+// (static __shared__ storage) but in whatever order the streams' dependencies allow, with a random delay
+// before every operation.  A missing cudaStreamWaitEvent / synchronize in the library shows up as a wrong
+// result here instead of only under unlucky timing on a GPU.  Pageable-memory semantics: the source of a
+// host-to-device copy is captured when the copy is issued; device-to-host copies land when the stream
+// gets there.
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <random>
+#include <set>
+namespace dp_emul {
+inline std::mutex g_device;                 // one kernel at a time
+inline std::mutex g_registry;
+inline std::set<dp_emul_stream *> g_streams;
+inline unsigned jitter_us() {
+    static const unsigned v = [] {
+        const char *e = getenv("DP_EMUL_JITTER_US");
+        return e ? (unsigned)atoi(e) : 200u;
+    }();
+    return v;
+}
+// adversarial schedule: DP_EMUL_SLOW="i:us" delays every operation of the streams whose creation index is
+// i mod 4 by `us` microseconds (a context creates compute, copy-in, copy-out, tail in that order), so an
+// operation that should have waited for that stream and does not is practically certain to run too early
+inline std::atomic<unsigned> g_stream_counter{0};
+inline unsigned slow_us(unsigned index) {
+    static const std::pair<int, unsigned> cfg = [] {
+        const char *e = getenv("DP_EMUL_SLOW");
+        int i = -1;
+        unsigned us = 0;
+        if (e && sscanf(e, "%d:%u", &i, &us) != 2) i = -1;
+        return std::make_pair(i, us);
+    }();
+    return cfg.first >= 0 && (int)(index % 4) == cfg.first ? cfg.second : 0u;
+}
+}  // namespace dp_emul
+struct dp_emul_stream {
+    std::mutex m;
+    std::condition_variable cv;
+    std::deque<std::function<void()>> q;
+    uint64_t enq = 0, done = 0;
+    bool stop = false;
+    unsigned index = dp_emul::g_stream_counter++;
+    std::thread worker;
+    dp_emul_stream() : worker([this] { run(); }) {}
+    void run() {
+        std::minstd_rand rng((unsigned)(uintptr_t)this);
+        for (;;) {
+            std::function<void()> f;
+            {
+                std::unique_lock<std::mutex> l(m);
+                cv.wait(l, [&] { return stop || !q.empty(); });
+                if (q.empty()) return;
+                f = std::move(q.front());
+                q.pop_front();
+            }
+            if (dp_emul::jitter_us()) std::this_thread::sleep_for(std::chrono::microseconds(rng() % dp_emul::jitter_us()));
+            if (dp_emul::slow_us(index)) std::this_thread::sleep_for(std::chrono::microseconds(dp_emul::slow_us(index)));
+            f();
+            {
+                std::lock_guard<std::mutex> l(m);
+                done++;
+            }
+            cv.notify_all();
+        }
+    }
+    void push(std::function<void()> f) {
+        {
+            std::lock_guard<std::mutex> l(m);
+            q.push_back(std::move(f));
+            enq++;
+        }
+        cv.notify_all();
+    }
+    void sync() {
+        std::unique_lock<std::mutex> l(m);
+        cv.wait(l, [&] { return done == enq; });
+    }
+    ~dp_emul_stream() {
+        {
+            std::lock_guard<std::mutex> l(m);
+            stop = true;
+        }
+        cv.notify_all();
+        worker.join();
+    }
+};
+struct dp_emul_event_state {
+    std::mutex m;
+    std::condition_variable cv;
+    uint64_t recorded = 0, completed = 0;
+    std::chrono::steady_clock::time_point t;
+};
+struct dp_emul_event { std::shared_ptr<dp_emul_event_state> st = std::make_shared<dp_emul_event_state>(); };
+namespace dp_emul {
+inline void run_on(cudaStream_t s, std::function<void()> f) {
+    if (s) s->push(std::move(f));
+    else f();
+}
+inline void sync_all() {
+    std::vector<dp_emul_stream *> all;
+    {
+        std::lock_guard<std::mutex> l(g_registry);
+        all.assign(g_streams.begin(), g_streams.end());
+    }
+    for (dp_emul_stream *s : all) s->sync();
+}
+inline void launch_on(cudaStream_t s, dim3 grid, dim3 block, size_t smem, std::function<void()> body) {
+    run_on(s, [=] {
+        std::lock_guard<std::mutex> g(g_device);
+        launch(grid, block, smem, body);
+    });
+}
+}  // namespace dp_emul
+#else
+struct dp_emul_event { std::chrono::steady_clock::time_point t; };
+namespace dp_emul {
+inline void launch_on(cudaStream_t, dim3 grid, dim3 block, size_t smem, const std::function<void()> &body) { launch(grid, block, smem, body); }
+}  // namespace dp_emul
+#endif
 
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount(int *n) { *n = 8; return cudaSuccess; }
@@ -190,11 +314,103 @@ inline cudaError_t cudaMalloc(void **p, size_t n) {
     return *p ? cudaSuccess : cudaErrorMemoryAllocation;
 }
 template <class T> inline cudaError_t cudaMalloc(T **p, size_t n) { return cudaMalloc((void **)p, n); }
+#if defined(DP_EMUL_ASYNC)
+inline cudaError_t cudaFree(void *p) { dp_emul::sync_all(); free(p); return cudaSuccess; }  // cudaFree synchronises the device
+#else
 inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+#endif
 inline cudaError_t cudaMallocHost(void **p, size_t n) { return cudaMalloc(p, n); }
 template <class T> inline cudaError_t cudaMallocHost(T **p, size_t n) { return cudaMalloc((void **)p, n); }
 inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new dp_emul_event; return cudaSuccess; }
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = new dp_emul_event; return cudaSuccess; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }  // queued closures hold the shared state
+#if defined(DP_EMUL_ASYNC)
+inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind kind, cudaStream_t st = nullptr) {
+    if (kind == cudaMemcpyHostToDevice && st) {  // pageable source: staged when the copy is issued
+        auto buf = std::make_shared<std::vector<unsigned char>>((const unsigned char *)s, (const unsigned char *)s + n);
+        st->push([=] { memcpy(d, buf->data(), n); });
+    } else {
+        dp_emul::run_on(st, [=] { memmove(d, s, n); });
+    }
+    return cudaSuccess;
+}
+inline cudaError_t cudaMemcpy2DAsync(void *d, size_t dp, const void *s, size_t sp, size_t w, size_t h,
+                                     cudaMemcpyKind, cudaStream_t st = nullptr) {
+    dp_emul::run_on(st, [=] {
+        for (size_t i = 0; i < h; i++) memmove((char *)d + i * dp, (const char *)s + i * sp, w);
+    });
+    return cudaSuccess;
+}
+inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t st = nullptr) {
+    dp_emul::run_on(st, [=] { memset(d, v, n); });
+    return cudaSuccess;
+}
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) {
+    *s = new dp_emul_stream;
+    std::lock_guard<std::mutex> l(dp_emul::g_registry);
+    dp_emul::g_streams.insert(*s);
+    return cudaSuccess;
+}
+inline cudaError_t cudaStreamCreate(cudaStream_t *s) { return cudaStreamCreateWithFlags(s, 0); }
+inline cudaError_t cudaStreamDestroy(cudaStream_t s) {
+    if (!s) return cudaSuccess;
+    s->sync();
+    {
+        std::lock_guard<std::mutex> l(dp_emul::g_registry);
+        dp_emul::g_streams.erase(s);
+    }
+    delete s;
+    return cudaSuccess;
+}
+inline cudaError_t cudaStreamSynchronize(cudaStream_t s) {
+    if (s) s->sync();
+    return cudaSuccess;
+}
+inline cudaError_t cudaDeviceSynchronize() { dp_emul::sync_all(); return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s = nullptr) {
+    auto st = e->st;
+    uint64_t gen;
+    {
+        std::lock_guard<std::mutex> l(st->m);
+        gen = ++st->recorded;
+    }
+    dp_emul::run_on(s, [st, gen] {
+        {
+            std::lock_guard<std::mutex> l(st->m);
+            if (st->completed < gen) st->completed = gen;
+            st->t = std::chrono::steady_clock::now();
+        }
+        st->cv.notify_all();
+    });
+    return cudaSuccess;
+}
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned = 0) {
+    auto st = e->st;
+    uint64_t gen;
+    {
+        std::lock_guard<std::mutex> l(st->m);
+        gen = st->recorded;  // the most recent record at the time of the call; never recorded: no-op
+    }
+    dp_emul::run_on(s, [st, gen] {
+        std::unique_lock<std::mutex> l(st->m);
+        st->cv.wait(l, [&] { return st->completed >= gen; });
+    });
+    return cudaSuccess;
+}
+inline cudaError_t cudaEventSynchronize(cudaEvent_t e) {
+    auto st = e->st;
+    std::unique_lock<std::mutex> l(st->m);
+    st->cv.wait(l, [&] { return st->completed >= st->recorded; });
+    return cudaSuccess;
+}
+inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) {
+    *ms = std::chrono::duration<float, std::milli>(b->st->t - a->st->t).count();
+    return cudaSuccess;
+}
+#else
 inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) {
     memmove(d, s, n);
     return cudaSuccess;
@@ -204,7 +420,6 @@ inline cudaError_t cudaMemcpy2DAsync(void *d, size_t dp, const void *s, size_t s
     for (size_t i = 0; i < h; i++) memmove((char *)d + i * dp, (const char *)s + i * sp, w);
     return cudaSuccess;
 }
-inline cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
 inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t = nullptr) { memset(d, v, n); return cudaSuccess; }
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = nullptr; return cudaSuccess; }
 inline cudaError_t cudaStreamCreate(cudaStream_t *s) { *s = nullptr; return cudaSuccess; }
@@ -212,9 +427,6 @@ inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
-inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new dp_emul_event; return cudaSuccess; }
-inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = new dp_emul_event; return cudaSuccess; }
-inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) {
     e->t = std::chrono::steady_clock::now();
     return cudaSuccess;
@@ -224,6 +436,7 @@ inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b)
     *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
     return cudaSuccess;
 }
+#endif
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
 inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated error"; }

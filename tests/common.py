@@ -530,20 +530,20 @@ def check_schedule(orc, ctx: Context, bases, log_n: int, log_m: int, seed: int, 
     agree = (lambda ok: ok) if world == 1 else None
     if world == 1:
         clock = iter([2.0, 1.0, 1.0, 2.0])
-        step, why = schedule.pick_schedule(run, transforms, com, (2, 1), digest, lambda f: next(clock), agree)
+        step, why = schedule.pick_schedule(run, transforms, com, (1,), digest, lambda f: next(clock), agree)
         assert why.startswith("overlapped"), why
         step()
-        step, why = schedule.pick_schedule(run, transforms, com, (2, 1), digest, lambda f: next(clock), agree)
+        step, why = schedule.pick_schedule(run, transforms, com, (1,), digest, lambda f: next(clock), agree)
         assert why.startswith("serial (overlapped schedule verified but slower"), why
         flip = iter(range(10**6))
-        step, why = schedule.pick_schedule(run, transforms, com, (2, 1), lambda t: next(flip), lambda f: 1.0, agree)
+        step, why = schedule.pick_schedule(run, transforms, com, (1,), lambda t: next(flip), lambda f: 1.0, agree)
         assert "different results" in why, why
-        step, why = schedule.pick_schedule(run, transforms, com, (2, 1), digest, lambda f: 1.0, agree, allow_overlap=False)
+        step, why = schedule.pick_schedule(run, transforms, com, (1,), digest, lambda f: 1.0, agree, allow_overlap=False)
         assert why == "serial"
 
         class Boom(schedule.Runner):
             def run_overlapped(self, *a, **k):
                 raise DpError(-4, "simulated failure")
-        step, why = schedule.pick_schedule(Boom(ctx, exchange, first_id=9000), transforms, com, (2, 1), digest, lambda f: 1.0, agree)
+        step, why = schedule.pick_schedule(Boom(ctx, exchange, first_id=9000), transforms, com, (1,), digest, lambda f: 1.0, agree)
         assert "failed" in why and "simulated" in why, why
         step()

@@ -547,3 +547,31 @@ def check_schedule(orc, ctx: Context, bases, log_n: int, log_m: int, seed: int, 
         step, why = schedule.pick_schedule(Boom(ctx, exchange, first_id=9000), transforms, com, (1,), digest, lambda f: 1.0, agree)
         assert "failed" in why and "simulated" in why, why
         step()
+
+
+TWO_G1_PUBLISHED = (0x0572CBEA904D67468808C8EB50A9450C9721DB309128012543902D0AC358A62AE28F75BB8F1C7C42C39A8C5529BF0F4E,
+                    0x166A9D8CABC673A322FDA673779D8E3822BA3ECB8670E461F73BB9021D5FD76A4C56D9D4CD16BD1BBA86881979749D28)
+
+
+def check_published_vector(orc, make_ctx):
+    """The library against the one PUBLISHED absolute value on this path: 2*G1 (EIP-2537 "bls_g1add_(g1+g1=2*g1)").
+    MSMs over copies of the generator must land on it whatever the bucket geometry."""
+    from oracle.py import bls12_381 as B
+    gen = np.zeros(104, dtype=np.uint8)
+    orc.lib().orc_g1_generator(gen.ctypes.data)
+    ctx = make_ctx()
+    for n in (1, 2, 40, 3000):
+        ctx.init(np.stack([gen] * n), 1 << 4, 1 << 7)
+        sc = np.zeros((n, 4), dtype=np.uint64)
+        sc[0, 0] = 2
+        assert B.g1_affine_from_bytes(orc.normalize(ctx.msm(0, n, sc)).tobytes()) == TWO_G1_PUBLISHED, f"2*G, n={n}"
+        if n >= 2:
+            sc[:] = 0
+            sc[0, 0] = sc[n - 1, 0] = 1
+            assert B.g1_affine_from_bytes(orc.normalize(ctx.msm(0, n, sc)).tobytes()) == TWO_G1_PUBLISHED, f"G+G, n={n}"
+            # r-1 copies of ... : (r + 2) * G = 2 * G  via scalars summing to r + 2 over identical bases
+            sc[:] = 0
+            sc[0] = np.frombuffer((B.FR_MOD - 1).to_bytes(32, "little"), dtype=np.uint64)
+            sc[1, 0] = 3
+            assert B.g1_affine_from_bytes(orc.normalize(ctx.msm(0, n, sc)).tobytes()) == TWO_G1_PUBLISHED, f"(r-1)G+3G, n={n}"
+    ctx.close()

@@ -205,6 +205,10 @@ def test_satisfied_circuit_divides_exactly(orc, ctx):
     common.check_satisfied_circuit(orc, ctx, 6, 1200)
 
 
+def test_published_vector(orc, emul_lib):
+    common.check_published_vector(orc, lambda: Context(emul_lib, 0, 0, 1))
+
+
 def test_compressed_srs_ingest(orc, emul_lib):
     common.check_compressed_init(orc, lambda: Context(emul_lib, 0, 0, 1), 40, 1300)
 

@@ -30,6 +30,25 @@ def test_public_constants():
     assert pow(7, (B.FR_MOD - 1) // 2, B.FR_MOD) == B.FR_MOD - 1   # 7 is a non-residue
 
 
+# Published known-answer vector: 2*G1 of BLS12-381 (EIP-2537 test vector "bls_g1add_(g1+g1=2*g1)", also the
+# doubled generator in the zkcrypto/bls12_381 test-suite).  The only absolute value for this path that exists
+# outside the (vector-less) reference; everything else is pinned by definition-level recomputation.
+TWO_G1 = (0x0572CBEA904D67468808C8EB50A9450C9721DB309128012543902D0AC358A62AE28F75BB8F1C7C42C39A8C5529BF0F4E,
+          0x166A9D8CABC673A322FDA673779D8E3822BA3ECB8670E461F73BB9021D5FD76A4C56D9D4CD16BD1BBA86881979749D28)
+
+
+def test_published_doubling_vector(orc):
+    assert B.g1_add(B.G1_GEN, B.G1_GEN) == TWO_G1 and B.g1_mul(B.G1_GEN, 2) == TWO_G1
+    gen = np.zeros(104, dtype=np.uint8)
+    orc.lib().orc_g1_generator(gen.ctypes.data)
+    two = np.array([2, 0, 0, 0], dtype=np.uint64)
+    assert B.g1_affine_from_bytes(orc.g1_mul(gen, two).tobytes()) == TWO_G1
+    # through the Pippenger restatement as well: msm([G, G], [1, 1]) and msm([G], [2])
+    one = np.array([1, 0, 0, 0], dtype=np.uint64)
+    assert B.g1_affine_from_bytes(orc.normalize(orc.msm(np.stack([gen, gen]), np.stack([one, one]))).tobytes()) == TWO_G1
+    assert B.g1_affine_from_bytes(orc.normalize(orc.msm(gen[None], two[None])).tobytes()) == TWO_G1
+
+
 def test_field_ops_c_vs_python(orc):
     rng = np.random.default_rng(1)
     L = orc.lib()

@@ -150,3 +150,8 @@ def test_resident_rounds(orc, gpu_lib, log_n):
     c.init(bases, 1 << log_n, 8 << log_n)
     common.check_resident_rounds(orc, c, bases, log_n, 3000 + log_n)
     c.close()
+
+
+def test_published_vector_on_gpu(orc, gpu_lib):
+    """2*G1 as published (EIP-2537 vector): the one absolute value on this path that exists outside the reference"""
+    common.check_published_vector(orc, lambda: Context(gpu_lib, 0, 0, 1))

@@ -18,4 +18,6 @@ for k in msm_accumulate_kernel ntt_tile_kernel quotient_kernel msm_reduce_kernel
     timeout 200 ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o $out/${tag}_$k \
         python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > /dev/null 2>&1
 done
+# feasibility of batched-affine bucket accumulation (tools/microbench4.cu; build it first with the nvcc line in its header)
+[ -x tools/microbench4 ] && timeout 180 ./tools/microbench4 24 > $out/${tag}_microbench_affine.txt 2>&1
 ls -la $out | tail -20

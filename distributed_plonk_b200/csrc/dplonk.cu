@@ -1741,7 +1741,11 @@ int dp_fft_dev_p2p(dp_ctx *ctx, const void *rows_dev, void *cols_dev, int is_quo
     DP_LAUNCH(p2p_barrier_kernel, dim3(1), dim3(32), 0, ctx->stream, pc, (uint32_t)W, (uint32_t)ctx->me, (uint32_t)(W * ctx->bar_seq));
     ctx->launches++;
     DP_TRY(plan_col_phase(ctx, d, slot, (Fr *)cols_dev, n_cols, ctx->me * n_cols, is_inv != 0, is_coset != 0));
-    return call_end(ctx, true);
+    DP_TRY(call_end(ctx, true));
+    uint32_t timed_out = 0;  // word 1 of the arena header, set by p2p_barrier_kernel when a peer never arrived
+    DP_CUDA(ctx, cudaMemcpy(&timed_out, reinterpret_cast<uint32_t *>(ctx->arena) + 1, 4, cudaMemcpyDeviceToHost));
+    if (timed_out) return fail(ctx, DP_E_COMM, "dp_fft_dev_p2p: a peer did not reach the barrier within 20 s");
+    return DP_OK;
 }
 
 }  // extern "C"

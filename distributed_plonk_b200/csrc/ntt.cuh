@@ -331,7 +331,16 @@ __global__ void p2p_barrier_kernel(PeerCounters pc, uint32_t n_ranks, uint32_t m
     if (t < n_ranks) atomicAdd_system(pc.c[t], 1u);
     if (t == 0) {
         volatile uint32_t *mine = pc.c[me];
-        while (*mine < target) __nanosleep(100);
+        unsigned long long t0, now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (*mine < target) {
+            __nanosleep(100);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - t0 > 20000000000ull) {  // 20 s: a peer is gone; give up instead of hanging the GPU
+                pc.c[me][1] = 1u;             // word 1 of my arena header = "barrier timed out" (read by the host)
+                break;
+            }
+        }
         __threadfence_system();
     }
 #endif

@@ -58,3 +58,28 @@ def test_fails_loudly_without_gpu(real_lib):
     with pytest.raises(dp.DpError) as e:
         dp.Context(real_lib, 0, 0, 1)
     assert e.value.code == _binding.DP_E_CUDA
+
+
+def test_header_is_plain_c_and_struct_layouts_match_the_binding(tmp_path):
+    """include/dplonk.h compiles as C11 (-Wall -Werror -pedantic: the boundary a cgo / Rust `extern "C"`
+    binding sees), and the structs mirrored in _binding.py have the same size and field offsets"""
+    import subprocess
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "dplonk.h"\n'
+        "int main(void) {\n"
+        '  printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(dp_quotient_args), offsetof(dp_quotient_args, sigmas),\n'
+        "         offsetof(dp_quotient_args, wires), offsetof(dp_quotient_args, perm), offsetof(dp_quotient_args, k),\n"
+        "         offsetof(dp_quotient_args, gamma), sizeof(dp_fft_workload), offsetof(dp_fft_workload, col_end));\n"
+        "  int (*f)(dp_ctx *, uint64_t, uint64_t, uint64_t, const void *, size_t) = dp_msm_submit; (void)f;\n"
+        "  return 0;\n}\n")
+    exe = tmp_path / "abi"
+    lib = dp.library_path()
+    subprocess.check_call([cc, "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", f"-I{os.path.join(ROOT, 'include')}", str(src), "-o", str(exe),
+                           f"-L{os.path.dirname(lib)}", f"-l:{os.path.basename(lib)}", f"-Wl,-rpath,{os.path.dirname(lib)}",
+                           "-Wl,--unresolved-symbols=ignore-in-shared-libs"])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    Q, W = _binding.QuotientArgs, _binding.FftWorkload
+    assert got == [ctypes.sizeof(Q), Q.sigmas.offset, Q.wires.offset, Q.perm.offset, Q.k.offset, Q.gamma.offset,
+                   ctypes.sizeof(W), W.col_end.offset]

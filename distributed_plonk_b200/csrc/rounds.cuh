@@ -65,6 +65,17 @@ __global__ void fr_invert_kernel(Fr *x, uint64_t n) {
 }
 
 // ------------------------------------------------------------------ round 3: quotient evaluations
+// The quotient kernel is ~60 field multiplications of straight-line code per thread; inlined that is
+// > 120 KB of instructions streamed through the instruction cache by every warp.  Calling the
+// out-of-line multiplication keeps the kernel a few KB (the lesson of msm_reduce: 215 ms -> 1.4 ms).
+DP_D Fr qmul(const Fr &a, const Fr &b) {
+#if defined(__CUDA_ARCH__)
+    return Fr::mul_outlined(a, b);
+#else
+    return a * b;
+#endif
+}
+
 struct QuotientArgs {
     const Fr *sel[13];  // q_lc[4], q_mul[2], q_hash[4], q_o, q_c, q_ecc   (dispatcher2.rs:437-450)
     const Fr *sig[5];
@@ -111,31 +122,31 @@ __global__ void __launch_bounds__(QUO_TPB) quotient_kernel(QuotientArgs q) {
     const Fr inv_xm1 = block_batch_invert<QUO_TPB>(xm1, tree, q.prod_inv ? q.prod_inv + blockIdx.x : nullptr);
     if (!live) return;
     const Fr a = gmem_ld(q.w[0] + i), b = gmem_ld(q.w[1] + i), c = gmem_ld(q.w[2] + i), d = gmem_ld(q.w[3] + i), e = gmem_ld(q.w[4] + i);
-    const Fr ab = a * b, cd = c * d;
+    const Fr ab = qmul(a, b), cd = qmul(c, d);
     // gate constraint (lines 451-472)
     Fr gate = gmem_ld(q.sel[11] + i) + gmem_ld(q.pi + i);
-    gate = gate + gmem_ld(q.sel[0] + i) * a + gmem_ld(q.sel[1] + i) * b + gmem_ld(q.sel[2] + i) * c + gmem_ld(q.sel[3] + i) * d;
-    gate = gate + gmem_ld(q.sel[4] + i) * ab + gmem_ld(q.sel[5] + i) * cd;
-    gate = gate + gmem_ld(q.sel[12] + i) * (ab * cd * e);
-    {
-        const Fr a2 = a.sqr(), b2 = b.sqr(), c2 = c.sqr(), d2 = d.sqr();
-        gate = gate + gmem_ld(q.sel[6] + i) * (a2.sqr() * a) + gmem_ld(q.sel[7] + i) * (b2.sqr() * b);
-        gate = gate + gmem_ld(q.sel[8] + i) * (c2.sqr() * c) + gmem_ld(q.sel[9] + i) * (d2.sqr() * d);
+    gate = gate + qmul(gmem_ld(q.sel[0] + i), a) + qmul(gmem_ld(q.sel[1] + i), b) + qmul(gmem_ld(q.sel[2] + i), c) + qmul(gmem_ld(q.sel[3] + i), d);
+    gate = gate + qmul(gmem_ld(q.sel[4] + i), ab) + qmul(gmem_ld(q.sel[5] + i), cd);
+    gate = gate + qmul(gmem_ld(q.sel[12] + i), qmul(qmul(ab, cd), e));
+    const Fr wv[5] = {a, b, c, d, e};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {  // q_hash[j] * w_j^5
+        const Fr w2 = qmul(wv[j], wv[j]);
+        gate = gate + qmul(gmem_ld(q.sel[6 + j] + i), qmul(qmul(w2, w2), wv[j]));
     }
-    gate = gate - gmem_ld(q.sel[10] + i) * e;
+    gate = gate - qmul(gmem_ld(q.sel[10] + i), e);
     // permutation constraint (lines 473-491): z(X) prod(w + beta k X + gamma) - z(omega X) prod(w + beta sigma + gamma)
     const Fr zi = gmem_ld(q.z + i);
     Fr acc1 = zi, acc2 = gmem_ld(q.z + ((i + q.ratio) & (q.m - 1)));
-    const Fr wv[5] = {a, b, c, d, e};
 #pragma unroll
     for (int j = 0; j < 5; j++) {
         const Fr t = wv[j] + q.gamma;
-        acc1 = acc1 * (t + q.k_beta[j] * x);
-        acc2 = acc2 * (t + gmem_ld(q.sig[j] + i) * q.beta);
+        acc1 = qmul(acc1, t + qmul(q.k_beta[j], x));
+        acc2 = qmul(acc2, t + qmul(gmem_ld(q.sig[j] + i), q.beta));
     }
-    Fr r = q.zh_inv[i % q.ratio] * (gate + q.alpha * (acc1 - acc2));
+    Fr r = qmul(q.zh_inv[i % q.ratio], gate + qmul(q.alpha, acc1 - acc2));
     // (z - 1) L_1 alpha^2 / Z_H = alpha^2/n (z - 1) / (x - 1)   (lines 493-499)
-    r = r + q.alpha_sq_div_n * (zi - one) * inv_xm1;
+    r = r + qmul(qmul(q.alpha_sq_div_n, zi - one), inv_xm1);
     gmem_st(q.out + i, r);
 }
 

@@ -27,13 +27,20 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return OUT
+    import fcntl
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", OUT, os.path.join(SRC, "dplonk.cu")]
-    if verbose:
-        cmd[1:1] = ["-Xptxas", "-v"]
-        print(" ".join(cmd), flush=True)
-    subprocess.check_call(cmd)
+    with open(OUT + ".lock", "w") as lock:          # several ranks of one job may get here together
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not is_stale():            # another process built it while we waited
+            return OUT
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        tmp = f"{OUT}.tmp.{os.getpid()}"
+        cmd = [nvcc, *NVCC_FLAGS, "-o", tmp, os.path.join(SRC, "dplonk.cu")]
+        if verbose:
+            cmd[1:1] = ["-Xptxas", "-v"]
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+        os.replace(tmp, OUT)                        # atomic: a loader never sees a half-written library
     return OUT
 
 

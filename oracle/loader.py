@@ -31,9 +31,15 @@ def build(force: bool = False) -> str:
     tag = _cpu_tag()
     same_host = os.path.exists(stamp) and open(stamp).read() == tag
     if force or not same_host or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-s", "-B", "-C", _HERE])
-        with open(stamp, "w") as f:
-            f.write(tag)
+        import fcntl
+        os.makedirs(os.path.dirname(_SO), exist_ok=True)
+        with open(_SO + ".lock", "w") as lock:      # several processes of one test may get here together
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            same_host = os.path.exists(stamp) and open(stamp).read() == tag
+            if force or not same_host or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+                subprocess.check_call(["make", "-s", "-B", "-C", _HERE])
+                with open(stamp, "w") as f:
+                    f.write(tag)
     return _SO
 
 

@@ -28,9 +28,16 @@ def _build(OUT, extra, force):
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    import fcntl
+    lock = open(OUT + ".lock", "w")                  # one builder at a time; released when the process drops the file
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
+        return OUT
+    tmp = f"{OUT}.tmp.{os.getpid()}"
     cmd = [CXX, "-O2", "-g", "-std=c++20", "-fPIC", "-shared", "-pthread", "-DDP_EMUL", *extra, "-Wall", "-Wno-unknown-pragmas",
-           "-x", "c++", os.path.join(SRC, "dplonk.cu"), "-o", OUT]
+           "-x", "c++", os.path.join(SRC, "dplonk.cu"), "-o", tmp]
     subprocess.check_call(cmd)
+    os.replace(tmp, OUT)          # atomic: concurrent builders / loaders never see a half-written library
     return OUT
 
 

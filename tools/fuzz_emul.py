@@ -10,7 +10,7 @@ from distributed_plonk_b200 import dispatcher as disp
 from oracle import loader as L
 from tests import common
 from tests.emul import build as _emul_build
-lib=bind(C.CDLL(_emul_build.build()))
+lib=bind(C.CDLL(_emul_build.build(async_streams=os.environ.get('DP_TEST_EMUL_ASYNC','0')=='1')))  # DP_TEST_EMUL_ASYNC=1: real asynchronous streams
 rng=random.Random(int(sys.argv[1]) if len(sys.argv)>1 else 1)
 def host_copy(d,s,n): C.memmove(d,s,n)
 t0=time.time(); it=0; fails=0

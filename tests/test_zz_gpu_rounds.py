@@ -155,3 +155,18 @@ def test_resident_rounds(orc, gpu_lib, log_n):
 def test_published_vector_on_gpu(orc, gpu_lib):
     """2*G1 as published (EIP-2537 vector): the one absolute value on this path that exists outside the reference"""
     common.check_published_vector(orc, lambda: Context(gpu_lib, 0, 0, 1))
+
+
+def test_host_schedules_two_ranks_nccl(orc, tmp_path):
+    """the serial / overlapped host schedules with the exchange as one NCCL all-to-all per transform (2 GPUs)"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    import distributed_plonk_b200 as dp
+    from tests.test_distributed_cpu import _free_port, _worker
+    dp.load()
+    orc.build()
+    mp.spawn(_worker, args=(2, _free_port(), dp.library_path(), str(tmp_path), "nccl", True), nprocs=2, join=True)
+    for r in range(2):
+        assert (tmp_path / f"rank{r}.txt").read_text() == "ok"

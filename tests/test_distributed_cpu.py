@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, lib_path, out_dir, backend="gloo", schedule_only=False):
+def _worker(rank, world, port, lib_path, out_dir, backend="gloo", extra=""):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     cuda = backend == "nccl"
@@ -67,11 +67,11 @@ def _worker(rank, world, port, lib_path, out_dir, backend="gloo", schedule_only=
                 good &= bool(np.array_equal(disp.assemble(cols), orc.fft(x, inv, cos)))
         return good
 
-    if not schedule_only:
+    if extra != "schedule":
         ok &= run_ffts("collective")      # one all_to_all_single per transform
 
     # the host schedules of bench.py's end-to-end leg (serial / commitments queued between transforms).
-    # Under NCCL this part runs from its own test (tests/test_zz_gpu_rounds.py, schedule_only=True) so that
+    # Under NCCL this part runs from its own test (tests/test_zz_gpu_rounds.py, extra="schedule") so that
     # the long-validated checks of this worker keep their place at the front of the GPU suite.
     def gather(a):
         mine = torch.from_numpy(a.view(np.int64))
@@ -80,6 +80,7 @@ def _worker(rank, world, port, lib_path, out_dir, backend="gloo", schedule_only=
         parts = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(parts, mine)
         return torch.cat(parts).cpu().numpy().view(np.uint64)
+    schedule_only = extra == "schedule"
     if not cuda or schedule_only:
         from tests import common
         try:
@@ -99,7 +100,8 @@ def _worker(rank, world, port, lib_path, out_dir, backend="gloo", schedule_only=
         ok &= run_ffts("fused")           # row kernel stores straight into peer memory
         # device-resident transform with the device-side barrier kernel (no host sync, no NCCL call)
         # (world 8 unverified in round 1: restricted to the sizes that were run on hardware)
-        for k, (inv, cos) in enumerate([(False, True), (True, True), (False, False)] * 2 if world <= 4 else []):
+        # (its own test too, extra="p2p_barrier": the kernel's bounded spin was added after its last run on hardware)
+        for k, (inv, cos) in enumerate([(False, True), (True, True), (False, False)] * 2 if world <= 4 and extra == "p2p_barrier" else []):
             L = 9
             r, c = 1 << (L >> 1), (1 << L) >> (L >> 1)
             x = orc.gen_fr(300 + k, 1 << L)

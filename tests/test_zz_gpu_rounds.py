@@ -167,6 +167,22 @@ def test_host_schedules_two_ranks_nccl(orc, tmp_path):
     from tests.test_distributed_cpu import _free_port, _worker
     dp.load()
     orc.build()
-    mp.spawn(_worker, args=(2, _free_port(), dp.library_path(), str(tmp_path), "nccl", True), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), dp.library_path(), str(tmp_path), "nccl", "schedule"), nprocs=2, join=True)
     for r in range(2):
+        assert (tmp_path / f"rank{r}.txt").read_text() == "ok"
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_device_side_barrier_transform(orc, tmp_path, world):
+    """dp_fft_dev_p2p: rows -> peer stores -> p2p_barrier_kernel -> columns on one stream (no host barrier)"""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+
+    import distributed_plonk_b200 as dp
+    from tests.test_distributed_cpu import _free_port, _worker
+    dp.load()
+    orc.build()
+    mp.spawn(_worker, args=(world, _free_port(), dp.library_path(), str(tmp_path), "nccl", "p2p_barrier"), nprocs=world, join=True)
+    for r in range(world):
         assert (tmp_path / f"rank{r}.txt").read_text() == "ok"

@@ -13,10 +13,11 @@
 #include "../../distributed_plonk_b200/host/plonk_worker.hpp"
 
 int main(int argc, char **argv) {
-    if (argc != 3) {
-        std::fprintf(stderr, "usage: %s request.bin reply.bin\n", argv[0]);
+    if (argc != 3 && argc != 4) {
+        std::fprintf(stderr, "usage: %s request.bin reply.bin [rounds]\n", argv[0]);
         return 2;
     }
+    const bool rounds = argc == 4;  // also exercise Promise-style varMsm and the round 4-5 bodies
     std::ifstream in(argv[1], std::ios::binary);
     uint64_t hdr[5];
     in.read(reinterpret_cast<char *>(hdr), sizeof hdr);
@@ -48,6 +49,10 @@ int main(int argc, char **argv) {
             std::fprintf(stderr, "fft2 on an unknown task did not raise DP_E_ARG\n");
             return 1;
         }
+        std::ofstream o(argv[2], std::ios::binary);
+        o.write(reinterpret_cast<const char *>(parts[0].data()), parts[0].size());
+        o.write(reinterpret_cast<const char *>(out.data()), out.size());
+        if (!rounds) return 0;
         // varMsm from a Promise: two jobs pending around another request, same partial as the blocking call
         worker.var_msm_begin(1, {0, n_bases}, dplonk::chunks(scalars.data(), scalars.size()));
         worker.var_msm_begin(2, {0, n_bases}, dplonk::chunks(scalars.data(), scalars.size()));
@@ -63,9 +68,6 @@ int main(int argc, char **argv) {
         std::memcpy(one_and_z.data(), z.data(), DP_FR_BYTES);
         std::memcpy(one_and_z.data() + DP_FR_BYTES, z.data(), DP_FR_BYTES);
         dplonk::Bytes lc = worker.lin_comb({coeffs, dplonk::Bytes(coeffs.begin(), coeffs.begin() + coeffs.size() / 2)}, one_and_z);
-        std::ofstream o(argv[2], std::ios::binary);
-        o.write(reinterpret_cast<const char *>(parts[0].data()), parts[0].size());
-        o.write(reinterpret_cast<const char *>(out.data()), out.size());
         o.write(reinterpret_cast<const char *>(pz.data()), pz.size());
         o.write(reinterpret_cast<const char *>(q.data()), q.size());
         o.write(reinterpret_cast<const char *>(lc.data()), lc.size());

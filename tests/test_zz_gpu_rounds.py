@@ -186,3 +186,12 @@ def test_device_side_barrier_transform(orc, tmp_path, world):
     mp.spawn(_worker, args=(world, _free_port(), dp.library_path(), str(tmp_path), "nccl", "p2p_barrier"), nprocs=world, join=True)
     for r in range(world):
         assert (tmp_path / f"rank{r}.txt").read_text() == "ok"
+
+
+def test_cpp_host_mirror_rounds_on_gpu(orc, tmp_path):
+    """the C++ mirror's Promise-style varMsm and round 4-5 bodies against the real library"""
+    import distributed_plonk_b200 as dp
+    from tests.test_host_mirror import build_cli, run_case
+    dp.load()
+    exe = build_cli(dp.library_path(), str(tmp_path / "host_mirror_gpu"))
+    run_case(orc, exe, tmp_path, (1 << 12) + 32, 12, 15, 0b101, 1 << 12, rounds=True)

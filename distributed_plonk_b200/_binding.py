@@ -17,6 +17,7 @@ EXPORTS = [
     "dp_quotient_evals", "dp_quotient_evals_dev", "dp_poly_eval", "dp_poly_eval_dev", "dp_poly_lincomb", "dp_poly_lincomb_dev",
     "dp_poly_div_linear", "dp_poly_div_linear_dev", "dp_init_compressed", "dp_get_bases",
     "dp_msm_submit", "dp_msm_collect", "dp_poly_put", "dp_poly_ptr", "dp_poly_get", "dp_poly_free", "dp_commit_dev",
+    "dp_fft_exchange_begin_async", "dp_compute_stream",
 ]
 
 
@@ -53,6 +54,8 @@ def bind(cdll: C.CDLL) -> C.CDLL:
         "dp_fft2_prepare": (i, [vp, u64]),
         "dp_fft_exchange_begin": (i, [vp, u64, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]),
         "dp_fft_exchange_end": (i, [vp, u64]),
+        "dp_fft_exchange_begin_async": (i, [vp, u64, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]),
+        "dp_compute_stream": (i, [vp, C.POINTER(vp)]),
         "dp_fft2": (i, [vp, u64, vp, sz]),
         "dp_ntt": (i, [vp, vp, sz, u32, i, i]),
         "dp_round1": (i, [vp, vp, sz, vp, vp]),
@@ -179,6 +182,17 @@ class Context:
         s, r, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
         self._ck(self.lib.dp_fft_exchange_begin(self.h, task_id, C.byref(s), C.byref(r), C.byref(n)))
         return s.value, r.value, n.value
+
+    def fft_exchange_begin_async(self, task_id: int):
+        """like fft_exchange_begin, without waiting: the buffers are valid for work on compute_stream()"""
+        s, r, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        self._ck(self.lib.dp_fft_exchange_begin_async(self.h, task_id, C.byref(s), C.byref(r), C.byref(n)))
+        return s.value, r.value, n.value
+
+    def compute_stream(self) -> int:
+        st = C.c_void_p()
+        self._ck(self.lib.dp_compute_stream(self.h, C.byref(st)))
+        return st.value or 0
 
     def fft_exchange_end(self, task_id: int):
         self._ck(self.lib.dp_fft_exchange_end(self.h, task_id))

@@ -1292,7 +1292,26 @@ int dp_fft1(dp_ctx *ctx, uint64_t id, uint64_t i, const void *row, size_t len) {
     return dp_fft1_rows(ctx, id, i, 1, row);
 }
 
+static int exchange_begin(dp_ctx *ctx, uint64_t id, void **send_dev, void **recv_dev, uint64_t *block_elems, bool wait);
+
 int dp_fft_exchange_begin(dp_ctx *ctx, uint64_t id, void **send_dev, void **recv_dev, uint64_t *block_elems) {
+    return exchange_begin(ctx, id, send_dev, recv_dev, block_elems, true);
+}
+
+// Same, but returns without waiting for the row phase: the buffers are complete only for work that is
+// enqueued on the context's compute stream (dp_compute_stream), e.g. the ncclSend / ncclRecv group of the
+// exchange.  With dp_fft_exchange_end right behind it a whole multi-worker transform is asynchronous.
+int dp_fft_exchange_begin_async(dp_ctx *ctx, uint64_t id, void **send_dev, void **recv_dev, uint64_t *block_elems) {
+    return exchange_begin(ctx, id, send_dev, recv_dev, block_elems, false);
+}
+
+int dp_compute_stream(dp_ctx *ctx, void **stream) {
+    if (!ctx || !stream) return fail(ctx, DP_E_ARG, "dp_compute_stream: NULL argument");
+    *stream = (void *)ctx->stream;
+    return DP_OK;
+}
+
+static int exchange_begin(dp_ctx *ctx, uint64_t id, void **send_dev, void **recv_dev, uint64_t *block_elems, bool wait) {
     if (!ctx || !send_dev || !recv_dev || !block_elems) return fail(ctx, DP_E_ARG, "dp_fft_exchange_begin: NULL argument");
     FftTask *t = find_task(ctx, id);
     if (!t) return fail(ctx, DP_E_ARG, "dp_fft_exchange_begin: unknown task %llu", (unsigned long long)id);
@@ -1308,7 +1327,7 @@ int dp_fft_exchange_begin(dp_ctx *ctx, uint64_t id, void **send_dev, void **recv
             if (!t->recv) return fail(ctx, DP_E_OOM, "exchange recv buffer");
         }
     }
-    DP_TRY(call_end(ctx, true));  // buffers must be complete before the caller's collective reads them
+    DP_TRY(call_end(ctx, wait));  // buffers must be complete before the caller's collective reads them (or ordered behind them)
     *send_dev = t->send;
     *recv_dev = t->recv;
     *block_elems = t->n_rows * t->n_cols;

@@ -53,6 +53,22 @@ def make_exchange(group=None, cuda: bool | None = None):
     return exchange
 
 
+def make_stream_ordered_exchange(ctx, group=None):
+    """The exchange enqueued on the context's compute stream (NCCL only): no host synchronisation, so a
+    multi-GPU transform is as asynchronous as a single-GPU one.  Pair it with
+    Context.fft_exchange_begin_async; block q of send goes to rank q as for make_exchange."""
+    world = dist.get_world_size(group)
+    stream = torch.cuda.ExternalStream(ctx.compute_stream())
+
+    def exchange(send_ptr: int, recv_ptr: int, block_elems: int):
+        nbytes = block_elems * 32 * world
+        with torch.cuda.stream(stream):   # the collective starts after the row kernels and the column kernels wait for it
+            dist.all_to_all_single(as_tensor(recv_ptr, nbytes, True), as_tensor(send_ptr, nbytes, True), group=group)
+
+    exchange.stream_ordered = True
+    return exchange
+
+
 def msm_shard(n_bases: int, rank: int, world: int):
     """MsmWorkload of `rank`: the global index range of dispatcher2.rs:870-881."""
     return rank * n_bases // world, (rank + 1) * n_bases // world

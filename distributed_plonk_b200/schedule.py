@@ -60,7 +60,8 @@ class Runner:
         if self.exchange is None:
             ctx.fft2_prepare(tid)
         else:   # several workers: one all-to-all on the task's own send / receive buffers
-            s, r, blk = ctx.fft_exchange_begin(tid)
+            ordered = getattr(self.exchange, "stream_ordered", False)   # enqueued on the compute stream: nothing to wait for
+            s, r, blk = ctx.fft_exchange_begin_async(tid) if ordered else ctx.fft_exchange_begin(tid)
             self.exchange(s, r, blk)
             ctx.fft_exchange_end(tid)
         return tid

@@ -131,6 +131,14 @@ int dp_fft2_prepare(dp_ctx *ctx, uint64_t id);
  * the all-to-all (block q of send -> rank q, into block `me` of its recv) and calls _end. */
 int dp_fft_exchange_begin(dp_ctx *ctx, uint64_t id, void **send_dev, void **recv_dev, uint64_t *block_elems);
 int dp_fft_exchange_end(dp_ctx *ctx, uint64_t id);
+/* Stream-ordered form of the same step, for a host that issues the exchange with its own NCCL
+ * communicator: dp_fft_exchange_begin_async returns without waiting for the row phase; the two buffers
+ * are then valid only for work enqueued on the context's compute stream (dp_compute_stream gives the
+ * cudaStream_t), i.e. ncclGroupStart(); ncclSend / ncclRecv(..., stream) x W; ncclGroupEnd(); followed
+ * by dp_fft_exchange_end.  Nothing blocks the host: copy-in, row kernels, all-to-all and column
+ * kernels of consecutive tasks pipeline as they do for a single worker.                             */
+int dp_fft_exchange_begin_async(dp_ctx *ctx, uint64_t id, void **send_dev, void **recv_dev, uint64_t *block_elems);
+int dp_compute_stream(dp_ctx *ctx, void **stream);
 
 /* ---- PlonkSlave.fft2 (src/worker.rs:347-381) -------------------------------------------------
  * Column transforms (fft2_helper, worker.rs:96-115); writes the local columns back to back

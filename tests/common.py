@@ -31,10 +31,17 @@ def check_whole_ntt(orc, ctx: Context, log_n: int, seed: int, n_in=None):
         assert np.array_equal(got, ref), f"dp_ntt log_n={log_n} inv={inv} coset={cos}"
 
 
-def local_exchange(ctxs, tid):
-    """in-process all-to-all over the split API (single process holding every worker)"""
+def local_exchange(ctxs, tid, async_begin=False):
+    """in-process all-to-all over the split API (single process holding every worker).  async_begin: the
+    stream-ordered form (dp_fft_exchange_begin_async) - the copies here are host-side, so the streams are
+    drained explicitly before them, which is exactly the wait the blocking form does internally"""
     W = len(ctxs)
-    bufs = [c.fft_exchange_begin(tid) for c in ctxs]
+    if async_begin:
+        bufs = [c.fft_exchange_begin_async(tid) for c in ctxs]
+        for c in ctxs:
+            c.sync()
+    else:
+        bufs = [c.fft_exchange_begin(tid) for c in ctxs]
     import_cuda = None
     for p in range(W):
         for q in range(W):
@@ -54,7 +61,7 @@ def attach_in_process(workers, arena_bytes):
         assert w.ctx.peer_ready()
 
 
-def check_distributed_fft(orc, workers, domain_log, is_quot, seed, copy_fn, n_in=None):
+def check_distributed_fft(orc, workers, domain_log, is_quot, seed, copy_fn, n_in=None, async_begin=False):
     """test_fft (dispatcher.rs:246-350): all flag combos through fft_init / fft1 / fft2_prepare /
     fft2 must equal Radix2EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}."""
     N = 1 << domain_log
@@ -82,7 +89,7 @@ def check_distributed_fft(orc, workers, domain_log, is_quot, seed, copy_fn, n_in
             for p, w in enumerate(workers):
                 for j in range(wl[p][1] - wl[p][0]):
                     w.fft1(tid, j, chunks(rows[wl[p][0] + j]))
-            for dst, src, n in local_exchange([w.ctx for w in workers], tid):
+            for dst, src, n in local_exchange([w.ctx for w in workers], tid, async_begin):
                 copy_fn(dst, src, n)
             cols = np.concatenate([w.fft2_array(tid) for w in workers], axis=0)
             got = disp.assemble(cols)

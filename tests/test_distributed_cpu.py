@@ -67,7 +67,7 @@ def _worker(rank, world, port, lib_path, out_dir, backend="gloo", extra=""):
                 good &= bool(np.array_equal(disp.assemble(cols), orc.fft(x, inv, cos)))
         return good
 
-    if extra != "schedule":
+    if not extra.startswith("schedule"):
         ok &= run_ffts("collective")      # one all_to_all_single per transform
 
     # the host schedules of bench.py's end-to-end leg (serial / commitments queued between transforms).
@@ -80,11 +80,12 @@ def _worker(rank, world, port, lib_path, out_dir, backend="gloo", extra=""):
         parts = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(parts, mine)
         return torch.cat(parts).cpu().numpy().view(np.uint64)
-    schedule_only = extra == "schedule"
+    schedule_only = extra in ("schedule", "schedule_stream_ordered")
     if not cuda or schedule_only:
         from tests import common
         try:
-            common.check_schedule(orc, w.ctx, bases, 6, 9, 1700, rank, world, exchange, gather)
+            ex = parallel.make_stream_ordered_exchange(w.ctx) if extra == "schedule_stream_ordered" else exchange
+            common.check_schedule(orc, w.ctx, bases, 6, 9, 1700, rank, world, ex, gather)
         except AssertionError as e:
             print("schedule check failed:", e, flush=True)
             ok = False

@@ -14,7 +14,8 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SELECT = "host_schedules or async_msm or commit_and_round1 or msm_dev_batch or resident_rounds or fused_peer_exchange"
+SELECT = ("host_schedules or async_msm or commit_and_round1 or msm_dev_batch or resident_rounds or fused_peer_exchange "
+          "or like_reference_test_fft")
 
 
 @pytest.mark.timeout(1500)

@@ -49,6 +49,9 @@ def test_distributed_fft_like_reference_test_fft(orc, emul_lib, W, logn, logq, l
     common.check_distributed_fft(orc, workers, logn, False, 3, host_copy)
     common.check_distributed_fft(orc, workers, logq, True, 4, host_copy)
     common.check_distributed_fft(orc, workers, logq, True, 5, host_copy, n_in=(1 << logq) // 8)  # n coeffs on the 8n domain
+    if W > 1:   # stream-ordered begin (dp_fft_exchange_begin_async) + the compute-stream handle
+        common.check_distributed_fft(orc, workers, logq, True, 6, host_copy, async_begin=True)
+        assert isinstance(workers[0].ctx.compute_stream(), int)
     for w in workers:
         w.close()
 

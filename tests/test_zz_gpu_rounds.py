@@ -157,8 +157,10 @@ def test_published_vector_on_gpu(orc, gpu_lib):
     common.check_published_vector(orc, lambda: Context(gpu_lib, 0, 0, 1))
 
 
-def test_host_schedules_two_ranks_nccl(orc, tmp_path):
-    """the serial / overlapped host schedules with the exchange as one NCCL all-to-all per transform (2 GPUs)"""
+@pytest.mark.parametrize("mode", ["schedule", "schedule_stream_ordered"])
+def test_host_schedules_two_ranks_nccl(orc, tmp_path, mode):
+    """the serial / overlapped host schedules with the exchange as one NCCL all-to-all per transform (2 GPUs):
+    host-synchronised (make_exchange) and enqueued on the compute stream (make_stream_ordered_exchange)"""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
@@ -167,7 +169,7 @@ def test_host_schedules_two_ranks_nccl(orc, tmp_path):
     from tests.test_distributed_cpu import _free_port, _worker
     dp.load()
     orc.build()
-    mp.spawn(_worker, args=(2, _free_port(), dp.library_path(), str(tmp_path), "nccl", "schedule"), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), dp.library_path(), str(tmp_path), "nccl", mode), nprocs=2, join=True)
     for r in range(2):
         assert (tmp_path / f"rank{r}.txt").read_text() == "ok"
 

@@ -1288,8 +1288,20 @@ int dp_fft1(dp_ctx *ctx, uint64_t id, uint64_t i, const void *row, size_t len) {
     FftTask *t = find_task(ctx, id);
     if (!t) return fail(ctx, DP_E_ARG, "dp_fft1: unknown task %llu", (unsigned long long)id);
     const uint64_t c = ctx->dom[t->is_quot ? 1 : 0].c();
-    if (len != c) return fail(ctx, DP_E_ARG, "dp_fft1: row of %zu elements, expected %llu", len, (unsigned long long)c);
-    return dp_fft1_rows(ctx, id, i, 1, row);
+    if (len >= c) return dp_fft1_rows(ctx, id, i, 1, row);  // a longer row is cut to c, as the resize does
+    // a shorter row is zero-extended: c_domain.fft_in_place resizes v to the domain size (worker.rs:81-85)
+    if (len && !row) return fail(ctx, DP_E_ARG, "dp_fft1: NULL argument");
+    if (t->row_phase_done) return fail(ctx, DP_E_STATE, "dp_fft1 after fft2_prepare");
+    if (i >= t->n_rows) return fail(ctx, DP_E_ARG, "dp_fft1: row %llu of %llu", (unsigned long long)i, (unsigned long long)t->n_rows);
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (len) DP_CUDA(ctx, cudaMemcpyAsync(t->rows + i * c, row, len * sizeof(Fr), cudaMemcpyHostToDevice, ctx->s_in));
+    DP_CUDA(ctx, cudaMemsetAsync(t->rows + i * c + len, 0, (c - len) * sizeof(Fr), ctx->s_in));
+    DP_CUDA(ctx, cudaEventRecord(t->ev_in, ctx->s_in));
+    if (!t->row_seen[i]) {
+        t->row_seen[i] = 1;
+        t->rows_filled++;
+    }
+    return DP_OK;
 }
 
 static int exchange_begin(dp_ctx *ctx, uint64_t id, void **send_dev, void **recv_dev, uint64_t *block_elems, bool wait);

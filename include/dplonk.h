@@ -112,8 +112,11 @@ int dp_fft_init(dp_ctx *ctx, uint64_t id, const dp_fft_workload *workloads, size
                 int is_inv, int is_coset);
 
 /* ---- PlonkSlave.fft1 (src/worker.rs:235-278) -------------------------------------------------
- * Hands in local row `i` (global row i + row_start): len must be c.  The row transform
- * (fft1_helper, worker.rs:66-94) runs on the device, at the latest in dp_fft2_prepare. */
+ * Hands in local row `i` (global row i + row_start).  len is normally c; a shorter row is zero-extended
+ * and a longer one cut to c, which is what `c_domain.fft_in_place(&mut v)` does to `v` in the reference
+ * (it resizes to the domain size) - a dispatcher may therefore leave out the zero tail of a padded
+ * polynomial's rows.  The row transform (fft1_helper, worker.rs:66-94) runs on the device, at the latest
+ * in dp_fft2_prepare. */
 int dp_fft1(dp_ctx *ctx, uint64_t id, uint64_t i, const void *row, size_t len);
 /* n_rows consecutive local rows in one call (rows = n_rows * c Fr, row-major) */
 int dp_fft1_rows(dp_ctx *ctx, uint64_t id, uint64_t i_first, uint64_t n_rows, const void *rows);

@@ -582,3 +582,30 @@ def check_published_vector(orc, make_ctx):
             sc[1, 0] = 3
             assert B.g1_affine_from_bytes(orc.normalize(ctx.msm(0, n, sc)).tobytes()) == TWO_G1_PUBLISHED, f"(r-1)G+3G, n={n}"
     ctx.close()
+
+
+def check_fft1_row_lengths(orc, worker: PlonkSlave, domain_log: int, is_quot: bool, seed: int):
+    """fft1 with rows shorter than c (the zero tail of a padded polynomial left out) or longer than c:
+    `c_domain.fft_in_place(&mut v)` resizes v, so the result is that of the zero-extended / cut row"""
+    N = 1 << domain_log
+    r = 1 << (domain_log >> 1)
+    c = N // r
+    x = orc.gen_fr(seed, N // 8 if N >= 8 else N)              # n coefficients on an 8n domain
+    padded = np.zeros((N, 4), dtype=np.uint64)
+    padded[: x.shape[0]] = x
+    rows = disp.dispatcher_rows(x, domain_log)                  # [r][c], columns >= c/8 are zero
+    keep = max(1, c // 8)
+    assert not rows[:, keep:].any()
+    wl = disp.fft_workloads(domain_log, 1)
+    for tid, (inv, cos) in enumerate(FLAG_COMBOS):
+        worker.fft_init(9100 + tid, wl, is_quot, inv, cos)
+        for j in range(r):
+            if j % 3 == 0:       # full row
+                worker.fft1(9100 + tid, j, chunks(rows[j]))
+            elif j % 3 == 1:     # only the non-zero prefix
+                worker.fft1(9100 + tid, j, chunks(np.ascontiguousarray(rows[j, :keep])))
+            else:                # a row with junk beyond c: cut
+                worker.fft1(9100 + tid, j, chunks(np.concatenate([rows[j], orc.gen_fr(seed + j, 3)])))
+        worker.fft2_prepare(9100 + tid)
+        got = disp.assemble(worker.fft2_array(9100 + tid))
+        assert np.array_equal(got, orc.fft(padded, inv, cos)), f"short / long rows, inv={inv} coset={cos}"

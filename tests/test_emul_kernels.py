@@ -56,6 +56,14 @@ def test_distributed_fft_like_reference_test_fft(orc, emul_lib, W, logn, logq, l
         w.close()
 
 
+def test_fft1_short_and_long_rows(orc, emul_lib):
+    w = PlonkSlave(emul_lib, 0, 1)
+    w.init([b""], 1 << 6, 1 << 9)
+    common.check_fft1_row_lengths(orc, w, 9, True, 60)
+    common.check_fft1_row_lengths(orc, w, 6, False, 61)
+    w.close()
+
+
 @pytest.mark.parametrize("W,limits", [(2, (11, 9)), (4, (2, 2))])
 def test_distributed_fft_fused_peer_exchange(orc, emul_lib, W, limits):
     """dp_peer_arena_create / dp_peer_attach: the row kernel stores into the owners' arenas (the
@@ -276,8 +284,10 @@ def test_error_behaviour(orc, emul_lib):
     c.fft_init(1, wl, False, False, False)
     with pytest.raises(DpError):
         c.fft_init(1, wl, False, False, False)     # duplicate id
-    with pytest.raises(DpError):
-        c.fft1(1, 0, np.zeros((3, 4), dtype=np.uint64))   # wrong row length
+    c.fft1(1, 0, np.zeros((3, 4), dtype=np.uint64))       # a short row is zero-extended (fft_in_place resizes)
+    with pytest.raises(DpError) as e:
+        c.fft1(1, 4, np.zeros((4, 4), dtype=np.uint64))   # row index outside the worker's range
+    assert e.value.code == -1
     with pytest.raises(DpError) as e:
         c.fft2_prepare(1)                          # rows missing
     assert e.value.code == -2

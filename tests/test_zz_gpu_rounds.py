@@ -197,3 +197,13 @@ def test_cpp_host_mirror_rounds_on_gpu(orc, tmp_path):
     dp.load()
     exe = build_cli(dp.library_path(), str(tmp_path / "host_mirror_gpu"))
     run_case(orc, exe, tmp_path, (1 << 12) + 32, 12, 15, 0b101, 1 << 12, rounds=True)
+
+
+def test_fft1_short_and_long_rows(orc, gpu_lib):
+    """fft1 rows shorter / longer than c behave like the reference's `fft_in_place` resize"""
+    from distributed_plonk_b200.worker import PlonkSlave
+    w = PlonkSlave(gpu_lib, 0, 1)
+    w.init([b""], 1 << 10, 1 << 13)
+    common.check_fft1_row_lengths(orc, w, 13, True, 3100)
+    common.check_fft1_row_lengths(orc, w, 10, False, 3101)
+    w.close()

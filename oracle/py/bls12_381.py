@@ -6,8 +6,9 @@ and bench.py's cpu_baseline / --impl reference legs use oracle/ as the checker.
 
 PARITY UNPINNED by reference fixtures: the reference (/root/reference, Rust, arkworks 0.3.0)
 holds no golden vectors / KATs and cannot be compiled here (no rustc).
-The one published absolute value that exists for this path - 2*G1, EIP-2537 test vector
-"bls_g1add_(g1+g1=2*g1)" - is checked in tests/test_oracle.py (both tiers) and against the library.
+The published absolute values that exist for this path - 2*G1 and G1 + P1, EIP-2537 test vectors
+"bls_g1add_(g1+g1=2*g1)" and "bls_g1add_(g1+p1)" - are checked in tests/test_oracle.py (both tiers)
+and against the library.
 Beyond it values are pinned by mathematics: NTT outputs and the MSM group element are unique,
 and this file computes them by definition (O(N^2) DFT, double-and-add) so it is independent
 of the fast C restatement in oracle/c/ that it cross-checks.  The public constants below

@@ -560,6 +560,12 @@ TWO_G1_PUBLISHED = (0x0572CBEA904D67468808C8EB50A9450C9721DB309128012543902D0AC3
                     0x166A9D8CABC673A322FDA673779D8E3822BA3ECB8670E461F73BB9021D5FD76A4C56D9D4CD16BD1BBA86881979749D28)
 
 
+P1_EIP2537 = (0x112B98340EEE2777CC3C14163DEA3EC97977AC3DC5C70DA32E6E87578F44912E902CCEF9EFE28D4A78B8999DFBCA9426,
+              0x186B28D92356C4DFEC4B5201AD099DBDEDE3781F8998DDF929B4CD7756192185CA7B8F4EF7088F813270AC3D48868A21)
+G1_PLUS_P1_PUBLISHED = (0x0A40300CE2DEC9888B60690E9A41D3004FDA4886854573974FAB73B046D3147BA5B7A5BDE85279FFEDE1B45B3918D82D,
+                        0x06D3D887E9F53B9EC4EB6CEDF5607226754B07C01ACE7834F57F3E7315FAEFB739E59018E22C492006190FBA4A870025)
+
+
 def check_published_vector(orc, make_ctx):
     """The library against the one PUBLISHED absolute value on this path: 2*G1 (EIP-2537 "bls_g1add_(g1+g1=2*g1)").
     MSMs over copies of the generator must land on it whatever the bucket geometry."""
@@ -567,6 +573,14 @@ def check_published_vector(orc, make_ctx):
     gen = np.zeros(104, dtype=np.uint8)
     orc.lib().orc_g1_generator(gen.ctypes.data)
     ctx = make_ctx()
+    # G1 + P1 (EIP-2537 "bls_g1add_(g1+p1)") as an MSM with unit scalars, alone and inside a longer SRS
+    p1 = np.frombuffer(B.g1_affine_to_bytes(P1_EIP2537), dtype=np.uint8)
+    for n in (2, 2500):
+        bases = np.stack([gen, p1] + [gen] * (n - 2))
+        ctx.init(bases, 1 << 4, 1 << 7)
+        sc = np.zeros((n, 4), dtype=np.uint64)
+        sc[0, 0] = sc[1, 0] = 1
+        assert B.g1_affine_from_bytes(orc.normalize(ctx.msm(0, n, sc)).tobytes()) == G1_PLUS_P1_PUBLISHED, f"G+P1, n={n}"
     for n in (1, 2, 40, 3000):
         ctx.init(np.stack([gen] * n), 1 << 4, 1 << 7)
         sc = np.zeros((n, 4), dtype=np.uint64)

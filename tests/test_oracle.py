@@ -37,6 +37,21 @@ TWO_G1 = (0x0572CBEA904D67468808C8EB50A9450C9721DB309128012543902D0AC358A62AE28F
           0x166A9D8CABC673A322FDA673779D8E3822BA3ECB8670E461F73BB9021D5FD76A4C56D9D4CD16BD1BBA86881979749D28)
 
 
+# EIP-2537 test vector "bls_g1add_(g1+p1)": the second test point of that suite and its sum with the generator
+P1_EIP2537 = (0x112B98340EEE2777CC3C14163DEA3EC97977AC3DC5C70DA32E6E87578F44912E902CCEF9EFE28D4A78B8999DFBCA9426,
+              0x186B28D92356C4DFEC4B5201AD099DBDEDE3781F8998DDF929B4CD7756192185CA7B8F4EF7088F813270AC3D48868A21)
+G1_PLUS_P1 = (0x0A40300CE2DEC9888B60690E9A41D3004FDA4886854573974FAB73B046D3147BA5B7A5BDE85279FFEDE1B45B3918D82D,
+              0x06D3D887E9F53B9EC4EB6CEDF5607226754B07C01ACE7834F57F3E7315FAEFB739E59018E22C492006190FBA4A870025)
+
+
+def test_published_addition_vector(orc):
+    assert B.g1_is_on_curve(P1_EIP2537) and B.g1_mul(P1_EIP2537, B.FR_MOD) is None
+    assert B.g1_add(B.G1_GEN, P1_EIP2537) == G1_PLUS_P1
+    bases = np.stack([np.frombuffer(B.g1_affine_to_bytes(pt), dtype=np.uint8) for pt in (B.G1_GEN, P1_EIP2537)])
+    one = np.array([1, 0, 0, 0], dtype=np.uint64)
+    assert B.g1_affine_from_bytes(orc.normalize(orc.msm(bases, np.stack([one, one]))).tobytes()) == G1_PLUS_P1
+
+
 def test_published_doubling_vector(orc):
     assert B.g1_add(B.G1_GEN, B.G1_GEN) == TWO_G1 and B.g1_mul(B.G1_GEN, 2) == TWO_G1
     gen = np.zeros(104, dtype=np.uint8)

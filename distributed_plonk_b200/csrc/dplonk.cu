@@ -1234,7 +1234,6 @@ int dp_fft_init(dp_ctx *ctx, uint64_t id, const dp_fft_workload *workloads, size
     if (!ctx || !workloads) return fail(ctx, DP_E_ARG, "dp_fft_init: NULL argument");
     if (!ctx->inited) return fail(ctx, DP_E_STATE, "dp_fft_init before dp_init");
     if (n_workloads != ctx->W) return fail(ctx, DP_E_ARG, "dp_fft_init: %zu workloads for %llu workers", n_workloads, (unsigned long long)ctx->W);
-    if (ctx->tasks.count(id)) return fail(ctx, DP_E_STATE, "dp_fft_init: task %llu already open", (unsigned long long)id);
     DP_CUDA(ctx, cudaSetDevice(ctx->device));
     const DomainDev &d = ctx->dom[is_quot ? 1 : 0];
     const uint64_t r = d.r(), c = d.c(), W = ctx->W;
@@ -1242,6 +1241,15 @@ int dp_fft_init(dp_ctx *ctx, uint64_t id, const dp_fft_workload *workloads, size
         const dp_fft_workload &x = workloads[w];
         if (x.row_start != w * r / W || x.row_end != (w + 1) * r / W || x.col_start != w * c / W || x.col_end != (w + 1) * c / W)
             return fail(ctx, DP_E_ARG, "dp_fft_init: workload %llu is not the equal block split of %llu x %llu", (unsigned long long)w, (unsigned long long)r, (unsigned long long)c);
+    }
+    if (FftTask *old_task = find_task(ctx, id)) {
+        // `fft_tasks.insert(id, ..)` (worker.rs:215) replaces an open task with the same id: drop it, once
+        // nothing of it is in flight any more
+        cudaStreamSynchronize(ctx->s_in);
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->s_out);
+        free_task(ctx, *old_task);
+        ctx->tasks.erase(id);
     }
     FftTask t;
     t.is_quot = is_quot != 0;

@@ -106,8 +106,9 @@ int dp_msm_collect(dp_ctx *ctx, uint64_t id, void *out144);
 int dp_commit(dp_ctx *ctx, const void *coeffs, size_t n, void *out);
 
 /* ---- PlonkSlave.fftInit (src/worker.rs:187-233) ----------------------------------------------
- * Opens task `id`.  workloads[w] is worker w's row / column range; n_workloads must equal
- * n_workers and the ranges must tile [0,r) x [0,c) in equal power-of-two blocks. */
+ * Opens task `id` (an open task with the same id is replaced, as `fft_tasks.insert` does).
+ * workloads[w] is worker w's row / column range; n_workloads must equal n_workers and the ranges
+ * must tile [0,r) x [0,c) in equal power-of-two blocks. */
 int dp_fft_init(dp_ctx *ctx, uint64_t id, const dp_fft_workload *workloads, size_t n_workloads, int is_quot,
                 int is_inv, int is_coset);
 

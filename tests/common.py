@@ -612,6 +612,9 @@ def check_fft1_row_lengths(orc, worker: PlonkSlave, domain_log: int, is_quot: bo
     assert not rows[:, keep:].any()
     wl = disp.fft_workloads(domain_log, 1)
     for tid, (inv, cos) in enumerate(FLAG_COMBOS):
+        if tid == 0:             # an abandoned task under the same id is simply replaced (fft_tasks.insert)
+            worker.fft_init(9100, wl, is_quot, not inv, cos)
+            worker.fft1(9100, 0, chunks(orc.gen_fr(seed + 99, c)))
         worker.fft_init(9100 + tid, wl, is_quot, inv, cos)
         for j in range(r):
             if j % 3 == 0:       # full row

@@ -282,8 +282,8 @@ def test_error_behaviour(orc, emul_lib):
     c.init(np.zeros(0, dtype=np.uint8), 1 << 4, 1 << 7)
     wl = [(0, 4, 0, 4)]
     c.fft_init(1, wl, False, False, False)
-    with pytest.raises(DpError):
-        c.fft_init(1, wl, False, False, False)     # duplicate id
+    c.fft1(1, 0, np.ones((4, 4), dtype=np.uint64))
+    c.fft_init(1, wl, False, False, False)         # same id again: the task is replaced (fft_tasks.insert, worker.rs:215)
     c.fft1(1, 0, np.zeros((3, 4), dtype=np.uint64))       # a short row is zero-extended (fft_in_place resizes)
     with pytest.raises(DpError) as e:
         c.fft1(1, 4, np.zeros((4, 4), dtype=np.uint64))   # row index outside the worker's range

@@ -4,6 +4,8 @@
 // operation that contributes to a result runs in a CUDA kernel.
 #include "../../include/dplonk.h"
 
+#include <sys/random.h>
+
 #include <cstdarg>
 #include <cstdio>
 #include <map>
@@ -147,12 +149,12 @@ struct dp_ctx {
     std::map<uint64_t, FftTask> tasks;
     Fr *wire = nullptr;
     uint64_t wire_len = 0;
-    uint64_t rng_state = 0x9E3779B97F4A7C15ull;
     // fused peer-memory exchange (dp_peer_arena_create / dp_peer_attach)
     Fr *arena = nullptr;            // my receive arena: two slots, alternating per exchange
     uint64_t arena_bytes = 0;
     Fr *peer_arena[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     uint64_t p2p_seq = 0;           // exchanges issued so far; must advance identically on every rank
+    bool p2p_slot_busy[2] = {false, false};  // receive slot written by a row phase whose column phase has not consumed it yet
     uint32_t bar_seq = 0;           // device-side barriers issued so far (p2p_barrier_kernel)
     // worker-resident polynomials (dp_poly_*): id -> device buffer of `cap` Fr, zero beyond what was written
     struct Poly {
@@ -582,7 +584,9 @@ void free_domain(dp_ctx *ctx, DomainDev &d) {
 }
 
 // only called when every stream is done with the task (after the D2H of dp_fft2, or at dp_init)
+void p2p_release_slot(dp_ctx *ctx, const Fr *slot);
 void free_task(dp_ctx *ctx, FftTask &t) {
+    if (t.p2p) p2p_release_slot(ctx, t.recv);
     if (t.recv && t.recv != t.send && !t.p2p) ctx->pool.release(t.recv);
     if (t.send && t.send != t.rows) ctx->pool.release(t.send);
     ctx->pool.release(t.cols);
@@ -750,15 +754,33 @@ bool p2p_ready(const dp_ctx *ctx) {
     return true;
 }
 
-// receive slot of the next exchange in every rank's arena (same sequence number on all ranks)
+// Receive slot of the next exchange in every rank's arena (same sequence number on all ranks).  The arena
+// holds TWO slots, so at most two fused exchanges may be between their row phase and their column phase per
+// context: a third one would overwrite a receive matrix nobody has read yet.  The slot is only reserved here;
+// p2p_commit_slot() consumes the sequence number once the row kernels were queued without error, so a
+// failed call leaves every rank's sequence where it was.
 int p2p_next_slot(dp_ctx *ctx, uint64_t recv_bytes, PeerDst &dst, Fr *&my_slot, uint64_t row_off) {
     const uint64_t slot_bytes = (ctx->arena_bytes - ARENA_HEADER_BYTES) / 2;
     if (recv_bytes > slot_bytes) return fail(ctx, DP_E_COMM, "peer arena slot %llu B < receive matrix %llu B", (unsigned long long)slot_bytes, (unsigned long long)recv_bytes);
-    const uint64_t off = ARENA_HEADER_BYTES / sizeof(Fr) + (ctx->p2p_seq++ & 1) * (slot_bytes / sizeof(Fr));
+    const uint64_t s = ctx->p2p_seq & 1;
+    if (ctx->p2p_slot_busy[s])
+        return fail(ctx, DP_E_STATE, "fused exchange: both receive slots hold transforms whose column phase has not run (at most 2 "
+                                     "between fft2_prepare and fft2 per context); finish one with dp_fft2 or use dp_fft_exchange_begin/_end");
+    const uint64_t off = ARENA_HEADER_BYTES / sizeof(Fr) + s * (slot_bytes / sizeof(Fr));
     for (uint64_t q = 0; q < ctx->W; q++) dst.base[q] = ctx->peer_arena[q] + off;
     dst.row_off = row_off;
     my_slot = ctx->arena + off;
     return DP_OK;
+}
+void p2p_commit_slot(dp_ctx *ctx) {
+    ctx->p2p_slot_busy[ctx->p2p_seq & 1] = true;
+    ctx->p2p_seq++;
+}
+void p2p_release_slot(dp_ctx *ctx, const Fr *slot) {
+    if (!slot || !ctx->arena) return;
+    const uint64_t slot_elems = (ctx->arena_bytes - ARENA_HEADER_BYTES) / 2 / sizeof(Fr);
+    const uint64_t s = (uint64_t)(slot - (ctx->arena + ARENA_HEADER_BYTES / sizeof(Fr))) / slot_elems;
+    if (s < 2) ctx->p2p_slot_busy[s] = false;
 }
 
 int run_row_phase(dp_ctx *ctx, FftTask &t, bool use_p2p = false) {
@@ -772,19 +794,20 @@ int run_row_phase(dp_ctx *ctx, FftTask &t, bool use_p2p = false) {
         if (!scratch) return fail(ctx, DP_E_OOM, "row-phase scratch");
     }
     PeerDst peers;
+    Fr *slot = nullptr;
     if (use_p2p) {
         // block q of my rows goes straight to rows [me*n_rows, ...) of worker q's receive matrix
-        Fr *slot = nullptr;
         int rc0 = p2p_next_slot(ctx, d.r() * t.n_cols * sizeof(Fr), peers, slot, ctx->me * t.n_rows * t.n_cols);
         if (rc0 != DP_OK) {
             ctx->pool.release(scratch);
             return rc0;
         }
-        t.recv = slot;
-        t.p2p = true;
     } else if (ctx->W > 1 && !t.send) {
         t.send = (Fr *)ctx->pool.alloc(t.n_rows * c * sizeof(Fr));
-        if (!t.send) return fail(ctx, DP_E_OOM, "exchange send buffer");
+        if (!t.send) {
+            ctx->pool.release(scratch);
+            return fail(ctx, DP_E_OOM, "exchange send buffer");
+        }
     } else if (ctx->W == 1) {
         t.send = t.rows;
     }
@@ -792,13 +815,22 @@ int run_row_phase(dp_ctx *ctx, FftTask &t, bool use_p2p = false) {
     int rc = plan_row_phase(ctx, d, t.rows, t.send, scratch, t.n_rows, t.row_start, t.is_inv, t.is_coset, ctx->W,
                             use_p2p ? &peers : nullptr);
     ctx->pool.release(scratch);
-    if (rc == DP_OK) t.row_phase_done = true;
+    if (rc == DP_OK) {
+        t.row_phase_done = true;
+        if (use_p2p) {
+            t.recv = slot;
+            t.p2p = true;
+            p2p_commit_slot(ctx);
+        }
+    }
     return rc;
 }
 
 // queue the column phase of a task whose recv matrix is complete; result lands in t.cols
 int queue_col_phase(dp_ctx *ctx, FftTask &t) {
     const DomainDev &d = ctx->dom[t.is_quot ? 1 : 0];
+    // the two-pass column plan works in place on `recv`: running it twice would transform garbage
+    if (t.exchanged) return fail(ctx, DP_E_STATE, "fft task: the column phase of this task was already queued");
     if (!t.cols) {
         t.cols = (Fr *)ctx->pool.alloc(t.n_cols * d.r() * sizeof(Fr));
         if (!t.cols) return fail(ctx, DP_E_OOM, "column buffer");
@@ -1458,11 +1490,14 @@ int dp_fft_dev_cols(dp_ctx *ctx, void *cols_dev) {
     const DomainDev &d = ctx->dom[(f & 4) ? 1 : 0];
     const uint64_t n_cols = d.c() / ctx->W;
     call_begin(ctx);
-    Fr *src = ctx->dev_p2p_slot ? ctx->dev_p2p_slot : (ctx->W > 1 ? ctx->dev_recv : ctx->dev_send);
+    Fr *p2p_slot = ctx->dev_p2p_slot;
+    Fr *src = p2p_slot ? p2p_slot : (ctx->W > 1 ? ctx->dev_recv : ctx->dev_send);
     ctx->dev_p2p_slot = nullptr;
-    DP_TRY(plan_col_phase(ctx, d, src, (Fr *)cols_dev, n_cols, ctx->me * n_cols, (f & 2) != 0, (f & 1) != 0));
     ctx->dev_flags = -1;
-    return call_end(ctx, true);
+    int rc = plan_col_phase(ctx, d, src, (Fr *)cols_dev, n_cols, ctx->me * n_cols, (f & 2) != 0, (f & 1) != 0);
+    if (rc == DP_OK) rc = call_end(ctx, true);
+    p2p_release_slot(ctx, p2p_slot);  // read (or given up): peers may store the next exchange into it
+    return rc;
 }
 
 static int ntt_device(dp_ctx *ctx, Fr *x, uint32_t log_n, bool is_inv, bool is_coset) {
@@ -1550,18 +1585,21 @@ int dp_round1(dp_ctx *ctx, const void *evals, size_t n, const void *blind, void 
     Fr b[2];
     if (blind) {
         memcpy(b, blind, sizeof b);
-    } else {  // SplitMix64-driven blinders (the reference uses ThreadRng: not reproducible either way)
+    } else {
+        // The reference blinds with ThreadRng, a CSPRNG (worker.rs:400): the two scalars must be unpredictable,
+        // so they come from the kernel's entropy pool: uniform canonical residues < r by rejection (r is 255
+        // bits: one try in ~2.2 is rejected).  Any residue < r is a valid Montgomery-form element.
         for (int k = 0; k < 2; k++) {
-            Fr v = Fr::zero();
-            for (int w = 0; w < 8; w += 2) {
-                uint64_t z = (ctx->rng_state += 0x9E3779B97F4A7C15ull);
-                z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-                z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-                z ^= z >> 31;
-                v.l[w] = (uint32_t)z;
-                v.l[w + 1] = (uint32_t)(z >> 32);
-            }
-            v.l[7] &= 0x3fffffffu;  // < 2^254 < r: already a valid (Montgomery-form) residue
+            Fr v;
+            do {
+                size_t got = 0;
+                while (got < sizeof(Fr)) {
+                    const ssize_t r = getrandom(reinterpret_cast<uint8_t *>(v.l) + got, sizeof(Fr) - got, 0);
+                    if (r < 0) return fail(ctx, DP_E_STATE, "dp_round1: getrandom failed; pass the blinders in `blind`");
+                    got += (size_t)r;
+                }
+                v.l[7] &= 0x7fffffffu;
+            } while (!v.canon_is_reduced());
             b[k] = v;
         }
     }
@@ -1746,7 +1784,10 @@ int dp_fft_dev_rows_p2p(dp_ctx *ctx, const void *rows_dev, int is_quot, int is_i
     Scratch tmp(ctx->pool);
     Fr *scratch = need_scratch ? tmp.get<Fr>(n_rows * c) : nullptr;
     if (need_scratch && !scratch) return fail(ctx, DP_E_OOM, "dp_fft_dev_rows_p2p scratch");
+    if (ctx->dev_p2p_slot) return fail(ctx, DP_E_STATE, "dp_fft_dev_rows_p2p: the previous transform still waits for dp_fft_dev_cols");
     DP_TRY(plan_row_phase(ctx, d, (const Fr *)rows_dev, nullptr, scratch, n_rows, ctx->me * n_rows, is_inv != 0, is_coset != 0, W, &peers));
+    p2p_commit_slot(ctx);
+    ctx->dev_p2p_slot = slot;
     DP_TRY(call_end(ctx, true));
     ctx->pool.release(ctx->dev_send);
     ctx->pool.release(ctx->dev_recv);
@@ -1774,6 +1815,12 @@ int dp_fft_dev_p2p(dp_ctx *ctx, const void *rows_dev, void *cols_dev, int is_quo
     Fr *scratch = need_scratch ? tmp.get<Fr>(n_rows * c) : nullptr;
     if (need_scratch && !scratch) return fail(ctx, DP_E_OOM, "dp_fft_dev_p2p scratch");
     DP_TRY(plan_row_phase(ctx, d, (const Fr *)rows_dev, nullptr, scratch, n_rows, ctx->me * n_rows, is_inv != 0, is_coset != 0, W, &peers));
+    p2p_commit_slot(ctx);
+    struct SlotGuard {  // the slot is free again once this call returns: the column kernels read it before the stream drains
+        dp_ctx *c;
+        Fr *s;
+        ~SlotGuard() { p2p_release_slot(c, s); }
+    } slot_guard{ctx, slot};
     PeerCounters pc;
     for (uint64_t q = 0; q < 8; q++) pc.c[q] = q < W ? reinterpret_cast<uint32_t *>(ctx->peer_arena[q]) : nullptr;
     ctx->bar_seq++;
@@ -1979,6 +2026,12 @@ static int poly_div_any(dp_ctx *ctx, const void *coeffs, size_t n, const void *p
     if (n == 0) {
         if (rem32) memset(rem32, 0, sizeof(Fr));
         return DP_OK;
+    }
+    if (on_device && n > 1) {
+        // blocks of poly_suffix_kernel read coefficients that other blocks' quotient stores may already have
+        // replaced: the quotient cannot be written over (or into) the dividend
+        const uintptr_t a0 = (uintptr_t)coeffs, a1 = a0 + n * sizeof(Fr), b0 = (uintptr_t)out, b1 = b0 + (n - 1) * sizeof(Fr);
+        if (a0 < b1 && b0 < a1) return fail(ctx, DP_E_ARG, "%s: out_dev overlaps coeffs_dev (in-place division is not supported)", who);
     }
     DP_CUDA(ctx, cudaSetDevice(ctx->device));
     call_begin(ctx);

@@ -124,6 +124,8 @@ class PlonkImpl {
         return out;
     }
     // round1 @6 (w :List(Data)) -> (c :Data)                                        worker.rs:383-408
+    // blind_2fr: two uniformly random secret Fr (the reference draws them from ThreadRng); nullptr = the
+    // library draws them from the operating system's entropy pool (getrandom), never from a fixed seed
     Bytes round1(const ListData &w, const uint8_t *blind_2fr = nullptr) {
         Bytes e = concat(w), out(DP_G1_PROJECTIVE_BYTES);
         check(dp_round1(ctx_, e.data(), e.size() / DP_FR_BYTES, blind_2fr, out.data()));

@@ -86,6 +86,7 @@ class PlonkSlave:
 
     # round1 @6 (w :List(Data)) -> (c :Data)                               worker.rs:383-408
     def round1(self, w, blind=None) -> bytes:
+        """blind: two secret uniformly random Fr (tests inject them); None = drawn by the library from getrandom(2)"""
         return self.ctx.round1(concat(w), blind).tobytes()
 
     def close(self):

@@ -158,8 +158,10 @@ int dp_ntt(dp_ctx *ctx, void *data, size_t n, uint32_t log_n, int is_inv, int is
 
 /* ---- PlonkSlave.round1 (src/worker.rs:383-408) -----------------------------------------------
  * evals (n Fr) -> ifft -> wire = (b0 + b1*X) * (X^n - 1) + poly -> commitment.  The reference
- * draws b0,b1 from the worker's ThreadRng; pass them in `blind` (2 raw Fr) to make the call
- * reproducible, or NULL for an internally generated pair.  The blinded polynomial stays resident
+ * draws b0,b1 from the worker's ThreadRng (a CSPRNG): pass two secret, uniformly random Fr from the
+ * host's own RNG in `blind` (2 raw Fr; also what makes the call reproducible in tests), or NULL to let
+ * the library draw them from the operating system's entropy pool (getrandom(2), rejection-sampled
+ * below r; DP_E_STATE if that source is unavailable).  The blinded polynomial stays resident
  * (state.wire, worker.rs:58) and can be read back with dp_get_wire. */
 int dp_round1(dp_ctx *ctx, const void *evals, size_t n, const void *blind, void *out);
 int dp_get_wire(dp_ctx *ctx, void *out, size_t out_bytes, size_t *n_coeffs);
@@ -215,7 +217,8 @@ int dp_poly_lincomb_dev(dp_ctx *ctx, const void *const *polys_dev, const size_t 
                         size_t out_len);
 
 /* Round 5, the opening witnesses (src/dispatcher2.rs:651-666, 672-688): the n-1 coefficients of
- * p(X) / (X - point) into out, and the remainder p(point) into rem32 when it is not NULL.          */
+ * p(X) / (X - point) into out, and the remainder p(point) into rem32 when it is not NULL.
+ * out_dev must not overlap coeffs_dev (DP_E_ARG): the division is not done in place.              */
 int dp_poly_div_linear(dp_ctx *ctx, const void *coeffs, size_t n, const void *point, void *out, void *rem32);
 int dp_poly_div_linear_dev(dp_ctx *ctx, const void *coeffs_dev, size_t n, const void *point, void *out_dev, void *rem32);
 
@@ -241,6 +244,10 @@ int dp_commit_dev(dp_ctx *ctx, const void *coeffs_dev, size_t n, void *out144);
  * arenas over NVLink (two slots, alternating per exchange: every rank must issue its exchanges in
  * the same order) and returns when its stores are complete; the caller provides the barrier across
  * ranks between fft2Prepare and fft2 - the dispatcher's join over the fft2Prepare replies is one.
+ * In-flight limit: the arena holds TWO receive slots, so at most two tasks per context may sit between
+ * dp_fft2_prepare and dp_fft2 on the fused path; a third dp_fft2_prepare returns DP_E_STATE (nothing is
+ * consumed: call dp_fft2 on an earlier task, then retry - or use dp_fft_exchange_begin/_end, which has
+ * per-task buffers and no limit).  The slot sequence only advances on success, identically on all ranks.
  * arena_bytes >= 2 * (r * c / n_workers) * 32 for the largest domain. */
 #define DP_IPC_HANDLE_BYTES 64
 int dp_peer_arena_create(dp_ctx *ctx, uint64_t arena_bytes, void *handle_out /* DP_IPC_HANDLE_BYTES */);

@@ -8,7 +8,8 @@ import numpy as np
 import pytest
 
 from distributed_plonk_b200._binding import Context, DpError
-from distributed_plonk_b200.worker import PlonkSlave
+from distributed_plonk_b200 import dispatcher as disp
+from distributed_plonk_b200.worker import PlonkSlave, chunks
 from tests import common
 
 
@@ -298,3 +299,100 @@ def test_error_behaviour(orc, emul_lib):
     c.close()
     with pytest.raises(DpError):
         Context(emul_lib, 0, 2, 2)                 # me >= n_workers
+
+
+def test_round1_default_blinders_come_from_the_os(orc, emul_lib):
+    """blind = NULL: the two blinders are drawn from getrandom(2) (the reference uses ThreadRng, worker.rs:400):
+    different between calls and between contexts, canonical residues, and the commitment still opens to
+    the blinded polynomial"""
+    bases = orc.gen_bases(5, 80, 64, True)
+    n = 1 << 6
+    evals = orc.gen_fr(22, n, True)
+    poly = orc.fft(evals, True, False)
+    L = orc.lib()
+    seen = set()
+    for _ in range(2):
+        c = Context(emul_lib, 0, 0, 1)
+        c.init(bases, n, 1 << 9)
+        for _ in range(2):
+            got = c.round1(evals, None)
+            wire = c.get_wire()
+            b = wire[n:n + 2]
+            for k in range(2):
+                v = sum(int(b[k, i]) << (64 * i) for i in range(4))
+                assert v < common.R_MOD
+                seen.add(v)
+                t = np.zeros(4, dtype=np.uint64)
+                L.orc_fr_sub(poly[k].ctypes.data, b[k].ctypes.data, t.ctypes.data)
+                assert np.array_equal(wire[k], t)
+            common.assert_point_eq(orc, got, orc.commit(bases, wire), "round1 commitment (library blinders)")
+        c.close()
+    assert len(seen) == 8                                      # 2 contexts x 2 calls x 2 blinders, all distinct
+
+
+def test_fused_exchange_in_flight_limit(orc, emul_lib):
+    """two receive slots per arena: a third fft2_prepare before any fft2 is refused (DP_E_STATE) without
+    consuming a slot; after an fft2 it goes through and every task still yields the right transform"""
+    W, L = 2, 9
+    workers = [PlonkSlave(emul_lib, p, W) for p in range(W)]
+    for w in workers:
+        w.init([b""], 1 << 6, 1 << L)
+    common.attach_in_process(workers, 2 * (1 << L) * 32 // W)
+    wl = disp.fft_workloads(L, W)
+    xs = [orc.gen_fr(700 + t, 1 << L) for t in range(3)]
+    for t in range(3):
+        rows = disp.dispatcher_rows(xs[t], L)
+        for p, w in enumerate(workers):
+            w.fft_init(t, wl, True, False, True)
+            for j in range(wl[p][1] - wl[p][0]):
+                w.fft1(t, j, chunks(rows[wl[p][0] + j]))
+    for t in range(2):
+        for w in workers:
+            w.fft2_prepare(t)
+    for w in workers:
+        with pytest.raises(DpError) as e:
+            w.fft2_prepare(2)
+        assert e.value.code == -2
+    outs = {}
+    outs[0] = [w.fft2_array(0) for w in workers]              # frees slot 0 on every worker
+    for w in workers:
+        w.fft2_prepare(2)
+    for t in (1, 2):
+        outs[t] = [w.fft2_array(t) for w in workers]
+    for t in range(3):
+        got = disp.assemble(np.concatenate(outs[t], axis=0))
+        assert np.array_equal(got, orc.fft(xs[t], False, True)), f"task {t}"
+    for w in workers:
+        w.close()
+
+
+def test_exchange_end_twice_and_in_place_division_are_refused(orc, emul_lib):
+    W, L = 2, 9
+    workers = [PlonkSlave(emul_lib, p, W) for p in range(W)]
+    for w in workers:
+        w.init([b""], 1 << 6, 1 << L)
+        w.ctx.debug_set_limits(3, 2, 0)                        # two-pass column plan: works in place on recv
+    x = orc.gen_fr(720, 1 << L)
+    wl = disp.fft_workloads(L, W)
+    rows = disp.dispatcher_rows(x, L)
+    for p, w in enumerate(workers):
+        w.fft_init(5, wl, True, False, False)
+        for j in range(wl[p][1] - wl[p][0]):
+            w.fft1(5, j, chunks(rows[wl[p][0] + j]))
+    for dst, src, n in common.local_exchange([w.ctx for w in workers], 5):
+        host_copy(dst, src, n)
+    for w in workers:
+        with pytest.raises(DpError) as e:
+            w.ctx.fft_exchange_end(5)                          # the column phase was queued once already
+        assert e.value.code == -2
+    got = disp.assemble(np.concatenate([w.fft2_array(5) for w in workers], axis=0))
+    assert np.array_equal(got, orc.fft(x, False, False))
+    # dp_poly_div_linear_dev: quotient over the dividend -> DP_E_ARG
+    c = workers[0].ctx
+    p = np.ascontiguousarray(orc.gen_fr(721, 5000))
+    pt = orc.gen_fr(722, 1)[0]
+    with pytest.raises(DpError) as e:
+        c.poly_div_linear(p.ctypes.data, pt, 5000, p.ctypes.data)
+    assert e.value.code == -1
+    for w in workers:
+        w.close()

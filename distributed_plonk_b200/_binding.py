@@ -17,7 +17,7 @@ EXPORTS = [
     "dp_quotient_evals", "dp_quotient_evals_dev", "dp_poly_eval", "dp_poly_eval_dev", "dp_poly_lincomb", "dp_poly_lincomb_dev",
     "dp_poly_div_linear", "dp_poly_div_linear_dev", "dp_init_compressed", "dp_get_bases",
     "dp_msm_submit", "dp_msm_collect", "dp_poly_put", "dp_poly_ptr", "dp_poly_get", "dp_poly_free", "dp_commit_dev",
-    "dp_fft_exchange_begin_async", "dp_compute_stream",
+    "dp_fft_exchange_begin_async", "dp_compute_stream", "dp_fft_dev_p2p_async", "dp_fft1_rows_short", "dp_fft_dev_hint_valid_cols", "dp_ntt_dev_padded",
 ]
 
 
@@ -51,6 +51,7 @@ def bind(cdll: C.CDLL) -> C.CDLL:
         "dp_fft_init": (i, [vp, u64, C.POINTER(FftWorkload), sz, i, i, i]),
         "dp_fft1": (i, [vp, u64, u64, vp, sz]),
         "dp_fft1_rows": (i, [vp, u64, u64, u64, vp]),
+        "dp_fft1_rows_short": (i, [vp, u64, u64, u64, vp, sz]),
         "dp_fft2_prepare": (i, [vp, u64]),
         "dp_fft_exchange_begin": (i, [vp, u64, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]),
         "dp_fft_exchange_end": (i, [vp, u64]),
@@ -67,6 +68,7 @@ def bind(cdll: C.CDLL) -> C.CDLL:
         "dp_sync": (i, [vp]),
         "dp_msm_dev": (i, [vp, u64, u64, vp, sz, vp]),
         "dp_ntt_dev": (i, [vp, vp, u32, i, i]),
+        "dp_ntt_dev_padded": (i, [vp, vp, sz, C.c_uint32, i, i, i]),
         "dp_fft_dev": (i, [vp, vp, vp, i, i, i]),
         "dp_debug_set_limits": (i, [vp, u32, u32, i]),
         "dp_last_msm_breakdown": (i, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
@@ -80,6 +82,8 @@ def bind(cdll: C.CDLL) -> C.CDLL:
         "dp_msm_dev_batch": (i, [vp, sz, C.POINTER(u64), C.POINTER(u64), C.POINTER(vp), C.POINTER(sz), C.POINTER(vp)]),
         "dp_fft_dev_rows_p2p": (i, [vp, vp, i, i, i]),
         "dp_fft_dev_p2p": (i, [vp, vp, vp, i, i, i]),
+        "dp_fft_dev_p2p_async": (i, [vp, vp, vp, i, i, i]),
+        "dp_fft_dev_hint_valid_cols": (i, [vp, i, u64]),
         "dp_poly_put": (i, [vp, u64, vp, sz, sz]),
         "dp_poly_ptr": (i, [vp, u64, C.POINTER(vp), C.POINTER(sz)]),
         "dp_poly_get": (i, [vp, u64, sz, sz, vp]),
@@ -174,6 +178,10 @@ class Context:
     def fft1_rows(self, task_id: int, i_first: int, rows: np.ndarray, n_rows: int):
         rows = np.ascontiguousarray(rows)
         self._ck(self.lib.dp_fft1_rows(self.h, task_id, i_first, n_rows, _addr(rows)))
+
+    def fft1_rows_short(self, task_id: int, i_first: int, rows, n_rows: int, row_len: int):
+        """n_rows rows of row_len leading entries each (compact array or host address); the tails are implicit zeros"""
+        self._ck(self.lib.dp_fft1_rows_short(self.h, task_id, i_first, n_rows, _addr(rows), row_len))
 
     def fft2_prepare(self, task_id: int):
         self._ck(self.lib.dp_fft2_prepare(self.h, task_id))
@@ -389,8 +397,15 @@ class Context:
     def ntt_dev(self, data_ptr: int, log_n: int, is_inv: bool, is_coset: bool):
         self._ck(self.lib.dp_ntt_dev(self.h, data_ptr, log_n, int(is_inv), int(is_coset)))
 
+    def ntt_dev_padded(self, data_ptr: int, n_valid: int, log_n: int, is_inv: bool, is_coset: bool, wait: bool = True):
+        """in place on 2^log_n Fr at data_ptr whose entries from n_valid on are zero"""
+        self._ck(self.lib.dp_ntt_dev_padded(self.h, data_ptr, n_valid, log_n, int(is_inv), int(is_coset), int(wait)))
+
     def fft_dev(self, rows_ptr: int, cols_ptr: int, is_quot: bool, is_inv: bool, is_coset: bool):
         self._ck(self.lib.dp_fft_dev(self.h, rows_ptr, cols_ptr, int(is_quot), int(is_inv), int(is_coset)))
+
+    def fft_dev_hint_valid_cols(self, is_quot: bool, valid_cols: int):
+        self._ck(self.lib.dp_fft_dev_hint_valid_cols(self.h, int(is_quot), valid_cols))
 
     def fft_dev_rows(self, rows_ptr: int, is_quot: bool, is_inv: bool, is_coset: bool):
         s, r, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
@@ -415,6 +430,9 @@ class Context:
     def fft_dev_p2p(self, rows_ptr: int, cols_ptr: int, is_quot: bool, is_inv: bool, is_coset: bool):
         self._ck(self.lib.dp_fft_dev_p2p(self.h, rows_ptr, cols_ptr, int(is_quot), int(is_inv), int(is_coset)))
 
+    def fft_dev_p2p_async(self, rows_ptr: int, cols_ptr: int, is_quot: bool, is_inv: bool, is_coset: bool):
+        self._ck(self.lib.dp_fft_dev_p2p_async(self.h, rows_ptr, cols_ptr, int(is_quot), int(is_inv), int(is_coset)))
+
     def fft_dev_cols(self, cols_ptr: int):
         self._ck(self.lib.dp_fft_dev_cols(self.h, cols_ptr))
 
@@ -430,6 +448,14 @@ class Context:
         out = np.zeros((n, G1_AFFINE_BYTES), dtype=np.uint8)
         self._ck(self.lib.dp_debug_gen_bases(self.h, seed, n, _addr(out) if n else None))
         return out
+
+    def gen_bases_into(self, seed: int, n: int, out_ptr: int):
+        """the same, written to `out_ptr` (n * 104 B of host or device memory)"""
+        self._ck(self.lib.dp_debug_gen_bases(self.h, seed, n, out_ptr))
+
+    def init_ptr(self, bases_ptr: int, n_bases: int, domain_size: int, quot_domain_size: int):
+        """PlonkSlave.init with the raw GroupAffine array at `bases_ptr` (host or device memory)"""
+        self._ck(self.lib.dp_init(self.h, bases_ptr if n_bases else None, n_bases, domain_size, quot_domain_size))
 
     def sync(self):
         self._ck(self.lib.dp_sync(self.h))

@@ -95,6 +95,11 @@ struct DomainDev {
     Fr *gi_col = nullptr;  // g^-i / r, i < c           (inverse coset + 1/r, by global column)
     Fr *gi_pt = nullptr;   // g^-(c*j), j < r
     Fr c_inv, r_inv, n_inv;
+    // whole-domain (natural order) coset transforms: x[j] * g^j = wg_a[j mod 2^(L-l1)] * wg_b[j >> (L-l1)] on the way in,
+    // X[k] * g^-k / N = wgi_a[k mod 2^(L-ll)] * wgi_b[k >> (L-ll)] on the way out, for the pass split (l1 first, ll last)
+    // plan_whole_ntt uses; two small table reads and two products instead of one Fr::pow per element
+    Fr *wg_a = nullptr, *wg_b = nullptr, *wgi_a = nullptr, *wgi_b = nullptr;
+    uint32_t w_l1 = 0, w_ll = 0;
     uint64_t n() const { return (uint64_t)1 << log_n; }
     uint64_t r() const { return (uint64_t)1 << log_r; }
     uint64_t c() const { return (uint64_t)1 << log_c; }
@@ -109,7 +114,7 @@ struct FftTask {
     Fr *recv = nullptr;  // [r][n_cols] = W blocks of [r/W][n_cols] (aliases send when W == 1)
     Fr *cols = nullptr;  // [n_cols][r]  column-phase result, produced asynchronously after the exchange
     uint64_t rows_filled = 0;
-    std::vector<uint8_t> row_seen;
+    std::vector<uint32_t> row_len;  // 0 = not received; else columns handed in for that row (c: a whole row)
     bool row_phase_done = false, exchanged = false;
     bool p2p = false;  // rows were stored straight into the peers' arenas; column phase waits for fft2
     cudaEvent_t ev_in = nullptr;  // last fft1 H2D copy (copy-in stream)
@@ -169,6 +174,7 @@ struct dp_ctx {
     Fr *dev_send = nullptr, *dev_recv = nullptr;  // dp_fft_dev_rows / _cols staging (one transform in flight)
     Fr *dev_p2p_slot = nullptr;                   // receive slot of the last dp_fft_dev_rows_p2p
     int dev_flags = -1;
+    uint64_t dev_valid[2] = {0, 0};  // dp_fft_dev_hint_valid_cols: leading non-zero columns of the rows given to dp_fft_dev*
     // pass-planning limits (dp_debug_set_limits lowers them so small tests reach the multi-pass plans)
     uint32_t max_contig_log_k = NTT_WTAB_LOG, max_strided_log_k = NTT_MAX_STRIDED_LOG_K;
     uint32_t msm_chunk = 0;    // experiment knob (env DP_MSM_CHUNK): digits per accumulate thread, 0 = default
@@ -265,9 +271,25 @@ struct PeerDst {
     uint64_t row_off;
 };
 
+// Columns of a row the row phase reads when only the first `valid` hold data (the rest of the row is an
+// implicit zero tail, as for n coefficients on the 8n-point domain): a power-of-two count of whole passes'
+// points, so that the kernel can drop the butterfly stages whose upper input is zero (NttPass.in_zlog).
+uint64_t row_read_cols(const dp_ctx *ctx, const DomainDev &d, uint64_t valid) {
+    const uint64_t c = d.c();
+    if (valid >= c) return c;
+    if (valid == 0) valid = 1;
+    uint64_t unit = 1;  // columns per point of the first pass
+    if (d.log_c > ctx->max_contig_log_k) unit = (uint64_t)1 << (d.log_c - d.log_c / 2);
+    uint64_t pts = (valid + unit - 1) / unit, p2 = 1;
+    while (p2 < pts) p2 <<= 1;
+    return p2 * unit < c ? p2 * unit : c;
+}
+
 int plan_row_phase(dp_ctx *ctx, const DomainDev &d, const Fr *src, Fr *dst, Fr *scratch, uint64_t n_rows,
-                   uint64_t row_start, bool is_inv, bool is_coset, uint64_t W, const PeerDst *peers = nullptr) {
+                   uint64_t row_start, bool is_inv, bool is_coset, uint64_t W, const PeerDst *peers = nullptr,
+                   uint64_t rd_cols = 0 /* row_read_cols(); 0 = whole rows */) {
     const uint32_t lc = d.log_c;
+    if (rd_cols == 0 || rd_cols > d.c()) rd_cols = d.c();
     const uint64_t c = d.c();
     const uint32_t log_ncq = lc - log2_ceil_u64(W);
     const bool pre = is_coset && !is_inv;
@@ -295,6 +317,7 @@ int plan_row_phase(dp_ctx *ctx, const DomainDev &d, const Fr *src, Fr *dst, Fr *
         p.out = dst;
         p.log_k = lc;
         p.log_g = pick_log_g(lc, n_rows);
+        p.in_zlog = lc - log2_ceil_u64(rd_cols);
         p.in_ls = c;
         p.in_ps = 1;
         p.out_ls = W > 1 ? ((uint64_t)1 << log_ncq) : c;
@@ -321,6 +344,7 @@ int plan_row_phase(dp_ctx *ctx, const DomainDev &d, const Fr *src, Fr *dst, Fr *
         p.out = scratch;
         p.log_k = l1;
         p.log_g = pick_log_g(l1, L2);
+        p.in_zlog = rd_cols >= L2 ? l1 - log2_ceil_u64(rd_cols / L2) : l1;
         p.n_outer = (uint32_t)n_rows;
         p.in_os = p.out_os = c;
         p.in_ls = p.out_ls = 1;
@@ -437,16 +461,55 @@ int plan_col_phase(dp_ctx *ctx, const DomainDev &d, Fr *src, Fr *dst, uint64_t n
     }
 }
 
-// Whole-domain transform of 2^L elements: x (in place) with scratch of the same size.
+// pass split of a whole-domain transform of 2^L points: sub-transform sizes (first .. last), 1-3 passes, 0 = too large
+int whole_split(const dp_ctx *ctx, uint32_t L, uint32_t l[3]) {
+    l[0] = l[1] = l[2] = 0;
+    if (L <= ctx->max_contig_log_k) {
+        l[0] = L;
+        return 1;
+    }
+    if (L <= 2 * ctx->max_strided_log_k) {
+        l[0] = L / 2;
+        l[1] = L - l[0];
+        return 2;
+    }
+    if (L > 3 * ctx->max_strided_log_k) return 0;
+    l[0] = L / 3;
+    l[1] = (L - l[0]) / 2;
+    l[2] = L - l[0] - l[1];
+    return 3;
+}
+
+// Whole-domain transform of 2^L elements: x (in place) with scratch of the same size.  n_valid: x[n_valid..) is
+// zero (a coefficient vector shorter than the domain): the first pass then reads and multiplies only what is there.
 int plan_whole_ntt(dp_ctx *ctx, const DomainDev *d, Fr *x, Fr *scratch, uint32_t L, bool is_inv, bool is_coset,
-                   const Fr *H, uint32_t H_log_n) {
+                   const Fr *H, uint32_t H_log_n, uint64_t n_valid = 0) {
     const uint64_t N = (uint64_t)1 << L;
-    (void)d;
+    if (n_valid == 0 || n_valid > N) n_valid = N;
+    uint32_t l[3];
+    const int np = whole_split(ctx, L, l);
+    if (np == 0) return fail(ctx, DP_E_ARG, "dp_ntt: log_n %u too large for one device pass plan", L);
+    const uint32_t l1 = l[0], ll = l[np - 1];
     Fr g = fr_from_u64(7), ninv = fr_from_u64(N).inverse();
-    if (is_coset && !is_inv) {
-        DP_LAUNCH(fr_scale_powers_kernel, dim3(blocks_for(N, 256)), dim3(256), 0, ctx->stream, x, N, g, Fr::one());
+    // coset scaling fused into the first load / the last store when this domain's factor tables fit the split
+    const bool tabs = d && d->log_n == L && d->wg_a && d->w_l1 == l1 && d->w_ll == ll && np >= 2;
+    if (is_coset && !is_inv && !tabs) {
+        DP_LAUNCH(fr_scale_powers_kernel, dim3(blocks_for(n_valid, 256)), dim3(256), 0, ctx->stream, x, n_valid, g, Fr::one());
         ctx->launches++;
     }
+    auto set_first = [&](NttPass &p, uint64_t lanes /* 2^(L - l1) */) {
+        if (n_valid < N) {  // points m >= ceil(n_valid / lanes) of every lane are zero
+            const uint64_t pts = (n_valid + lanes - 1) / lanes;
+            const uint32_t vlog = log2_ceil_u64(pts);
+            p.in_zlog = vlog < p.log_k ? p.log_k - vlog : 0;
+        }
+        if (is_coset && !is_inv && tabs) {
+            p.pre_a = d->wg_a;
+            p.pa_l = 1;
+            p.pre_b = d->wg_b;
+            p.pb_m = 1;
+        }
+    };
     auto set_final = [&](NttPass &p) {
         if (is_inv && !is_coset) {
             p.post_const_on = 1;
@@ -454,17 +517,18 @@ int plan_whole_ntt(dp_ctx *ctx, const DomainDev *d, Fr *x, Fr *scratch, uint32_t
         }
     };
     const uint64_t tw_mul = (uint64_t)1 << (H_log_n - L);  // omega_N = omega_H^(tw_mul)
-    if (L <= ctx->max_contig_log_k) {
+    if (np == 1) {
         NttPass p = pass_base(ctx, is_inv);
         p.in = x;
         p.out = x;
         p.log_k = L;
         p.log_g = 0;
         p.in_ps = p.out_ps = 1;
+        if (n_valid < N) p.in_zlog = L - log2_ceil_u64(n_valid);
         set_final(p);
         DP_TRY(launch_pass(ctx, p, 1));
-    } else if (L <= 2 * ctx->max_strided_log_k) {
-        const uint32_t l1 = L / 2, l2 = L - l1;
+    } else if (np == 2) {
+        const uint32_t l2 = l[1];
         const uint64_t N1 = (uint64_t)1 << l1, N2 = (uint64_t)1 << l2;
         NttPass p = pass_base(ctx, is_inv);
         p.in = x;
@@ -477,6 +541,7 @@ int plan_whole_ntt(dp_ctx *ctx, const DomainDev *d, Fr *x, Fr *scratch, uint32_t
         p.tw_log_n = H_log_n;
         p.tw_la = tw_mul;
         p.tw_fb = 1;
+        set_first(p, N2);
         DP_TRY(launch_pass(ctx, p, N2));
         NttPass q = pass_base(ctx, is_inv);
         q.in = scratch;
@@ -488,10 +553,15 @@ int plan_whole_ntt(dp_ctx *ctx, const DomainDev *d, Fr *x, Fr *scratch, uint32_t
         q.out_ls = 1;
         q.out_ps = N1;
         set_final(q);
+        if (is_coset && is_inv && tabs) {  // k = lane + N1 * f
+            q.post_a = d->wgi_a;
+            q.qa_l = 1;
+            q.post_b = d->wgi_b;
+            q.qb_f = 1;
+        }
         DP_TRY(launch_pass(ctx, q, N1));
     } else {
-        if (L > 3 * ctx->max_strided_log_k) return fail(ctx, DP_E_ARG, "dp_ntt: log_n %u too large for one device pass plan", L);
-        const uint32_t l1 = L / 3, l2 = (L - l1) / 2, l3 = L - l1 - l2;
+        const uint32_t l2 = l[1], l3 = l[2];
         const uint64_t N1 = (uint64_t)1 << l1, N2 = (uint64_t)1 << l2, N3 = (uint64_t)1 << l3;
         NttPass a = pass_base(ctx, is_inv);
         a.in = x;
@@ -504,6 +574,7 @@ int plan_whole_ntt(dp_ctx *ctx, const DomainDev *d, Fr *x, Fr *scratch, uint32_t
         a.tw_log_n = H_log_n;
         a.tw_la = tw_mul;
         a.tw_fb = 1;
+        set_first(a, N2 * N3);
         DP_TRY(launch_pass(ctx, a, N2 * N3));
         NttPass b = pass_base(ctx, is_inv);
         b.in = scratch;
@@ -532,9 +603,16 @@ int plan_whole_ntt(dp_ctx *ctx, const DomainDev *d, Fr *x, Fr *scratch, uint32_t
         c3.in_ps = 1;
         c3.out_ps = N1 * N2;
         set_final(c3);
+        if (is_coset && is_inv && tabs) {  // k = lane + N1 * o + N1 N2 * f
+            c3.post_a = d->wgi_a;
+            c3.qa_l = 1;
+            c3.qa_o = N1;
+            c3.post_b = d->wgi_b;
+            c3.qb_f = 1;
+        }
         DP_TRY(launch_pass(ctx, c3, N1));
     }
-    if (is_coset && is_inv) {
+    if (is_coset && is_inv && !tabs) {
         DP_LAUNCH(fr_scale_powers_kernel, dim3(blocks_for(N, 256)), dim3(256), 0, ctx->stream, x, N, g.inverse(), ninv);
         ctx->launches++;
     }
@@ -571,6 +649,22 @@ int build_domain(dp_ctx *ctx, DomainDev &d, uint64_t min_size) {
     DP_TRY(gen_powers(ctx, d.g_col, c, g, 0, r, one));
     DP_TRY(gen_powers(ctx, d.gi_col, c, gi, 0, 1, d.r_inv));
     DP_TRY(gen_powers(ctx, d.gi_pt, r, gi, 0, c, one));
+    uint32_t l[3];
+    const int np = whole_split(ctx, d.log_n, l);
+    if (np >= 2) {
+        d.w_l1 = l[0];
+        d.w_ll = l[np - 1];
+        const uint64_t na = N >> d.w_l1, nb = (uint64_t)1 << d.w_l1, nia = N >> d.w_ll, nib = (uint64_t)1 << d.w_ll;
+        d.wg_a = (Fr *)ctx->pool.alloc(na * sizeof(Fr));
+        d.wg_b = (Fr *)ctx->pool.alloc(nb * sizeof(Fr));
+        d.wgi_a = (Fr *)ctx->pool.alloc(nia * sizeof(Fr));
+        d.wgi_b = (Fr *)ctx->pool.alloc(nib * sizeof(Fr));
+        if (!d.wg_a || !d.wg_b || !d.wgi_a || !d.wgi_b) return fail(ctx, DP_E_OOM, "coset factor tables (2^%u)", d.log_n);
+        DP_TRY(gen_powers(ctx, d.wg_a, na, g, 0, 1, one));
+        DP_TRY(gen_powers(ctx, d.wg_b, nb, g, 0, na, one));
+        DP_TRY(gen_powers(ctx, d.wgi_a, nia, gi, 0, 1, d.n_inv));
+        DP_TRY(gen_powers(ctx, d.wgi_b, nib, gi, 0, nia, one));
+    }
     return DP_OK;
 }
 
@@ -580,6 +674,10 @@ void free_domain(dp_ctx *ctx, DomainDev &d) {
     ctx->pool.release(d.g_col);
     ctx->pool.release(d.gi_col);
     ctx->pool.release(d.gi_pt);
+    ctx->pool.release(d.wg_a);
+    ctx->pool.release(d.wg_b);
+    ctx->pool.release(d.wgi_a);
+    ctx->pool.release(d.wgi_b);
     d = DomainDev();
 }
 
@@ -812,8 +910,24 @@ int run_row_phase(dp_ctx *ctx, FftTask &t, bool use_p2p = false) {
         t.send = t.rows;
     }
     cudaStreamWaitEvent(ctx->stream, t.ev_in, 0);
+    // rows handed in short (dp_fft1 with len < c, dp_fft1_rows_short): the row kernel reads rd columns of every row;
+    // whatever lies between a row's own length and rd is zero-filled here, the rest of the tail is never touched
+    uint64_t valid = 1;
+    bool same = true;
+    for (uint64_t i = 0; i < t.n_rows; i++) {
+        if (t.row_len[i] > valid) valid = t.row_len[i];
+        same = same && t.row_len[i] == t.row_len[0];
+    }
+    const uint64_t rd = row_read_cols(ctx, d, valid);
+    if (same) {
+        if (t.n_rows && t.row_len[0] < rd)
+            cudaMemset2DAsync(t.rows + t.row_len[0], c * sizeof(Fr), 0, (rd - t.row_len[0]) * sizeof(Fr), t.n_rows, ctx->stream);
+    } else {
+        for (uint64_t i = 0; i < t.n_rows; i++)
+            if (t.row_len[i] < rd) cudaMemsetAsync(t.rows + i * c + t.row_len[i], 0, (rd - t.row_len[i]) * sizeof(Fr), ctx->stream);
+    }
     int rc = plan_row_phase(ctx, d, t.rows, t.send, scratch, t.n_rows, t.row_start, t.is_inv, t.is_coset, ctx->W,
-                            use_p2p ? &peers : nullptr);
+                            use_p2p ? &peers : nullptr, rd);
     ctx->pool.release(scratch);
     if (rc == DP_OK) {
         t.row_phase_done = true;
@@ -932,13 +1046,14 @@ int dp_destroy(dp_ctx *ctx) {
     return DP_OK;
 }
 
+static int p2p_check_timeout(dp_ctx *ctx);
 int dp_sync(dp_ctx *ctx) {
     if (!ctx) return DP_E_ARG;
     DP_CUDA(ctx, cudaStreamSynchronize(ctx->s_in));
     DP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     DP_CUDA(ctx, cudaStreamSynchronize(ctx->s_tail));
     DP_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
-    return DP_OK;
+    return p2p_check_timeout(ctx);
 }
 
 int dp_last_timing(const dp_ctx *ctx, float *kernel_ms, uint64_t *launches) {
@@ -983,7 +1098,7 @@ static int init_impl(dp_ctx *ctx, const void *bases, size_t n_bases, uint64_t do
         Scratch stage(ctx->pool);
         void *staging = stage.get<uint8_t>(in_bytes);
         if (!ctx->bases || !staging) return fail(ctx, DP_E_OOM, "dp_init: %zu bases", n_bases);
-        DP_CUDA(ctx, cudaMemcpyAsync(staging, bases, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        DP_CUDA(ctx, cudaMemcpyAsync(staging, bases, in_bytes, cudaMemcpyDefault, ctx->stream));  // host or device memory
         if (format == 0) {
             DP_LAUNCH(g1_import_ark_kernel, dim3(blocks_for(n_bases, 256)), dim3(256), 0, ctx->stream,
                       (const uint64_t *)staging, ctx->bases, (uint64_t)n_bases);
@@ -1300,7 +1415,7 @@ int dp_fft_init(dp_ctx *ctx, uint64_t id, const dp_fft_workload *workloads, size
         ctx->pool_io.release(t.rows);
         return fail(ctx, DP_E_CUDA, "dp_fft_init: event creation");
     }
-    t.row_seen.assign(t.n_rows, 0);
+    t.row_len.assign(t.n_rows, 0);
     ctx->tasks.emplace(id, std::move(t));
     return DP_OK;
 }
@@ -1315,11 +1430,31 @@ int dp_fft1_rows(dp_ctx *ctx, uint64_t id, uint64_t i_first, uint64_t n_rows, co
     const uint64_t c = ctx->dom[t->is_quot ? 1 : 0].c();
     DP_CUDA(ctx, cudaMemcpyAsync(t->rows + i_first * c, rows, n_rows * c * sizeof(Fr), cudaMemcpyHostToDevice, ctx->s_in));
     DP_CUDA(ctx, cudaEventRecord(t->ev_in, ctx->s_in));
-    for (uint64_t i = i_first; i < i_first + n_rows; i++)
-        if (!t->row_seen[i]) {
-            t->row_seen[i] = 1;
-            t->rows_filled++;
-        }
+    for (uint64_t i = i_first; i < i_first + n_rows; i++) {
+        if (!t->row_len[i]) t->rows_filled++;
+        t->row_len[i] = (uint32_t)c;
+    }
+    return DP_OK;
+}
+
+// n_rows consecutive local rows of row_len <= c leading entries each (compact: n_rows * row_len Fr); the tail of
+// every row is the implicit zero padding of Radix2EvaluationDomain::fft_in_place's resize (worker.rs:81-85)
+int dp_fft1_rows_short(dp_ctx *ctx, uint64_t id, uint64_t i_first, uint64_t n_rows, const void *rows, size_t row_len) {
+    if (!ctx || !rows) return fail(ctx, DP_E_ARG, "dp_fft1_rows_short: NULL argument");
+    FftTask *t = find_task(ctx, id);
+    if (!t) return fail(ctx, DP_E_ARG, "dp_fft1_rows_short: unknown task %llu", (unsigned long long)id);
+    if (t->row_phase_done) return fail(ctx, DP_E_STATE, "dp_fft1 after fft2_prepare");
+    if (i_first + n_rows > t->n_rows) return fail(ctx, DP_E_ARG, "dp_fft1_rows_short: rows [%llu,%llu) of %llu", (unsigned long long)i_first, (unsigned long long)(i_first + n_rows), (unsigned long long)t->n_rows);
+    const uint64_t c = ctx->dom[t->is_quot ? 1 : 0].c();
+    if (row_len == 0 || row_len > c) return fail(ctx, DP_E_ARG, "dp_fft1_rows_short: row length %zu outside 1..%llu", row_len, (unsigned long long)c);
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    DP_CUDA(ctx, cudaMemcpy2DAsync(t->rows + i_first * c, c * sizeof(Fr), rows, row_len * sizeof(Fr), row_len * sizeof(Fr), n_rows,
+                                   cudaMemcpyHostToDevice, ctx->s_in));
+    DP_CUDA(ctx, cudaEventRecord(t->ev_in, ctx->s_in));
+    for (uint64_t i = i_first; i < i_first + n_rows; i++) {
+        if (!t->row_len[i]) t->rows_filled++;
+        t->row_len[i] = (uint32_t)row_len;
+    }
     return DP_OK;
 }
 
@@ -1334,13 +1469,15 @@ int dp_fft1(dp_ctx *ctx, uint64_t id, uint64_t i, const void *row, size_t len) {
     if (t->row_phase_done) return fail(ctx, DP_E_STATE, "dp_fft1 after fft2_prepare");
     if (i >= t->n_rows) return fail(ctx, DP_E_ARG, "dp_fft1: row %llu of %llu", (unsigned long long)i, (unsigned long long)t->n_rows);
     DP_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (len) DP_CUDA(ctx, cudaMemcpyAsync(t->rows + i * c, row, len * sizeof(Fr), cudaMemcpyHostToDevice, ctx->s_in));
-    DP_CUDA(ctx, cudaMemsetAsync(t->rows + i * c + len, 0, (c - len) * sizeof(Fr), ctx->s_in));
-    DP_CUDA(ctx, cudaEventRecord(t->ev_in, ctx->s_in));
-    if (!t->row_seen[i]) {
-        t->row_seen[i] = 1;
-        t->rows_filled++;
+    if (len == 0) {  // an empty row is a row of zeros: one explicit zero, the rest is the implicit tail
+        DP_CUDA(ctx, cudaMemsetAsync(t->rows + i * c, 0, sizeof(Fr), ctx->s_in));
+        len = 1;
+    } else {
+        DP_CUDA(ctx, cudaMemcpyAsync(t->rows + i * c, row, len * sizeof(Fr), cudaMemcpyHostToDevice, ctx->s_in));
     }
+    DP_CUDA(ctx, cudaEventRecord(t->ev_in, ctx->s_in));
+    if (!t->row_len[i]) t->rows_filled++;
+    t->row_len[i] = (uint32_t)len;   // the zero tail is filled in (as far as the row phase reads) by run_row_phase
     return DP_OK;
 }
 
@@ -1439,6 +1576,18 @@ int dp_fft2(dp_ctx *ctx, uint64_t id, void *out, size_t out_bytes) {
     return rc;
 }
 
+// rows handed to the dp_fft_dev* entries: how many columns the row phase has to read (0 = all)
+static uint64_t dev_rd_cols(const dp_ctx *ctx, const DomainDev &d, int is_quot, int is_inv) {
+    const uint64_t v = ctx->dev_valid[is_quot ? 1 : 0];
+    return (v && !is_inv) ? row_read_cols(ctx, d, v) : 0;
+}
+
+int dp_fft_dev_hint_valid_cols(dp_ctx *ctx, int is_quot, uint64_t valid_cols) {
+    if (!ctx) return DP_E_ARG;
+    ctx->dev_valid[is_quot ? 1 : 0] = valid_cols;
+    return DP_OK;
+}
+
 int dp_fft_dev(dp_ctx *ctx, const void *rows_dev, void *cols_dev, int is_quot, int is_inv, int is_coset) {
     if (!ctx || !rows_dev || !cols_dev) return fail(ctx, DP_E_ARG, "dp_fft_dev: NULL argument");
     if (!ctx->inited) return fail(ctx, DP_E_STATE, "dp_fft_dev before dp_init");
@@ -1452,7 +1601,8 @@ int dp_fft_dev(dp_ctx *ctx, const void *rows_dev, void *cols_dev, int is_quot, i
     const bool need_scratch = d.log_c > ctx->max_contig_log_k;
     Fr *scratch = need_scratch ? tmp.get<Fr>(N) : nullptr;
     if (!work || (need_scratch && !scratch)) return fail(ctx, DP_E_OOM, "dp_fft_dev buffers");
-    DP_TRY(plan_row_phase(ctx, d, (const Fr *)rows_dev, work, scratch, d.r(), 0, is_inv != 0, is_coset != 0, 1));
+    DP_TRY(plan_row_phase(ctx, d, (const Fr *)rows_dev, work, scratch, d.r(), 0, is_inv != 0, is_coset != 0, 1, nullptr,
+                          dev_rd_cols(ctx, d, is_quot, is_inv)));
     DP_TRY(plan_col_phase(ctx, d, work, (Fr *)cols_dev, d.c(), 0, is_inv != 0, is_coset != 0));
     return call_end(ctx, true);  // synchronises before the scratch goes back to the pool
 }
@@ -1473,7 +1623,8 @@ int dp_fft_dev_rows(dp_ctx *ctx, const void *rows_dev, int is_quot, int is_inv, 
     Scratch tmp(ctx->pool);
     Fr *scratch = need_scratch ? tmp.get<Fr>(n_rows * c) : nullptr;
     if (!ctx->dev_send || (W > 1 && !ctx->dev_recv) || (need_scratch && !scratch)) return fail(ctx, DP_E_OOM, "dp_fft_dev_rows buffers");
-    DP_TRY(plan_row_phase(ctx, d, (const Fr *)rows_dev, ctx->dev_send, scratch, n_rows, ctx->me * n_rows, is_inv != 0, is_coset != 0, W));
+    DP_TRY(plan_row_phase(ctx, d, (const Fr *)rows_dev, ctx->dev_send, scratch, n_rows, ctx->me * n_rows, is_inv != 0, is_coset != 0, W, nullptr,
+                          dev_rd_cols(ctx, d, is_quot, is_inv)));
     DP_TRY(call_end(ctx, true));
     ctx->dev_flags = (is_quot ? 4 : 0) | (is_inv ? 2 : 0) | (is_coset ? 1 : 0);
     *send_dev = ctx->dev_send;
@@ -1500,7 +1651,7 @@ int dp_fft_dev_cols(dp_ctx *ctx, void *cols_dev) {
     return rc;
 }
 
-static int ntt_device(dp_ctx *ctx, Fr *x, uint32_t log_n, bool is_inv, bool is_coset) {
+static int ntt_device(dp_ctx *ctx, Fr *x, uint32_t log_n, bool is_inv, bool is_coset, uint64_t n_valid = 0) {
     // twiddles: reuse a resident domain table when it is at least as large, else build one.
     // Everything is queued on the compute stream, so handing the scratch back at scope exit is
     // stream-ordered with respect to every later user of the pool.
@@ -1520,7 +1671,7 @@ static int ntt_device(dp_ctx *ctx, Fr *x, uint32_t log_n, bool is_inv, bool is_c
     }
     Fr *scratch = multi ? tmp.get<Fr>(N) : nullptr;
     if (multi && !scratch) return fail(ctx, DP_E_OOM, "dp_ntt scratch");
-    return plan_whole_ntt(ctx, d, x, scratch, log_n, is_inv, is_coset, H, H_log);
+    return plan_whole_ntt(ctx, d, x, scratch, log_n, is_inv, is_coset, H, H_log, is_inv ? 0 : n_valid);
 }
 
 int dp_ntt_dev(dp_ctx *ctx, void *data_dev, uint32_t log_n, int is_inv, int is_coset) {
@@ -1530,6 +1681,18 @@ int dp_ntt_dev(dp_ctx *ctx, void *data_dev, uint32_t log_n, int is_inv, int is_c
     call_begin(ctx);
     DP_TRY(ntt_device(ctx, (Fr *)data_dev, log_n, is_inv != 0, is_coset != 0));
     return call_end(ctx, true);
+}
+
+// in place on a device buffer of 2^log_n Fr whose entries from n_valid on are zero (a resident coefficient vector
+// shorter than the domain, e.g. n coefficients evaluated on the 8n-point coset): the forward transform neither reads
+// nor multiplies the zero tail.  Asynchronous variant of dp_ntt_dev when `wait` is 0 (dp_sync waits).
+int dp_ntt_dev_padded(dp_ctx *ctx, void *data_dev, size_t n_valid, uint32_t log_n, int is_inv, int is_coset, int wait) {
+    if (!ctx || !data_dev) return fail(ctx, DP_E_ARG, "dp_ntt_dev_padded: NULL argument");
+    if (log_n > 32 || n_valid > ((uint64_t)1 << log_n)) return fail(ctx, DP_E_ARG, "dp_ntt_dev_padded: %zu valid entries, log_n %u", n_valid, log_n);
+    DP_CUDA(ctx, cudaSetDevice(ctx->device));
+    call_begin(ctx);
+    DP_TRY(ntt_device(ctx, (Fr *)data_dev, log_n, is_inv != 0, is_coset != 0, n_valid));
+    return call_end(ctx, wait != 0);
 }
 
 int dp_ntt(dp_ctx *ctx, void *data, size_t n, uint32_t log_n, int is_inv, int is_coset) {
@@ -1544,7 +1707,7 @@ int dp_ntt(dp_ctx *ctx, void *data, size_t n, uint32_t log_n, int is_inv, int is
     if (!x) return fail(ctx, DP_E_OOM, "dp_ntt buffer");
     DP_CUDA(ctx, cudaMemcpyAsync(x, data, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
     if (n < N) DP_CUDA(ctx, cudaMemsetAsync(x + n, 0, (N - n) * sizeof(Fr), ctx->stream));
-    DP_TRY(ntt_device(ctx, x, log_n, is_inv != 0, is_coset != 0));
+    DP_TRY(ntt_device(ctx, x, log_n, is_inv != 0, is_coset != 0, n));
     DP_CUDA(ctx, cudaMemcpyAsync(data, x, N * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
     return call_end(ctx, true);
 }
@@ -1709,7 +1872,7 @@ int dp_debug_gen_bases(dp_ctx *ctx, uint64_t seed, size_t n, void *out) {
     if (!dev) return fail(ctx, DP_E_OOM, "dp_debug_gen_bases");
     DP_LAUNCH(g1_gen_bases_kernel, dim3(blocks_for(n, 128)), dim3(128), 0, ctx->stream, dev, (uint64_t)n, seed);
     ctx->launches++;
-    cudaError_t e = cudaMemcpyAsync(out, dev, n * (size_t)DP_G1_AFFINE_BYTES, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaMemcpyAsync(out, dev, n * (size_t)DP_G1_AFFINE_BYTES, cudaMemcpyDefault, ctx->stream);  // host or device memory
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     ctx->pool.release(dev);
     if (e != cudaSuccess) return fail(ctx, DP_E_CUDA, "dp_debug_gen_bases: %s", cudaGetErrorString(e));
@@ -1785,7 +1948,8 @@ int dp_fft_dev_rows_p2p(dp_ctx *ctx, const void *rows_dev, int is_quot, int is_i
     Fr *scratch = need_scratch ? tmp.get<Fr>(n_rows * c) : nullptr;
     if (need_scratch && !scratch) return fail(ctx, DP_E_OOM, "dp_fft_dev_rows_p2p scratch");
     if (ctx->dev_p2p_slot) return fail(ctx, DP_E_STATE, "dp_fft_dev_rows_p2p: the previous transform still waits for dp_fft_dev_cols");
-    DP_TRY(plan_row_phase(ctx, d, (const Fr *)rows_dev, nullptr, scratch, n_rows, ctx->me * n_rows, is_inv != 0, is_coset != 0, W, &peers));
+    DP_TRY(plan_row_phase(ctx, d, (const Fr *)rows_dev, nullptr, scratch, n_rows, ctx->me * n_rows, is_inv != 0, is_coset != 0, W, &peers,
+                          dev_rd_cols(ctx, d, is_quot, is_inv)));
     p2p_commit_slot(ctx);
     ctx->dev_p2p_slot = slot;
     DP_TRY(call_end(ctx, true));
@@ -1798,8 +1962,30 @@ int dp_fft_dev_rows_p2p(dp_ctx *ctx, const void *rows_dev, int is_quot, int is_i
     return DP_OK;
 }
 
+static int fft_dev_p2p(dp_ctx *ctx, const void *rows_dev, void *cols_dev, int is_quot, int is_inv, int is_coset, bool wait);
+
 // rows -> peer memory -> device-side barrier -> columns, all queued on the compute stream
 int dp_fft_dev_p2p(dp_ctx *ctx, const void *rows_dev, void *cols_dev, int is_quot, int is_inv, int is_coset) {
+    return fft_dev_p2p(ctx, rows_dev, cols_dev, is_quot, is_inv, is_coset, true);
+}
+// The same without waiting: the whole transform (and any number of following ones) stays queued on the
+// compute stream; dp_sync() waits and reports a barrier time-out.  Two receive slots are enough for an
+// unbounded stream of transforms: rank A stores transform k+2 into the slot of transform k only after its
+// own column phase k+1, which waited at barrier k+1 for every rank B to finish its row phase k+1, which B's
+// stream runs after B's column phase k - the last reader of that slot.
+int dp_fft_dev_p2p_async(dp_ctx *ctx, const void *rows_dev, void *cols_dev, int is_quot, int is_inv, int is_coset) {
+    return fft_dev_p2p(ctx, rows_dev, cols_dev, is_quot, is_inv, is_coset, false);
+}
+
+static int p2p_check_timeout(dp_ctx *ctx) {
+    if (!ctx->arena || !ctx->bar_seq) return DP_OK;
+    uint32_t timed_out = 0;  // word 1 of the arena header, set by p2p_barrier_kernel when a peer never arrived
+    DP_CUDA(ctx, cudaMemcpy(&timed_out, reinterpret_cast<uint32_t *>(ctx->arena) + 1, 4, cudaMemcpyDeviceToHost));
+    if (timed_out) return fail(ctx, DP_E_COMM, "fused exchange: a peer did not reach the device-side barrier within 20 s");
+    return DP_OK;
+}
+
+static int fft_dev_p2p(dp_ctx *ctx, const void *rows_dev, void *cols_dev, int is_quot, int is_inv, int is_coset, bool wait) {
     if (!ctx || !rows_dev || !cols_dev) return fail(ctx, DP_E_ARG, "dp_fft_dev_p2p: NULL argument");
     if (!ctx->inited) return fail(ctx, DP_E_STATE, "dp_fft_dev_p2p before dp_init");
     if (!p2p_ready(ctx)) return fail(ctx, DP_E_COMM, "dp_fft_dev_p2p: peers not attached");
@@ -1814,7 +2000,8 @@ int dp_fft_dev_p2p(dp_ctx *ctx, const void *rows_dev, void *cols_dev, int is_quo
     const bool need_scratch = d.log_c > ctx->max_contig_log_k;
     Fr *scratch = need_scratch ? tmp.get<Fr>(n_rows * c) : nullptr;
     if (need_scratch && !scratch) return fail(ctx, DP_E_OOM, "dp_fft_dev_p2p scratch");
-    DP_TRY(plan_row_phase(ctx, d, (const Fr *)rows_dev, nullptr, scratch, n_rows, ctx->me * n_rows, is_inv != 0, is_coset != 0, W, &peers));
+    DP_TRY(plan_row_phase(ctx, d, (const Fr *)rows_dev, nullptr, scratch, n_rows, ctx->me * n_rows, is_inv != 0, is_coset != 0, W, &peers,
+                          dev_rd_cols(ctx, d, is_quot, is_inv)));
     p2p_commit_slot(ctx);
     struct SlotGuard {  // the slot is free again once this call returns: the column kernels read it before the stream drains
         dp_ctx *c;
@@ -1827,11 +2014,8 @@ int dp_fft_dev_p2p(dp_ctx *ctx, const void *rows_dev, void *cols_dev, int is_quo
     DP_LAUNCH(p2p_barrier_kernel, dim3(1), dim3(32), 0, ctx->stream, pc, (uint32_t)W, (uint32_t)ctx->me, (uint32_t)(W * ctx->bar_seq));
     ctx->launches++;
     DP_TRY(plan_col_phase(ctx, d, slot, (Fr *)cols_dev, n_cols, ctx->me * n_cols, is_inv != 0, is_coset != 0));
-    DP_TRY(call_end(ctx, true));
-    uint32_t timed_out = 0;  // word 1 of the arena header, set by p2p_barrier_kernel when a peer never arrived
-    DP_CUDA(ctx, cudaMemcpy(&timed_out, reinterpret_cast<uint32_t *>(ctx->arena) + 1, 4, cudaMemcpyDeviceToHost));
-    if (timed_out) return fail(ctx, DP_E_COMM, "dp_fft_dev_p2p: a peer did not reach the barrier within 20 s");
-    return DP_OK;
+    DP_TRY(call_end(ctx, wait));
+    return wait ? p2p_check_timeout(ctx) : DP_OK;
 }
 
 }  // extern "C"

@@ -41,6 +41,10 @@ struct FrParams {
     }
     static constexpr uint32_t INV = 0xffffffffu;  // -r^-1 mod 2^32
     static constexpr bool OUTLINE_MUL = false;    // NTT butterflies: a handful of call sites, keep inline
+    // r = 1 - 2^32 (mod 2^64): the two lowest modulus limbs are 1 and 2^32 - 1, so m * r[0] = m and
+    // m * r[1] = (m << 32) - m need no multiplier: 16 of the 128 multiply-accumulates of a product become
+    // additions on the ALU pipe (the multiplier pipe is what bounds the NTT)
+    static constexpr bool LOW_LIMBS_ARE_1_AND_FFFFFFFF = true;
 };
 
 struct FqParams {
@@ -69,6 +73,7 @@ struct FqParams {
     // thrashed the instruction cache (ncu: 14% "no instruction" stalls in msm_accumulate, 30x
     // slowdown of msm_reduce).  A real call costs ~30 register moves (args travel in registers).
     static constexpr bool OUTLINE_MUL = true;
+    static constexpr bool LOW_LIMBS_ARE_1_AND_FFFFFFFF = false;
 };
 
 // ------------------------------------------------------------------------------ field
@@ -159,6 +164,21 @@ struct Field : Limbs<P::N> {
     // constant-operand variant with the modulus limbs {p[off], p[off+2], ...}
     template <int OFF>
     DP_HD static void mad_row_mod(uint32_t *acc, uint32_t mi) {
+        if (P::LOW_LIMBS_ARE_1_AND_FFFFFFFF) {
+            static_assert(!P::LOW_LIMBS_ARE_1_AND_FFFFFFFF || (P::mod(0) == 1u && P::mod(1) == 0xffffffffu), "modulus shape");
+            if (OFF == 0) {  // + mi * 1
+                acc[0] = ptx::add_cc(acc[0], mi);
+                acc[1] = ptx::addc_cc(acc[1], 0u);
+            } else {         // + mi * (2^32 - 1) = {hi: mi - (mi != 0), lo: -mi}
+                const uint32_t xlo = ptx::sub_cc(0u, mi);
+                const uint32_t xhi = ptx::subc(mi, 0u);
+                acc[0] = ptx::add_cc(acc[0], xlo);
+                acc[1] = ptx::addc_cc(acc[1], xhi);
+            }
+#pragma unroll
+            for (int j = 2; j < N; j += 2) ptx::madc_wide_cc(acc[j], acc[j + 1], P::mod(OFF + j), mi);
+            return;
+        }
         ptx::mad_wide_cc(acc[0], acc[1], P::mod(OFF), mi);
 #pragma unroll
         for (int j = 2; j < N; j += 2) ptx::madc_wide_cc(acc[j], acc[j + 1], P::mod(OFF + j), mi);

@@ -87,6 +87,12 @@ struct NttPass {
     uint64_t qa_o, qa_l, qb_o, qb_f, qb_l;
     uint32_t post_const_on;           // v *= post_const
     Fr post_const;
+    // Zero-padded input: only points m < 2^(log_k - in_zlog) of every lane are read, the rest are implicit zeros
+    // (in_zlog == 0: everything is read).  This is the shape of 25 of the 33 transforms of a proof:
+    // n coefficients on the 8n-point quotient domain (dispatcher2.rs:386-388).  The first in_zlog
+    // butterfly stages then have a zero upper input each and collapse into ONE product per element,
+    // out[j + V*t] = x[j] * omega_K^(j * bitrev(t)), instead of a load and up to three products.
+    uint32_t in_zlog;
 };
 
 // ------------------------------------------------------------------ shared-memory element access
@@ -159,6 +165,20 @@ DP_D void mbar_wait(uint64_t *bar, uint32_t phase) {
         "r"(phase)
         : "memory");
 }
+// 16-byte asynchronous copy global -> shared (LDGSTS): the tile load needs no registers and every thread's
+// copies are in flight together instead of one dependent load-store pair after the other
+DP_D void cp_async16(void *dst_smem, const void *src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+DP_D void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+DP_D void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#else
+DP_D void cp_async16(void *dst_smem, const void *src_gmem) { memcpy(dst_smem, src_gmem, 16); }
+DP_D void cp_async_wait_all() {}
+DP_D void prefetch_l2(const void *) {}
 #endif
 
 // dynamic shared memory: [lo plane | hi plane] of G*(K+1) uint4 each, [w_lo | w_hi] of K uint4 each,
@@ -198,28 +218,68 @@ __global__ void __launch_bounds__(NTT_TPB, 2) ntt_tile_kernel(NttPass p) {
     }
 #endif
 
-    // ---- load the tile (natural point order), fused input scaling
+    // ---- the omega_N twiddles of the epilogue are known now: pull them towards L2 while the tile is loaded and
+    // transformed (the table of a 2^25-point domain is 512 MiB; a demand miss in the store loop costs ~1 us)
+    const bool out_pts_contig = (p.out_ps == 1 && !p.out_lc);
+    if (p.tw_tab) {
+        const uint64_t n_tw = (uint64_t)1 << p.tw_log_n, half_tw = n_tw >> 1;
+        for (uint32_t idx = tid; idx < tile; idx += NTT_TPB) {
+            uint32_t f, g;
+            if (out_pts_contig) {
+                f = idx & (K - 1);
+                g = idx >> p.log_k;
+            } else {
+                g = idx & (G - 1);
+                f = idx >> p.log_g;
+            }
+            const uint64_t lane = lane0 + g;
+            uint64_t e = ((p.tw_la * lane + p.tw_oa * o + p.tw_c0) * (p.tw_fb * f + p.tw_lb * lane)) & (n_tw - 1);
+            if (p.tw_inverse) e = (n_tw - e) & (n_tw - 1);
+            if (half_tw && e >= half_tw) e -= half_tw;
+            prefetch_l2(p.tw_tab + e);
+        }
+    }
+
+    // ---- load the tile (natural point order) with asynchronous 16-byte copies straight into the two planes
+    const uint32_t vlog = p.log_k - p.in_zlog, V = 1u << vlog;  // points >= V of every lane are implicit zeros
     {
         const Fr *src = p.in + (uint64_t)o * p.in_os + (uint64_t)lane0 * p.in_ls;
         const bool pts_contig = (p.in_ps == 1);
-        for (uint32_t idx = tid; idx < tile; idx += NTT_TPB) {
+        const uint32_t n_ld = G << vlog;
+        for (uint32_t idx = tid; idx < n_ld; idx += NTT_TPB) {
             uint32_t m, g;
             if (pts_contig) {
-                m = idx & (K - 1);
-                g = idx >> p.log_k;
+                m = idx & (V - 1);
+                g = idx >> vlog;
             } else {
                 g = idx & (G - 1);
                 m = idx >> p.log_g;
             }
-            Fr v = gmem_ld(src + (uint64_t)g * p.in_ls + (uint64_t)m * p.in_ps);
-            // zero inputs stay zero: the quotient-domain transforms are fed n coefficients padded
-            // to 8n (dispatcher2.rs:386-388), so 7/8 of the loads skip both products (whole warps)
-            if (p.pre_a && !v.is_zero()) {
-                const uint64_t lane = lane0 + g;
-                v = v * gmem_ld(p.pre_a + p.pa_o * o + p.pa_l * lane);
-                v = v * gmem_ld(p.pre_b + p.pb_m * m + p.pb_l * lane);
+            const uint4 *q = reinterpret_cast<const uint4 *>(src + (uint64_t)g * p.in_ls + (uint64_t)m * p.in_ps);
+            cp_async16(lo + g * pitch + m, q);
+            cp_async16(hi + g * pitch + m, q + 1);
+        }
+        cp_async_wait_all();
+        // fused input scaling, in place, every thread on the elements it copied itself (no barrier needed).
+        // Zero inputs stay zero: whole warps skip both products on padded data.
+        if (p.pre_a) {
+            for (uint32_t idx = tid; idx < n_ld; idx += NTT_TPB) {
+                uint32_t m, g;
+                if (pts_contig) {
+                    m = idx & (V - 1);
+                    g = idx >> vlog;
+                } else {
+                    g = idx & (G - 1);
+                    m = idx >> p.log_g;
+                }
+                Fr v = smem_ld(lo, hi, g * pitch + m);
+                if (!v.is_zero()) {
+                    const uint64_t lane = lane0 + g;
+                    v = v * gmem_ld(p.pre_a + p.pa_o * o + p.pa_l * lane);
+                    v = v * gmem_ld(p.pre_b + p.pb_m * m + p.pb_l * lane);
+                    smem_st(lo, hi, g * pitch + m, v);
+                }
             }
-            smem_st(lo, hi, g * pitch + m, v);
         }
     }
 #if !defined(DP_EMUL)
@@ -227,9 +287,29 @@ __global__ void __launch_bounds__(NTT_TPB, 2) ntt_tile_kernel(NttPass p) {
 #endif
     __syncthreads();
 
-    // ---- butterflies: decimation in frequency, stages log_k-1 .. 0
-    int s = (int)p.log_k - 1;
-    if (p.log_k & 1) {  // one radix-2 stage on top so that the rest pairs up
+    // ---- zero-padded input: the stages whose upper input is zero, as one product per element
+    int s = (int)vlog - 1;
+    if (p.in_zlog) {
+        const uint32_t z = p.in_zlog, halfK = K >> 1;
+        for (uint32_t idx = tid; idx < tile; idx += NTT_TPB) {
+            const uint32_t g = idx >> p.log_k, mm = idx & (K - 1);
+            const uint32_t t = mm >> vlog, j = mm & (V - 1);
+            if (t == 0) continue;                                   // x[j] itself stays where it is
+            Fr v = smem_ld(lo, hi, g * pitch + j);
+            uint32_t e = j * (__brev(t) >> (32 - z));                // < K
+            if (e) {
+                const bool neg = e >= halfK;
+                if (neg) e -= halfK;
+                if (e) v = v * smem_ld(wlo, whi, halfK + e);        // W[K/2 + e] = omega_K^(+-e)
+                if (neg) v = v.neg();
+            }
+            smem_st(lo, hi, g * pitch + mm, v);
+        }
+        __syncthreads();
+    }
+
+    // ---- butterflies: decimation in frequency, stages s .. 0
+    if ((s + 1) & 1) {  // one radix-2 stage on top so that the rest pairs up
         const uint32_t span = 1u << s, units = tile >> 1, upl = K >> 1;  // units per lane
         for (uint32_t u = tid; u < units; u += NTT_TPB) {
             const uint32_t g = u >> (p.log_k - 1), uu = u & (upl - 1);
@@ -257,7 +337,8 @@ __global__ void __launch_bounds__(NTT_TPB, 2) ntt_tile_kernel(NttPass p) {
             Fr x0 = smem_ld(lo, hi, e0), x1 = smem_ld(lo, hi, e0 + q);
             Fr x2 = smem_ld(lo, hi, e0 + 2 * q), x3 = smem_ld(lo, hi, e0 + 3 * q);
             // stage s (span 2q): (x0,x2) with T_s[j], (x1,x3) with T_s[j+q]
-            Fr b0 = x0 + x2, b2 = (x0 - x2) * smem_ld(wlo, whi, 2 * q + j);
+            Fr b0 = x0 + x2, b2 = x0 - x2;
+            if (sl > 0) b2 = b2 * smem_ld(wlo, whi, 2 * q + j);  // sl == 0: T_1[0] = 1
             Fr b1 = x1 + x3, b3 = (x1 - x3) * smem_ld(wlo, whi, 2 * q + j + q);
             // stage s-1 (span q): (b0,b1), (b2,b3) with T_{s-1}[j]
             Fr c0 = b0 + b1, c1 = b0 - b1, c2 = b2 + b3, c3 = b2 - b3;
@@ -277,7 +358,8 @@ __global__ void __launch_bounds__(NTT_TPB, 2) ntt_tile_kernel(NttPass p) {
     // ---- write out (frequency f sits at bit-reversed position), fused twiddle / scaling
     {
         Fr *dst = p.out + (uint64_t)o * p.out_os;
-        const bool pts_contig = (p.out_ps == 1 && !p.out_lc);
+        const bool pts_contig = out_pts_contig;
+#pragma unroll 2
         for (uint32_t idx = tid; idx < tile; idx += NTT_TPB) {
             uint32_t f, g;
             if (pts_contig) {

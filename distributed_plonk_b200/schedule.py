@@ -32,6 +32,7 @@ class Transform:
     is_quot: bool
     is_inv: bool
     is_coset: bool
+    row_len: Optional[int] = None   # leading entries handed in per row (None: whole rows of c); in_ptr is then compact
 
 
 @dataclass
@@ -56,7 +57,10 @@ class Runner:
         """fft_init + fft1 over all local rows (async H2D) + fft2_prepare (async kernels)"""
         ctx, tid = self.ctx, self._id()
         ctx.fft_init(tid, t.workloads, t.is_quot, t.is_inv, t.is_coset)
-        ctx._ck(self.lib.dp_fft1_rows(ctx.h, tid, 0, t.n_rows, t.in_ptr))
+        if t.row_len is None:
+            ctx._ck(self.lib.dp_fft1_rows(ctx.h, tid, 0, t.n_rows, t.in_ptr))
+        else:
+            ctx._ck(self.lib.dp_fft1_rows_short(ctx.h, tid, 0, t.n_rows, t.in_ptr, t.row_len))
         if self.exchange is None:
             ctx.fft2_prepare(tid)
         else:   # several workers: one all-to-all on the task's own send / receive buffers

@@ -63,7 +63,8 @@ const char *dp_version(void);
 /* ---- PlonkSlave.init (src/worker.rs:126-157) -------------------------------------------------
  * Stores the SRS bases on the device and builds the (r, c) split domains for `domain_size` and
  * `quot_domain_size` (Radix2EvaluationDomain::new rounds both up to powers of two).
- * bases: n_bases raw G1Affine (104 B each), the concatenation of the `bases` Data chunks. */
+ * bases: n_bases raw G1Affine (104 B each), the concatenation of the `bases` Data chunks; host memory, or
+ * device memory of the context's GPU (a resident SRS: the copy is then device-to-device). */
 int dp_init(dp_ctx *ctx, const void *bases, size_t n_bases, uint64_t domain_size, uint64_t quot_domain_size);
 
 /* "next" row: the same, from the canonical encoding SRS files hold - what the
@@ -121,6 +122,10 @@ int dp_fft_init(dp_ctx *ctx, uint64_t id, const dp_fft_workload *workloads, size
 int dp_fft1(dp_ctx *ctx, uint64_t id, uint64_t i, const void *row, size_t len);
 /* n_rows consecutive local rows in one call (rows = n_rows * c Fr, row-major) */
 int dp_fft1_rows(dp_ctx *ctx, uint64_t id, uint64_t i_first, uint64_t n_rows, const void *rows);
+/* the same for rows that are all cut after their first row_len <= c entries (rows = n_rows * row_len Fr,
+ * compact): only the non-zero part of a padded polynomial's rows crosses PCIe, and the row kernel neither
+ * reads the zero tail nor spends multiplications on it */
+int dp_fft1_rows_short(dp_ctx *ctx, uint64_t id, uint64_t i_first, uint64_t n_rows, const void *rows, size_t row_len);
 
 /* ---- PlonkSlave.fft2Prepare + PlonkPeer.fftExchange (src/worker.rs:280-345, 412-438) ---------
  * Finishes the row phase and moves every (rows_p x cols_q) block to its owner.  n_workers == 1:
@@ -267,7 +272,8 @@ int dp_sync(dp_ctx *ctx);
 int dp_last_msm_breakdown(const dp_ctx *ctx, float *sort_ms, float *accumulate_ms, float *reduce_ms);
 
 /* synthetic SRS: n distinct points k_i*G (k_i = SplitMix64(seed, i)), raw 104-byte G1Affine each,
- * computed on the device and written to HOST memory `out` (feeds dp_init in benches and tests) */
+ * computed on the device and written to `out` (host memory, or device memory of the same GPU); feeds
+ * dp_init in benches and tests */
 int dp_debug_gen_bases(dp_ctx *ctx, uint64_t seed, size_t n, void *out);
 
 /* test hook: lower the pass-planning limits (sub-transform sizes 2^k handled by one kernel pass;
@@ -285,9 +291,18 @@ int dp_msm_dev(dp_ctx *ctx, uint64_t start, uint64_t end, const void *scalars_de
 int dp_msm_dev_batch(dp_ctx *ctx, size_t n_jobs, const uint64_t *starts, const uint64_t *ends, const void *const *scalars_dev,
                      const size_t *n_scalars, void *const *outs_dev);
 int dp_ntt_dev(dp_ctx *ctx, void *data_dev, uint32_t log_n, int is_inv, int is_coset);
+/* the same on a buffer whose entries from n_valid on are ZERO (a resident coefficient vector shorter than the
+ * domain: n coefficients evaluated on the 8n-point coset, dispatcher2.rs:386-388): the forward transform neither
+ * reads nor multiplies the zero tail.  wait = 0 returns once the kernels are queued (dp_sync waits).        */
+int dp_ntt_dev_padded(dp_ctx *ctx, void *data_dev, size_t n_valid, uint32_t log_n, int is_inv, int is_coset, int wait);
 /* full 2-D pipeline of one worker on device-resident rows: rows_dev = my rows (n_rows*c Fr),
  * cols_dev receives my columns (n_cols*r Fr); n_workers must be 1 or peers attached. */
 int dp_fft_dev(dp_ctx *ctx, const void *rows_dev, void *cols_dev, int is_quot, int is_inv, int is_coset);
+/* Promise about the rows given to the dp_fft_dev* entries of one domain (is_quot) from now on: every row is
+ * zero from column valid_cols on - the shape of n coefficients on the 8n-point quotient domain, where
+ * valid_cols = c/8 (dispatcher2.rs:386-388).  Forward transforms then neither read nor multiply the zero
+ * tail (same effect as short rows through dp_fft1); inverse transforms ignore the promise.  0 = no promise. */
+int dp_fft_dev_hint_valid_cols(dp_ctx *ctx, int is_quot, uint64_t valid_cols);
 /* the same split around the caller's all-to-all for n_workers > 1 (one transform in flight per ctx):
  * _rows runs the row phase on my row block (rows_dev: r/W x c Fr) and returns the exchange buffers
  * exactly like dp_fft_exchange_begin; after the all-to-all _cols runs the column phase into
@@ -303,6 +318,10 @@ int dp_fft_dev_rows_p2p(dp_ctx *ctx, const void *rows_dev, int is_quot, int is_i
  * over NVLink), column kernels, queued back to back on the context stream; returns when done.
  * Every rank must call it for the same transforms in the same order (it blocks like a collective). */
 int dp_fft_dev_p2p(dp_ctx *ctx, const void *rows_dev, void *cols_dev, int is_quot, int is_inv, int is_coset);
+/* the same, returning as soon as the kernels are queued (rows_dev / cols_dev must stay valid until dp_sync,
+ * which also reports a barrier time-out as DP_E_COMM).  Any number of transforms may be queued back to back:
+ * the two arena slots are recycled in stream order behind the device-side barriers.                      */
+int dp_fft_dev_p2p_async(dp_ctx *ctx, const void *rows_dev, void *cols_dev, int is_quot, int is_inv, int is_coset);
 
 #ifdef __cplusplus
 }

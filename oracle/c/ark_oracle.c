@@ -448,6 +448,79 @@ void orc_ntt_output_at(const u64 *data, u64 n, u64 k, int inverse, int coset, u6
     memcpy(out, &acc, 32);
 }
 
+/* The same for several positions at once (one thread each) and for a coefficient vector shorter than the
+ * domain: X[k] of the domain_size-point transform of x zero-padded from n_coeffs to domain_size - what
+ * Prover::fft is fed on the quotient domain (n coefficients on 8n points, dispatcher2.rs:386-388). */
+void orc_ntt_outputs_at(const u64 *data, u64 n_coeffs, u64 domain_size, const u64 *ks, u64 n_k, int inverse, int coset, u64 *out) {
+    const fr_t *x = (const fr_t *)data;
+    int log_n = log2_ceil(domain_size);
+    fr_t w, g, ninv, gi;
+    domain_gen(&w, log_n, inverse);
+    fr_from_u64(&g, 7);
+    fr_inv(&gi, &g);
+    {
+        fr_t nn;
+        fr_from_u64(&nn, domain_size);
+        fr_inv(&ninv, &nn);
+    }
+#pragma omp parallel for schedule(dynamic, 1)
+    for (u64 t = 0; t < n_k; t++) {
+        fr_t z, acc;
+        fr_pow_u64(&z, &w, ks[t]);
+        if (coset && !inverse) fr_mul(&z, &z, &g);
+        memset(&acc, 0, sizeof acc);
+        for (u64 j = n_coeffs; j-- > 0;) {
+            fr_mul(&acc, &acc, &z);
+            fr_add(&acc, &acc, &x[j]);
+        }
+        if (inverse) {
+            fr_mul(&acc, &acc, &ninv);
+            if (coset) {
+                fr_t gk;
+                fr_pow_u64(&gk, &gi, ks[t]);
+                fr_mul(&acc, &acc, &gk);
+            }
+        }
+        memcpy(out + 4 * t, &acc, 32);
+    }
+}
+
+/* sum_i s_i * k_i mod r for canonical scalars s (n x 4 words) and 64-bit multipliers k: the discrete
+ * logarithm of sum_i s_i * (k_i * G), used to check MSMs over synthetic bases k_i * G whose size makes a
+ * second full Pippenger on the CPU too slow.  Result canonical. */
+void orc_fr_dot_u64(const u64 *scalars, const u64 *ks, u64 n, u64 *out) {
+    int nt = 1;
+#ifdef _OPENMP
+    nt = omp_get_max_threads();
+#endif
+    fr_t *part = (fr_t *)calloc((size_t)nt, sizeof(fr_t));
+#pragma omp parallel
+    {
+        int me = 0;
+#ifdef _OPENMP
+        me = omp_get_thread_num();
+#endif
+        fr_t acc;
+        memset(&acc, 0, sizeof acc);
+#pragma omp for schedule(static)
+        for (u64 i = 0; i < n; i++) {
+            fr_t s, k, t;
+            fr_from_canonical(&s, (const fr_t *)(scalars + 4 * i));
+            fr_from_u64(&k, ks[i]);
+            fr_mul(&t, &s, &k);
+            fr_add(&acc, &acc, &t);
+        }
+        part[me] = acc;
+    }
+    fr_t tot;
+    memset(&tot, 0, sizeof tot);
+    for (int t = 0; t < nt; t++) fr_add(&tot, &tot, &part[t]);
+    free(part);
+    fr_t c;
+    fr_to_canonical(&c, &tot);
+    memcpy(out, &c, 32);
+}
+
 /* Round-2 permutation grand product exactly as the dispatcher computes it (src/dispatcher2.rs:329-345):
  * product_vec[0] = 1; product_vec[j+1] = product_vec[j] * a / b with one field division per row.
  * wires / id / sigma: [n_types][n] Montgomery Fr (wire value, extended_id_permutation at (i,j), and at
@@ -1097,6 +1170,16 @@ void orc_commit(const uint8_t *bases104, u64 n_bases, const u64 *fr_mont, u64 n,
     orc_fr_into_repr(fr_mont, sc, n < n_bases ? n : n_bases);
     orc_msm(bases104, sc, n_bases, out144);
     free(sc);
+}
+
+/* the checker's own thread count: torchrun exports OMP_NUM_THREADS=1 to its children, which would make the
+ * O(N) checks of a multi-GPU bench run crawl on one core */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
 }
 
 int orc_num_threads(void) {

@@ -74,6 +74,9 @@ def lib():
             "orc_msm": (None, [p, p, u64, p]),
             "orc_commit": (None, [p, u64, p, u64, p]),
             "orc_num_threads": (i, []),
+            "orc_set_num_threads": (None, [i]),
+            "orc_ntt_outputs_at": (None, [p, u64, u64, p, u64, i, i, p]),
+            "orc_fr_dot_u64": (None, [p, p, u64, p]),
             "orc_ntt_output_at": (None, [p, u64, u64, i, i, p]),
             "orc_perm_product": (i, [p, p, p, u64, u64, p, p, p]),
             "orc_quotient_evals": (None, [p, p, p, p, p, p, p, p, p, u64, u64, p]),
@@ -145,6 +148,34 @@ def ntt_output_at(x: np.ndarray, k: int, inverse: bool, coset: bool) -> np.ndarr
     out = np.zeros(4, dtype=np.uint64)
     lib().orc_ntt_output_at(_ptr(x), x.shape[0], k, int(inverse), int(coset), _ptr(out))
     return out
+
+
+def ntt_outputs_at(x: np.ndarray, domain_size: int, ks, inverse: bool, coset: bool) -> np.ndarray:
+    """elements ks of the domain_size-point (coset) (i)NTT of x zero-padded to the domain, O(len(x)) each"""
+    x = np.ascontiguousarray(x, dtype=np.uint64)
+    kk = np.ascontiguousarray(ks, dtype=np.uint64)
+    out = np.zeros((kk.shape[0], 4), dtype=np.uint64)
+    lib().orc_ntt_outputs_at(_ptr(x), x.shape[0], domain_size, _ptr(kk), kk.shape[0], int(inverse), int(coset), _ptr(out))
+    return out
+
+
+def fr_dot_u64(scalars_canonical: np.ndarray, ks: np.ndarray) -> np.ndarray:
+    """sum_i s_i * k_i mod r (canonical), s canonical Fr, k 64-bit"""
+    s = np.ascontiguousarray(scalars_canonical, dtype=np.uint64)
+    kk = np.ascontiguousarray(ks, dtype=np.uint64)
+    out = np.zeros(4, dtype=np.uint64)
+    lib().orc_fr_dot_u64(_ptr(s), _ptr(kk), kk.shape[0], _ptr(out))
+    return out
+
+
+def g1_generator() -> np.ndarray:
+    out = np.zeros(104, dtype=np.uint8)
+    lib().orc_g1_generator(_ptr(out))
+    return out
+
+
+def set_num_threads(n: int) -> None:
+    lib().orc_set_num_threads(int(n))
 
 
 def perm_product(wires: np.ndarray, idp: np.ndarray, sigma: np.ndarray, beta: np.ndarray, gamma: np.ndarray) -> np.ndarray:

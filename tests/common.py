@@ -626,3 +626,60 @@ def check_fft1_row_lengths(orc, worker: PlonkSlave, domain_log: int, is_quot: bo
         worker.fft2_prepare(9100 + tid)
         got = disp.assemble(worker.fft2_array(9100 + tid))
         assert np.array_equal(got, orc.fft(padded, inv, cos)), f"short / long rows, inv={inv} coset={cos}"
+
+
+def check_short_rows(orc, workers, domain_log: int, is_quot: bool, row_len: int, seed: int, copy_fn=None, per_row=False):
+    """Rows handed in cut after `row_len` entries (dp_fft1_rows_short, or dp_fft1 per row when per_row): the transform
+    is that of the zero-extended rows (Radix2EvaluationDomain::fft_in_place resizes, worker.rs:81-85), whether the
+    row kernel drops the zero-input butterfly stages (power-of-two counts) or reads a zero-filled tail."""
+    N = 1 << domain_log
+    r = 1 << (domain_log >> 1)
+    c = N // r
+    W = len(workers)
+    wl = disp.fft_workloads(domain_log, W)
+    for k, (inv, cos) in enumerate(FLAG_COMBOS):
+        rows = np.zeros((r, c, 4), dtype=np.uint64)
+        rows[:, :row_len] = orc.gen_fr(seed + k, r * row_len).reshape(r, row_len, 4)
+        x = np.ascontiguousarray(rows.transpose(1, 0, 2)).reshape(N, 4)          # rows[i][j] = x[i + r*j]
+        tid = 0x5A0000 + seed * 16 + k
+        for w in workers:
+            w.fft_init(tid, wl, is_quot, inv, cos)
+        for p, w in enumerate(workers):
+            lo, hi = wl[p][0], wl[p][1]
+            short = np.ascontiguousarray(rows[lo:hi, :row_len])
+            if per_row:
+                for j in range(hi - lo):
+                    w.ctx.fft1(tid, j, short[j])
+            else:
+                half = (hi - lo) // 2                                              # two calls: the bookkeeping is per row
+                if half:
+                    w.ctx.fft1_rows_short(tid, 0, np.ascontiguousarray(short[:half]), half, row_len)
+                w.ctx.fft1_rows_short(tid, half, np.ascontiguousarray(short[half:]), hi - lo - half, row_len)
+        if W == 1 or workers[0].ctx.peer_ready():
+            for w in workers:
+                w.fft2_prepare(tid)
+        else:
+            for dst, src, nb in local_exchange([w.ctx for w in workers], tid):
+                copy_fn(dst, src, nb)
+        got = disp.assemble(np.concatenate([w.fft2_array(tid) for w in workers], axis=0))
+        assert np.array_equal(got, orc.fft(x, inv, cos)), f"short rows L={domain_log} W={W} len={row_len} inv={inv} coset={cos}"
+
+
+def check_dev_valid_cols_hint(orc, ctx: Context, domain_log: int, is_quot: bool, valid: int, seed: int, as_ptr):
+    """dp_fft_dev with the promise that every row is zero from column `valid` on (W = 1)"""
+    N = 1 << domain_log
+    r = 1 << (domain_log >> 1)
+    c = N // r
+    rows = np.zeros((r, c, 4), dtype=np.uint64)
+    rows[:, :valid] = orc.gen_fr(seed, r * valid).reshape(r, valid, 4)
+    x = np.ascontiguousarray(rows.transpose(1, 0, 2)).reshape(N, 4)
+    ctx.fft_dev_hint_valid_cols(is_quot, valid)
+    try:
+        for inv, cos in FLAG_COMBOS:
+            src, dst = as_ptr(rows), as_ptr(np.zeros((c, r, 4), dtype=np.uint64))
+            ctx.fft_dev(src.ptr, dst.ptr, is_quot, inv, cos)
+            got = disp.assemble(dst.read().reshape(c, r, 4))
+            # inverse transforms ignore the promise (their inputs are evaluations); the rows here are zero-padded anyway
+            assert np.array_equal(got, orc.fft(x, inv, cos)), f"valid-cols hint L={domain_log} valid={valid} inv={inv} coset={cos}"
+    finally:
+        ctx.fft_dev_hint_valid_cols(is_quot, 0)

@@ -338,7 +338,15 @@ inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyK
     return cudaSuccess;
 }
 inline cudaError_t cudaMemcpy2DAsync(void *d, size_t dp, const void *s, size_t sp, size_t w, size_t h,
-                                     cudaMemcpyKind, cudaStream_t st = nullptr) {
+                                     cudaMemcpyKind kind, cudaStream_t st = nullptr) {
+    if (kind == cudaMemcpyHostToDevice && st) {  // pageable source: staged when the copy is issued
+        auto buf = std::make_shared<std::vector<unsigned char>>(w * h);
+        for (size_t i = 0; i < h; i++) memcpy(buf->data() + i * w, (const char *)s + i * sp, w);
+        st->push([=] {
+            for (size_t i = 0; i < h; i++) memcpy((char *)d + i * dp, buf->data() + i * w, w);
+        });
+        return cudaSuccess;
+    }
     dp_emul::run_on(st, [=] {
         for (size_t i = 0; i < h; i++) memmove((char *)d + i * dp, (const char *)s + i * sp, w);
     });
@@ -346,6 +354,12 @@ inline cudaError_t cudaMemcpy2DAsync(void *d, size_t dp, const void *s, size_t s
 }
 inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t st = nullptr) {
     dp_emul::run_on(st, [=] { memset(d, v, n); });
+    return cudaSuccess;
+}
+inline cudaError_t cudaMemset2DAsync(void *d, size_t pitch, int v, size_t w, size_t h, cudaStream_t st = nullptr) {
+    dp_emul::run_on(st, [=] {
+        for (size_t i = 0; i < h; i++) memset((char *)d + i * pitch, v, w);
+    });
     return cudaSuccess;
 }
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) {
@@ -421,6 +435,10 @@ inline cudaError_t cudaMemcpy2DAsync(void *d, size_t dp, const void *s, size_t s
     return cudaSuccess;
 }
 inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t = nullptr) { memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemset2DAsync(void *d, size_t pitch, int v, size_t w, size_t h, cudaStream_t = nullptr) {
+    for (size_t i = 0; i < h; i++) memset((char *)d + i * pitch, v, w);
+    return cudaSuccess;
+}
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = nullptr; return cudaSuccess; }
 inline cudaError_t cudaStreamCreate(cudaStream_t *s) { *s = nullptr; return cudaSuccess; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }

@@ -44,6 +44,62 @@ def _worker(rank, world, port, lib_path, out_dir, backend="gloo", extra=""):
     w.init(chunks(bases), 1 << 6, 1 << 9)
     exchange = parallel.make_exchange()
     ok = True
+    if cuda and extra == "p2p_async":
+        # a stream of transforms on the device-side barrier with no host synchronisation in between
+        L, seeds = 15, range(6)
+        r, c = 1 << (L >> 1), (1 << L) >> (L >> 1)
+        ins, outs, xs = [], [], []
+        w.init(chunks(bases), 1 << 12, 1 << L)
+        ok &= bool(parallel.attach_peers(w.ctx, 2 * (1 << L) * 32 // world))
+        for k in seeds:
+            x = orc.gen_fr(900 + k, (1 << L) // 8)                  # n coefficients on the 8n domain
+            xs.append(np.concatenate([x, np.zeros(((1 << L) - x.shape[0], 4), dtype=np.uint64)]))
+            rows = disp.dispatcher_rows(x, L)[rank * r // world:(rank + 1) * r // world]
+            ins.append(torch.from_numpy(np.ascontiguousarray(rows).view(np.int64)).cuda())
+            outs.append(torch.empty(((c // world) * r, 4), dtype=torch.int64, device="cuda"))
+        torch.cuda.synchronize()
+        w.ctx.fft_dev_hint_valid_cols(True, c // 8)
+        for k in seeds:
+            w.ctx.fft_dev_p2p_async(ins[k].data_ptr(), outs[k].data_ptr(), True, False, True)
+        w.ctx.sync()
+        w.ctx.fft_dev_hint_valid_cols(True, 0)
+        for k in seeds:
+            gathered = [torch.empty_like(outs[k]) for _ in range(world)]
+            dist.all_gather(gathered, outs[k])
+            cols = torch.cat(gathered).cpu().numpy().view(np.uint64).reshape(c, r, 4)
+            ok &= bool(np.array_equal(disp.assemble(cols), orc.fft(xs[k], False, True)))
+        # fft2_prepare form: a third task between prepare and fft2 is refused, nothing is consumed
+        from distributed_plonk_b200._binding import DpError
+        wl = disp.fft_workloads(L, world)
+        for t in range(3):
+            rows = disp.dispatcher_rows(xs[t][: (1 << L) // 8], L)
+            w.fft_init(7000 + t, wl, True, False, True)
+            w.ctx.fft1_rows(7000 + t, 0, np.ascontiguousarray(rows[wl[rank][0]:wl[rank][1]]), wl[rank][1] - wl[rank][0])
+        for t in range(2):
+            w.ctx.fft2_prepare(7000 + t)
+        try:
+            w.ctx.fft2_prepare(7002)
+            ok = False
+        except DpError as e:
+            ok &= e.code == -2
+        dist.barrier()
+        got = {0: w.fft2_array(7000)}
+        dist.barrier()                                              # every rank has read slot 0
+        w.ctx.fft2_prepare(7002)
+        dist.barrier()
+        for t in (1, 2):
+            got[t] = w.fft2_array(7000 + t)
+        for t in range(3):
+            mine = torch.from_numpy(got[t].view(np.int64)).cuda()
+            gathered = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(gathered, mine)
+            cols = torch.cat(gathered).cpu().numpy().view(np.uint64).reshape(c, r, 4)
+            ok &= bool(np.array_equal(disp.assemble(cols), orc.fft(xs[t], False, True)))
+        with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as f:
+            f.write("ok" if ok else "FAIL")
+        w.close()
+        dist.destroy_process_group()
+        return
     def run_ffts(mode):
         good = True
         for is_quot, L in ((False, 6), (True, 9)):

@@ -396,3 +396,58 @@ def test_exchange_end_twice_and_in_place_division_are_refused(orc, emul_lib):
     assert e.value.code == -1
     for w in workers:
         w.close()
+
+
+class _HostBuf:
+    """device-pointer stand-in under the emulator: host memory"""
+
+    def __init__(self, a):
+        self.a = np.ascontiguousarray(a)
+        self.ptr = self.a.ctypes.data
+
+    def read(self):
+        return self.a
+
+
+@pytest.mark.parametrize("W,limits", [(1, (11, 9)), (1, (3, 2)), (2, (3, 2)), (2, (11, 9))])
+def test_short_rows_skip_the_zero_stages(orc, emul_lib, W, limits):
+    """n coefficients on the 8n domain and other cuts: power-of-two row lengths drop butterfly stages (single-pass and
+    two-pass row plans), other lengths read a zero-filled tail; through dp_fft1_rows_short and per-row dp_fft1"""
+    workers = [PlonkSlave(emul_lib, p, W) for p in range(W)]
+    for w in workers:
+        w.init([b""], 1 << 6, 1 << 9)
+        w.ctx.debug_set_limits(limits[0], limits[1], 0)
+    c_q = 1 << 5                                                   # quotient domain 2^9 = 16 x 32
+    for k, row_len in enumerate((c_q // 8, 1, c_q // 2, 3, c_q // 8 + 1, c_q)):
+        common.check_short_rows(orc, workers, 9, True, row_len, 40 + k, host_copy)
+    common.check_short_rows(orc, workers, 6, False, 2, 50, host_copy)
+    common.check_short_rows(orc, workers, 9, True, c_q // 8, 51, host_copy, per_row=True)
+    if W == 1:
+        for valid in (c_q // 8, 1, 5, c_q):
+            common.check_dev_valid_cols_hint(orc, workers[0].ctx, 9, True, valid, 60 + valid, _HostBuf)
+    for w in workers:
+        w.close()
+
+
+@pytest.mark.parametrize("limits,domains", [((3, 2), (6, 5)), ((3, 3), (6, 5)), ((2, 2), (4, 6))])
+def test_whole_ntt_fused_coset_tables_and_short_inputs(orc, emul_lib, limits, domains):
+    """whole-domain transforms of the two domains given to dp_init: coset scaling from the two factor tables (2- and
+    3-pass splits), inputs shorter than the domain (the first pass drops the zero-input stages), resident padded form"""
+    c = Context(emul_lib, 0, 0, 1)
+    c.debug_set_limits(limits[0], limits[1], 0)       # before init: the factor tables follow the pass split
+    c.init(np.zeros(0, dtype=np.uint8), 1 << domains[0], 1 << domains[1])
+    for log_n in domains:
+        N = 1 << log_n
+        for n_in in (None, max(1, N // 8), 3, 1, N // 2 + 1):
+            common.check_whole_ntt(orc, c, log_n, 70 + log_n, n_in=n_in)
+        # dp_ntt_dev_padded on a "device" buffer (host memory under the emulator)
+        n_in = max(1, N // 8)
+        x = orc.gen_fr(90 + log_n, n_in)
+        for inv, cos in common.FLAG_COMBOS:
+            buf = np.zeros((N, 4), dtype=np.uint64)
+            buf[:n_in] = x
+            ref = orc.fft(buf, inv, cos)
+            c.ntt_dev_padded(buf.ctypes.data, n_in, log_n, inv, cos)
+            assert np.array_equal(buf, ref), f"ntt_dev_padded log_n={log_n} inv={inv} coset={cos}"
+    common.check_whole_ntt(orc, c, 3, 77)              # a size that is neither domain: scaling kernel fallback
+    c.close()

@@ -204,6 +204,7 @@ def workload_config(log_n: int, n_gpus: int):
                     f"{N_COSET_INTT_8N} coset-iNTT(2^{log_n + 3})",
         "log_gates": log_n, "parallelism": f"{n_gpus} GPU(s): MSM index-range shards, 2-D NTT rows/cols + 1 all-to-all",
         "l2": "inputs larger than L2 (>=128 MiB each), rotated between calls",
+        "inputs": "coset-NTT(8n) inputs are n coefficients zero-padded to 8n (rows with c/8 non-zero leading entries), declared as such",
     }
 
 
@@ -301,6 +302,9 @@ def main():
         t[:, c_m // 8:, :] = 0
         in_m.append(t.view(-1, 4))
     out_m = torch.empty((cols_m * r_m, 4), dtype=torch.int64, device="cuda")
+    # what the dispatcher feeds the quotient-domain transforms is n coefficients (dispatcher2.rs:386-388): the row
+    # kernels are told that columns >= c/8 of these rows are zero, as short rows tell them on the wire path (dp_fft1)
+    ctx.fft_dev_hint_valid_cols(True, c_m // 8)
     msm_out = torch.zeros(18, dtype=torch.int64, device="cuda")
     exchange = parallel.make_exchange() if W > 1 else None
     fused = False

@@ -177,6 +177,8 @@ struct dp_ctx {
     uint64_t dev_valid[2] = {0, 0};  // dp_fft_dev_hint_valid_cols: leading non-zero columns of the rows given to dp_fft_dev*
     // pass-planning limits (dp_debug_set_limits lowers them so small tests reach the multi-pass plans)
     uint32_t max_contig_log_k = NTT_WTAB_LOG, max_strided_log_k = NTT_MAX_STRIDED_LOG_K;
+    bool ntt_tw_prefetch = false;  // experiment knob (env DP_NTT_PREFETCH)
+    int ntt_min_blocks = 3;    // knob (env DP_NTT_BLOCKS): register budget of ntt_tile_kernel for 2 or 3 CTAs per SM (3: -7 % per transform)
     uint32_t msm_chunk = 0;    // experiment knob (env DP_MSM_CHUNK): digits per accumulate thread, 0 = default
     int msm_force_c = 0;       // 0 auto, 1 = windowed path with automatic c, >= 2 forced c (windowed)
     bool pre_disabled = false;
@@ -242,6 +244,7 @@ NttPass pass_base(dp_ctx *ctx, bool inverse) {
     p.n_outer = 1;
     p.lane_tiles = 1;
     p.tw_inverse = inverse ? 1 : 0;
+    p.tw_prefetch = ctx->ntt_tw_prefetch ? 1 : 0;
     return p;
 }
 
@@ -257,7 +260,10 @@ int launch_pass(dp_ctx *ctx, NttPass &p, uint64_t n_lanes) {
     const uint64_t grid = (uint64_t)p.n_outer * p.lane_tiles;
     if (grid == 0 || grid > 0x7fffffffull) return fail(ctx, DP_E_ARG, "ntt pass grid %llu out of range", (unsigned long long)grid);
     const size_t smem = ntt_pass_smem_bytes(p.log_k, p.log_g);
-    DP_LAUNCH(ntt_tile_kernel, dim3((unsigned)grid), dim3(NTT_TPB), smem, ctx->stream, p);
+    if (ctx->ntt_min_blocks == 3)
+        DP_LAUNCH(ntt_tile_kernel<3>, dim3((unsigned)grid), dim3(NTT_TPB), smem, ctx->stream, p);
+    else
+        DP_LAUNCH(ntt_tile_kernel<2>, dim3((unsigned)grid), dim3(NTT_TPB), smem, ctx->stream, p);
     ctx->launches++;
     DP_CUDA(ctx, cudaGetLastError());
     return DP_OK;
@@ -979,6 +985,8 @@ int dp_create(int cuda_device, uint64_t me, uint64_t n_workers, dp_ctx **out) {
     dp_ctx *ctx = new dp_ctx();
     ctx->device = cuda_device;
     if (const char *e = getenv("DP_MSM_CHUNK")) ctx->msm_chunk = (uint32_t)atoi(e) >= 8 ? (uint32_t)atoi(e) : 0;
+    if (const char *e = getenv("DP_NTT_BLOCKS")) ctx->ntt_min_blocks = atoi(e) == 2 ? 2 : 3;
+    if (const char *e = getenv("DP_NTT_PREFETCH")) ctx->ntt_tw_prefetch = atoi(e) != 0;
     ctx->me = me;
     ctx->W = n_workers;
     int rc = DP_OK;
@@ -991,7 +999,9 @@ int dp_create(int cuda_device, uint64_t me, uint64_t n_workers, dp_ctx **out) {
         cudaEventCreate(&ctx->ev0);
         cudaEventCreate(&ctx->ev1);
         for (int k = 0; k < 4; k++) cudaEventCreate(&ctx->ev_msm[k]);
-        if (cudaFuncSetAttribute(ntt_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(ntt_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)ntt_pass_smem_bytes(NTT_WTAB_LOG, 0)) != cudaSuccess) { rc = DP_E_CUDA; break; }
+        if (cudaFuncSetAttribute(ntt_tile_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)ntt_pass_smem_bytes(NTT_WTAB_LOG, 0)) != cudaSuccess) { rc = DP_E_CUDA; break; }
         const size_t wb = ((size_t)1 << NTT_WTAB_LOG) * sizeof(uint4);
         ctx->wf_lo = (uint4 *)ctx->pool.alloc(wb);

@@ -93,6 +93,7 @@ struct NttPass {
     // butterfly stages then have a zero upper input each and collapse into ONE product per element,
     // out[j + V*t] = x[j] * omega_K^(j * bitrev(t)), instead of a load and up to three products.
     uint32_t in_zlog;
+    uint32_t tw_prefetch;             // experiment knob: pull the epilogue's omega_N twiddles towards L2 while the tile is transformed
 };
 
 // ------------------------------------------------------------------ shared-memory element access
@@ -188,7 +189,10 @@ DP_HD size_t ntt_pass_smem_bytes(uint32_t log_k, uint32_t log_g) {
     return 2 * G * (K + 1) * 16 + 2 * K * 16 + 16;
 }
 
-__global__ void __launch_bounds__(NTT_TPB, 2) ntt_tile_kernel(NttPass p) {
+// MINB = resident CTAs per SM the register allocation aims for: 2 (<= 128 registers) or 3 (<= 85; three 64-70 KB tiles
+// fit the 227 KB of shared memory): more warps to cover the dependent carry chains and the table loads
+template <int MINB>
+__global__ void __launch_bounds__(NTT_TPB, MINB) ntt_tile_kernel(NttPass p) {
     DP_DYN_SMEM(smem_raw);
     const uint32_t K = 1u << p.log_k, G = 1u << p.log_g, tile = K * G, pitch = K + 1;
     uint4 *lo = reinterpret_cast<uint4 *>(smem_raw);
@@ -218,10 +222,11 @@ __global__ void __launch_bounds__(NTT_TPB, 2) ntt_tile_kernel(NttPass p) {
     }
 #endif
 
-    // ---- the omega_N twiddles of the epilogue are known now: pull them towards L2 while the tile is loaded and
-    // transformed (the table of a 2^25-point domain is 512 MiB; a demand miss in the store loop costs ~1 us)
+    // ---- the omega_N twiddles of the epilogue are known now: optionally pull them towards L2 while the tile is loaded
+    // and transformed (the table of a 2^25-point domain is 512 MiB; a demand miss in the store loop costs ~1 us).
+    // Measured on B200 (profiles/README.md): DRAM reads of the 2-D twiddle pass grow from 4.3 to 6.8 GB - off by default.
     const bool out_pts_contig = (p.out_ps == 1 && !p.out_lc);
-    if (p.tw_tab) {
+    if (p.tw_tab && p.tw_prefetch) {
         const uint64_t n_tw = (uint64_t)1 << p.tw_log_n, half_tw = n_tw >> 1;
         for (uint32_t idx = tid; idx < tile; idx += NTT_TPB) {
             uint32_t f, g;
@@ -287,12 +292,18 @@ __global__ void __launch_bounds__(NTT_TPB, 2) ntt_tile_kernel(NttPass p) {
 #endif
     __syncthreads();
 
+    // Work-item order of the in-tile stages.  A quarter-warp (8 threads) is conflict-free for 16-byte accesses when its
+    // elements fall into 8 different 16-byte bank groups.  With the point index fastest that fails for the short-span
+    // stages (elements 4 apart: 4-way conflicts in the last radix-4 pair, 2-way in the one before - 84 % extra
+    // shared-memory wavefronts per tile, ncu r02a).  With the LANE index fastest the eight threads sit in eight lanes,
+    // pitch K + 1 elements apart, i.e. in eight different bank groups whatever the stage; they also share one twiddle.
+    const bool lanes_fast = G >= 8;
     // ---- zero-padded input: the stages whose upper input is zero, as one product per element
     int s = (int)vlog - 1;
     if (p.in_zlog) {
         const uint32_t z = p.in_zlog, halfK = K >> 1;
         for (uint32_t idx = tid; idx < tile; idx += NTT_TPB) {
-            const uint32_t g = idx >> p.log_k, mm = idx & (K - 1);
+            const uint32_t g = lanes_fast ? idx & (G - 1) : idx >> p.log_k, mm = lanes_fast ? idx >> p.log_g : idx & (K - 1);
             const uint32_t t = mm >> vlog, j = mm & (V - 1);
             if (t == 0) continue;                                   // x[j] itself stays where it is
             Fr v = smem_ld(lo, hi, g * pitch + j);
@@ -312,7 +323,7 @@ __global__ void __launch_bounds__(NTT_TPB, 2) ntt_tile_kernel(NttPass p) {
     if ((s + 1) & 1) {  // one radix-2 stage on top so that the rest pairs up
         const uint32_t span = 1u << s, units = tile >> 1, upl = K >> 1;  // units per lane
         for (uint32_t u = tid; u < units; u += NTT_TPB) {
-            const uint32_t g = u >> (p.log_k - 1), uu = u & (upl - 1);
+            const uint32_t g = lanes_fast ? u & (G - 1) : u >> (p.log_k - 1), uu = lanes_fast ? u >> p.log_g : u & (upl - 1);
             const uint32_t j = uu & (span - 1);
             const uint32_t m0 = ((uu >> s) << (s + 1)) | j;
             const uint32_t e0 = g * pitch + m0, e1 = e0 + span;
@@ -330,7 +341,7 @@ __global__ void __launch_bounds__(NTT_TPB, 2) ntt_tile_kernel(NttPass p) {
         const int sl = s - 1;
         const uint32_t q = 1u << sl, units = tile >> 2, upl = K >> 2;
         for (uint32_t u = tid; u < units; u += NTT_TPB) {
-            const uint32_t g = u >> (p.log_k - 2), uu = u & (upl - 1);
+            const uint32_t g = lanes_fast ? u & (G - 1) : u >> (p.log_k - 2), uu = lanes_fast ? u >> p.log_g : u & (upl - 1);
             const uint32_t j = uu & (q - 1);
             const uint32_t m0 = ((uu >> sl) << (sl + 2)) | j;
             const uint32_t e0 = g * pitch + m0;

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Everything profiles/ needs for a round, in ONE gpurun call (1 GPU), bounded by timeouts:
-#   /usr/local/graft/bin/gpurun --timeout 1700 -- 'bash tools/round_profile.sh r02'
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/round_profile.sh r02'
 # Produces under gpurun_out/ (copy what should be judged into profiles/):
 #   <tag>_pytest_gpu.txt            tail of `pytest -m gpu`
 #   <tag>_bench_1gpu.json           the bench line (never taken under a profiler)
@@ -10,14 +10,13 @@
 tag=${1:-rXX}
 out=gpurun_out
 mkdir -p $out
-timeout 1000 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > $out/${tag}_pytest_gpu.txt
-timeout 420 python bench.py --steps 5 --warmup 3 > $out/${tag}_bench_1gpu.json 2> $out/${tag}_bench_1gpu.err
-timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $out/${tag}_launches_bench.csv \
-    python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > /dev/null 2>&1
-for k in msm_accumulate_kernel ntt_tile_kernel quotient_kernel msm_reduce_kernel; do
-    timeout 200 ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o $out/${tag}_$k \
-        python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > /dev/null 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -30 > $out/${tag}_pytest_gpu.txt
+timeout 600 python bench.py --steps 3 --warmup 3 > $out/${tag}_bench_1gpu.json 2> $out/${tag}_bench_1gpu.err
+quick="python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-verify"
+timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $out/${tag}_launches_bench.csv $quick > /dev/null 2>&1
+# the four passes of one 2^25 coset transform (launches 0-20 of ntt_tile_kernel are the 2^22 passes of the warm-up step)
+timeout 240 ncu --set full --clock-control none --import-source on -k regex:ntt_tile_kernel -s 25 -c 4 -f -o $out/${tag}_ntt_tile_2p25 $quick > /dev/null 2>&1
+for k in msm_accumulate_kernel quotient_kernel msm_reduce_kernel; do
+    timeout 200 ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -f -o $out/${tag}_$k $quick > /dev/null 2>&1
 done
-# feasibility of batched-affine bucket accumulation (tools/microbench4.cu; build it first with the nvcc line in its header)
-[ -x tools/microbench4 ] && timeout 180 ./tools/microbench4 24 > $out/${tag}_microbench_affine.txt 2>&1
 ls -la $out | tail -20

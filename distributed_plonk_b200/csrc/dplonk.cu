@@ -177,6 +177,7 @@ struct dp_ctx {
     uint64_t dev_valid[2] = {0, 0};  // dp_fft_dev_hint_valid_cols: leading non-zero columns of the rows given to dp_fft_dev*
     // pass-planning limits (dp_debug_set_limits lowers them so small tests reach the multi-pass plans)
     uint32_t max_contig_log_k = NTT_WTAB_LOG, max_strided_log_k = NTT_MAX_STRIDED_LOG_K;
+    int msm_min_blocks = 3;        // experiment knob (env DP_MSM_BLOCKS): register budget of msm_accumulate_kernel for 3, 4 or 5 blocks per SM
     bool ntt_tw_prefetch = false;  // experiment knob (env DP_NTT_PREFETCH)
     int ntt_min_blocks = 3;    // knob (env DP_NTT_BLOCKS): register budget of ntt_tile_kernel for 2 or 3 CTAs per SM (3: -7 % per transform)
     uint32_t msm_chunk = 0;    // experiment knob (env DP_MSM_CHUNK): digits per accumulate thread, 0 = default
@@ -777,8 +778,15 @@ int msm_enqueue(dp_ctx *ctx, uint64_t start, const uint4 *scalars_dev, uint64_t 
     DP_LAUNCH(msm_find_big_kernel, dim3(blocks_for(g.n_keys, 256)), dim3(256), 0, st, offsets, g.n_keys, g.chunk, multi_keys + 1,
               multi_keys);
     if (record_breakdown) cudaEventRecord(ctx->ev_msm[1], st);
-    DP_LAUNCH(msm_accumulate_kernel, dim3(blocks_for(max_chunks, MSM_TPB)), dim3(MSM_TPB), 0, st, offsets, g.n_keys, g.chunk, sorted,
-              bases, partials);
+    if (ctx->msm_min_blocks == 4)
+        DP_LAUNCH(msm_accumulate_kernel<4>, dim3(blocks_for(max_chunks, MSM_TPB)), dim3(MSM_TPB), 0, st, offsets, g.n_keys, g.chunk, sorted,
+                  bases, partials);
+    else if (ctx->msm_min_blocks == 5)
+        DP_LAUNCH(msm_accumulate_kernel<5>, dim3(blocks_for(max_chunks, MSM_TPB)), dim3(MSM_TPB), 0, st, offsets, g.n_keys, g.chunk, sorted,
+                  bases, partials);
+    else
+        DP_LAUNCH(msm_accumulate_kernel<3>, dim3(blocks_for(max_chunks, MSM_TPB)), dim3(MSM_TPB), 0, st, offsets, g.n_keys, g.chunk, sorted,
+                  bases, partials);
     DP_LAUNCH(msm_collapse_kernel, dim3(max_multi * 32 < 148ull * 8 * MSM_TPB ? blocks_for(max_multi * 32, MSM_TPB) : 148 * 8),
               dim3(MSM_TPB), 0, st, multi_keys + 1, multi_keys, offsets, g.chunk, partials);
     if (record_breakdown) cudaEventRecord(ctx->ev_msm[2], st);
@@ -987,6 +995,7 @@ int dp_create(int cuda_device, uint64_t me, uint64_t n_workers, dp_ctx **out) {
     if (const char *e = getenv("DP_MSM_CHUNK")) ctx->msm_chunk = (uint32_t)atoi(e) >= 8 ? (uint32_t)atoi(e) : 0;
     if (const char *e = getenv("DP_NTT_BLOCKS")) ctx->ntt_min_blocks = atoi(e) == 2 ? 2 : 3;
     if (const char *e = getenv("DP_NTT_PREFETCH")) ctx->ntt_tw_prefetch = atoi(e) != 0;
+    if (const char *e = getenv("DP_MSM_BLOCKS")) ctx->msm_min_blocks = atoi(e) >= 3 && atoi(e) <= 5 ? atoi(e) : 3;
     ctx->me = me;
     ctx->W = n_workers;
     int rc = DP_OK;

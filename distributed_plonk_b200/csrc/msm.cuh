@@ -405,8 +405,12 @@ DP_D G1Affine load_affine(const G1Affine *p) {
     return r;
 }
 
-__global__ void __launch_bounds__(MSM_TPB) msm_accumulate_kernel(const uint32_t *offsets, uint32_t n_keys, uint32_t chunk,
-                                                                  const uint32_t *sorted, const G1Affine *bases, G1XYZZ *partials) {
+// MINB: resident blocks per SM the register allocation aims for (3: 152 registers, no spills; 4: 128 registers and a
+// few hundred bytes of spills around the outlined multiplications).  The kernel is bound by the dependent carry
+// chains of the Fq products (ncu r02a: 52 % of the warp samples are fixed-latency waits at 3 warps per scheduler).
+template <int MINB>
+__global__ void __launch_bounds__(MSM_TPB, MINB) msm_accumulate_kernel(const uint32_t *offsets, uint32_t n_keys, uint32_t chunk,
+                                                                        const uint32_t *sorted, const G1Affine *bases, G1XYZZ *partials) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_digits = offsets[n_keys];  // the grid is sized for the worst case
     const uint64_t pos0 = (uint64_t)j * chunk;

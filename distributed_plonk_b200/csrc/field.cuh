@@ -288,6 +288,86 @@ struct Field : Limbs<P::N> {
             if (l[i] != P::mod(i)) return l[i] < P::mod(i);
         return false;
     }
+    // 1/x for ONE thread on the critical path (msm_final: a single lane normalises the result): binary extended
+    // Euclid on the limbs - shifts, additions and comparisons only, ~1.5 * bits iterations with data-dependent
+    // branches - instead of the ~1.5 * bits dependent Montgomery products of Fermat's exponentiation (0.7 ms for a
+    // lone warp at Fq size, ncu r02; this is ~10x shorter).  Divergent across a warp: keep inverse() for full warps.
+    // x != 0, Montgomery form in and out.
+    DP_HD Field inverse_vartime() const {
+        uint32_t u[N], v[N], x1[N], x2[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            u[i] = l[i];
+            v[i] = P::mod(i);
+            x1[i] = i == 0 ? 1u : 0u;
+            x2[i] = 0u;
+        }
+        auto is_one = [](const uint32_t *a) {
+            uint32_t o = a[0] ^ 1u;
+#pragma unroll
+            for (int i = 1; i < N; i++) o |= a[i];
+            return o == 0;
+        };
+        auto halve = [](uint32_t *a, uint32_t top) {  // (top:a) >> 1
+#pragma unroll
+            for (int i = 0; i < N - 1; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 31);
+            a[N - 1] = (a[N - 1] >> 1) | (top << 31);
+        };
+        auto halve_mod = [&](uint32_t *a) {  // a / 2 mod p, a < p
+            uint32_t top = 0;
+            if (a[0] & 1u) {
+                a[0] = ptx::add_cc(a[0], P::mod(0));
+#pragma unroll
+                for (int i = 1; i < N; i++) a[i] = ptx::addc_cc(a[i], P::mod(i));
+                top = ptx::addc(0u, 0u);
+            }
+            halve(a, top);
+        };
+        auto geq = [](const uint32_t *a, const uint32_t *b) {
+            for (int i = N - 1; i >= 0; i--)
+                if (a[i] != b[i]) return a[i] > b[i];
+            return true;
+        };
+        auto sub = [](uint32_t *a, const uint32_t *b) {  // a -= b, a >= b
+            a[0] = ptx::sub_cc(a[0], b[0]);
+#pragma unroll
+            for (int i = 1; i < N; i++) a[i] = ptx::subc_cc(a[i], b[i]);
+        };
+        auto sub_mod = [&](uint32_t *a, const uint32_t *b) {  // a = a - b mod p, both < p
+            a[0] = ptx::sub_cc(a[0], b[0]);
+#pragma unroll
+            for (int i = 1; i < N; i++) a[i] = ptx::subc_cc(a[i], b[i]);
+            const uint32_t borrow = ptx::subc(0u, 0u);
+            if (borrow) {
+                a[0] = ptx::add_cc(a[0], P::mod(0));
+#pragma unroll
+                for (int i = 1; i < N; i++) a[i] = ptx::addc_cc(a[i], P::mod(i));
+            }
+        };
+        while (!is_one(u) && !is_one(v)) {
+            while (!(u[0] & 1u)) {
+                halve(u, 0u);
+                halve_mod(x1);
+            }
+            while (!(v[0] & 1u)) {
+                halve(v, 0u);
+                halve_mod(x2);
+            }
+            if (geq(u, v)) {
+                sub(u, v);
+                sub_mod(x1, x2);
+            } else {
+                sub(v, u);
+                sub_mod(x2, x1);
+            }
+        }
+        // (x R)^-1 = x^-1 R^-1 as a plain residue; times R^3 (Montgomery product) = x^-1 R
+        Field r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = is_one(u) ? x1[i] : x2[i];
+        return r * (r2() * r2());
+    }
+
     // x^(p-2) (Fermat); x != 0
     DP_HD Field inverse() const {
         uint32_t e[N];

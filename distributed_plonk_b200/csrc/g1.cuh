@@ -101,10 +101,11 @@ struct alignas(16) G1XYZZ {
         return o;
     }
 
-    // -> affine (one field inversion)
-    DP_HD G1Affine to_affine() const {
+    // -> affine (one field inversion); lone_thread: the caller is a single active lane (see Field::inverse_vartime)
+    DP_HD G1Affine to_affine(bool lone_thread = false) const {
         if (is_inf()) return G1Affine::inf();
-        Fq t = (zz * zzz).inverse();
+        const Fq d = zz * zzz;
+        const Fq t = lone_thread ? d.inverse_vartime() : d.inverse();
         return G1Affine{x * (t * zzz), y * (t * zz)};
     }
 };

@@ -72,7 +72,13 @@ inline MsmGeom msm_make_geom(uint32_t c, bool pre, uint64_t stride) {
     g.stride = (uint32_t)stride;
     g.red_windows = pre ? 1 : g.n_windows;
     g.n_keys = g.red_windows * g.bpw;
-    g.seg = g.bpw < MSM_SEG ? g.bpw : MSM_SEG;
+    // buckets per reduce thread: 16 while the bucket set is large (throughput-bound: 3.4 point operations per bucket);
+    // small sets - a worker's shard of a multi-GPU MSM gets a narrower window - are latency-bound (a thread's chain of
+    // 2*seg additions + a ~1.5*log2(buckets/seg)-step scalar multiple: 2.0 ms for 2^15 buckets at seg 16, ncu r02), so
+    // they get more, shorter threads
+    uint32_t seg = g.bpw >= (1u << 18) ? 16 : g.bpw >= (1u << 17) ? 8 : g.bpw >= (1u << 16) ? 4 : 2;
+    if (seg > MSM_SEG) seg = MSM_SEG;
+    g.seg = g.bpw < seg ? g.bpw : seg;
     g.segs_per_window = g.bpw / g.seg;
     g.slices = g.segs_per_window / 64;  // >= 64 segment sums per slice block
     if (g.slices < 1) g.slices = 1;
@@ -541,7 +547,7 @@ __global__ void msm_final_kernel(const G1XYZZ *slice_sums, MsmGeom g, G1Jacobian
             for (uint32_t k = 0; k < g.c; k++) total = total.dbl();
         total = total.add(part);
     }
-    if (lane == 0) *out = G1JacobianOut::from_affine(total.to_affine());
+    if (lane == 0) *out = G1JacobianOut::from_affine(total.to_affine(true));
 }
 
 // ------------------------------------------------------------------ precomputed window multiples

@@ -62,6 +62,11 @@ def test_field_ops_random_and_edges(E, name):
         a, o = arr([x], nl), np.zeros((1, nl), dtype=np.uint64)
         getattr(E, f"emu_{name}_inverse")(a.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p))
         assert ints(o)[0] == pow(x * rinv % mod, -1, mod) * R % mod
+    # the single-thread inversion of msm_final (binary extended Euclid): same value as Fermat's, edge operands included
+    for x in [1, 2, 3, mod - 1, mod - 2, R % mod, (mod - R) % mod, (1 << 32), (1 << (nl * 64 - 3)) % mod, mod >> 1] + [rng.randrange(1, mod) for _ in range(300)]:
+        a, o = arr([x], nl), np.zeros((1, nl), dtype=np.uint64)
+        getattr(E, f"emu_{name}_inverse_vartime")(a.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p))
+        assert ints(o)[0] == pow(x * rinv % mod, -1, mod) * R % mod, hex(x)
 
 
 @settings(max_examples=200, deadline=None)

@@ -719,6 +719,7 @@ def run_verify(args, torch, dist, ctx, rank, W, log_n, rand_fr, fft_resident, ba
     results = {}
     for md in modes:
         dst.zero_()
+        torch.cuda.synchronize()      # torch's stream (inputs just built) -> the library's own streams
         try:
             fft_resident(rows_in, dst, True, False, True, md)
             barrier()
@@ -759,6 +760,7 @@ def run_verify(args, torch, dist, ctx, rank, W, log_n, rand_fr, fft_resident, ba
     q_host = q.cpu().numpy().view(np.uint64) if rank == 0 else None
     rows_in = gather_rows(q, r_n, c_n, c_n)
     dst = torch.empty(((c_n // W) * r_n, 4), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
     fft_resident(rows_in, dst, False, True, False, mode)
     barrier()
     spot_check("intt_n_horner", dst, q_host, n, r_n, c_n, True, False)
@@ -768,7 +770,9 @@ def run_verify(args, torch, dist, ctx, rank, W, log_n, rand_fr, fft_resident, ba
     s_all = rand_fr(nb, vgen)
     s_all[n + 2:] = 0
     part = torch.zeros(18, dtype=torch.int64, device="cuda")
-    ctx.msm_dev(lo, hi, s_all[lo:hi].contiguous().data_ptr(), hi - lo, part.data_ptr())
+    s_mine = s_all[lo:hi].contiguous()
+    torch.cuda.synchronize()
+    ctx.msm_dev(lo, hi, s_mine.data_ptr(), hi - lo, part.data_ptr())
     parts = [part]
     if W > 1:
         parts = [torch.empty_like(part) for _ in range(W)]

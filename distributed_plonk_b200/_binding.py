@@ -17,7 +17,7 @@ EXPORTS = [
     "dp_quotient_evals", "dp_quotient_evals_dev", "dp_poly_eval", "dp_poly_eval_dev", "dp_poly_lincomb", "dp_poly_lincomb_dev",
     "dp_poly_div_linear", "dp_poly_div_linear_dev", "dp_init_compressed", "dp_get_bases",
     "dp_msm_submit", "dp_msm_collect", "dp_poly_put", "dp_poly_ptr", "dp_poly_get", "dp_poly_free", "dp_commit_dev",
-    "dp_fft_exchange_begin_async", "dp_compute_stream", "dp_fft_dev_p2p_async", "dp_fft1_rows_short", "dp_fft_dev_hint_valid_cols", "dp_ntt_dev_padded",
+    "dp_fft_exchange_begin_async", "dp_compute_stream", "dp_fft_dev_p2p_async", "dp_fft1_rows_short", "dp_fft_dev_hint_valid_cols", "dp_ntt_dev_padded", "dp_debug_set_three_pass",
 ]
 
 
@@ -84,6 +84,7 @@ def bind(cdll: C.CDLL) -> C.CDLL:
         "dp_fft_dev_p2p": (i, [vp, vp, vp, i, i, i]),
         "dp_fft_dev_p2p_async": (i, [vp, vp, vp, i, i, i]),
         "dp_fft_dev_hint_valid_cols": (i, [vp, i, u64]),
+        "dp_debug_set_three_pass": (i, [vp, C.c_uint32]),
         "dp_poly_put": (i, [vp, u64, vp, sz, sz]),
         "dp_poly_ptr": (i, [vp, u64, C.POINTER(vp), C.POINTER(sz)]),
         "dp_poly_get": (i, [vp, u64, sz, sz, vp]),
@@ -438,6 +439,9 @@ class Context:
 
     def debug_set_limits(self, max_contig_log_k=11, max_strided_log_k=9, msm_window_bits=0):
         self._ck(self.lib.dp_debug_set_limits(self.h, max_contig_log_k, max_strided_log_k, msm_window_bits))
+
+    def debug_set_three_pass(self, min_log_n: int):
+        self._ck(self.lib.dp_debug_set_three_pass(self.h, min_log_n))
 
     def msm_breakdown(self):
         a, b, c = C.c_float(), C.c_float(), C.c_float()

@@ -177,6 +177,8 @@ struct dp_ctx {
     uint64_t dev_valid[2] = {0, 0};  // dp_fft_dev_hint_valid_cols: leading non-zero columns of the rows given to dp_fft_dev*
     // pass-planning limits (dp_debug_set_limits lowers them so small tests reach the multi-pass plans)
     uint32_t max_contig_log_k = NTT_WTAB_LOG, max_strided_log_k = NTT_MAX_STRIDED_LOG_K;
+    uint32_t three_pass_min_log = 20;  // smallest domain the three-pass single-worker plan is used for (tests lower it)
+    bool no_three_pass = false;    // knob (env DP_NTT_NO_3PASS / dp_debug_set_limits): single-worker transforms use the 2-D four-pass plan
     int msm_min_blocks = 3;        // experiment knob (env DP_MSM_BLOCKS): register budget of msm_accumulate_kernel for 3, 4 or 5 blocks per SM
     bool ntt_tw_prefetch = false;  // experiment knob (env DP_NTT_PREFETCH)
     int ntt_min_blocks = 3;    // knob (env DP_NTT_BLOCKS): register budget of ntt_tile_kernel for 2 or 3 CTAs per SM (3: -7 % per transform)
@@ -258,6 +260,14 @@ uint32_t pick_log_g(uint32_t log_k, uint64_t n_lanes) {
 
 int launch_pass(dp_ctx *ctx, NttPass &p, uint64_t n_lanes) {
     p.lane_tiles = (uint32_t)(n_lanes >> p.log_g);
+    if (!p.map_set) {  // the two classic tile walks: points contiguous, or lanes contiguous with strided points
+        const bool in_contig = p.in_ps == 1, out_contig = p.out_ps == 1 && !p.out_lc;
+        p.in_a_log = in_contig ? p.log_k - p.in_zlog : 0;
+        p.out_a_log = out_contig ? p.log_k : 0;
+        p.in_a_hi = p.out_a_hi = 0;
+        p.in_ps_a = p.in_ps_b = p.in_ps;
+        p.out_ps_a = p.out_ps_b = p.out_ps;
+    }
     const uint64_t grid = (uint64_t)p.n_outer * p.lane_tiles;
     if (grid == 0 || grid > 0x7fffffffull) return fail(ctx, DP_E_ARG, "ntt pass grid %llu out of range", (unsigned long long)grid);
     const size_t smem = ntt_pass_smem_bytes(p.log_k, p.log_g);
@@ -278,6 +288,32 @@ struct PeerDst {
     uint64_t row_off;
 };
 
+// Three-pass plan of a single worker (n_workers == 1), for domains of >= 2^20 points.  With every row and every
+// column on one device the transform need not stop at the row / column boundary of the 2-D scheme (two passes for the
+// rows, two for the columns at 2^25): the index n = i + r*j of rows[i][j] is cut into three digit groups instead,
+//   n1 = high a bits of j            pass A: 2^a-point transforms along a row, points 2^lj apart, 2^lj-element runs
+//   n2 = (low lj bits of j, high ih bits of i)   pass B: runs of 2^lj contiguous elements from 2^ih row slabs
+//   n3 = low il bits of i            pass C: 2^il-point strided transforms, written as the columns cols[k2][k1]
+// with the usual twiddles omega_N^(k1' * n_low) after A and omega_N^(2^a * k2' * n3) after B.  Same input and output
+// layouts, same values (the transform is unique) - one pass over HBM and one twiddle product per element fewer.
+struct Split3 {
+    uint32_t a, lj, ih, il;
+    bool ok;
+};
+Split3 single_worker_split(const dp_ctx *ctx, const DomainDev &d) {
+    Split3 s{0, 0, 0, 0, false};
+    if (ctx->W != 1 || ctx->no_three_pass || d.log_n < ctx->three_pass_min_log || d.log_r < 4 || d.log_c < 5 || ctx->max_strided_log_k != NTT_MAX_STRIDED_LOG_K || ctx->max_contig_log_k != NTT_WTAB_LOG)
+        return s;
+    const uint32_t lr = d.log_r, lc = d.log_c;
+    s.ih = lr <= 12 ? 3 : lr - 9;
+    s.il = lr - s.ih;
+    s.lj = lc > 11 ? lc - 8 : 3;
+    if (s.lj + s.ih > 9) s.lj = lc - 9;
+    s.a = lc - s.lj;
+    s.ok = s.a <= 9 && s.lj + s.ih <= 9 && s.il <= 9 && s.ih >= 2 && s.ih <= 5 && s.lj >= 2;
+    return s;
+}
+
 // Columns of a row the row phase reads when only the first `valid` hold data (the rest of the row is an
 // implicit zero tail, as for n coefficients on the 8n-point domain): a power-of-two count of whole passes'
 // points, so that the kernel can drop the butterfly stages whose upper input is zero (NttPass.in_zlog).
@@ -286,10 +322,105 @@ uint64_t row_read_cols(const dp_ctx *ctx, const DomainDev &d, uint64_t valid) {
     if (valid >= c) return c;
     if (valid == 0) valid = 1;
     uint64_t unit = 1;  // columns per point of the first pass
-    if (d.log_c > ctx->max_contig_log_k) unit = (uint64_t)1 << (d.log_c - d.log_c / 2);
+    const Split3 s3 = single_worker_split(ctx, d);
+    if (s3.ok)
+        unit = (uint64_t)1 << s3.lj;
+    else if (d.log_c > ctx->max_contig_log_k)
+        unit = (uint64_t)1 << (d.log_c - d.log_c / 2);
     uint64_t pts = (valid + unit - 1) / unit, p2 = 1;
     while (p2 < pts) p2 <<= 1;
     return p2 * unit < c ? p2 * unit : c;
+}
+
+int plan_single_worker3(dp_ctx *ctx, const DomainDev &d, const Split3 &s3, const Fr *src, Fr *w1, Fr *w2, Fr *dst, bool is_inv,
+                        bool is_coset, uint64_t rd_cols) {
+    const uint64_t r = d.r(), c = d.c(), N = d.n();
+    const uint32_t a = s3.a, lj = s3.lj, ih = s3.ih, il = s3.il, b = lj + ih;
+    if (rd_cols == 0 || rd_cols > c) rd_cols = c;
+    {   // ---- pass A: o = row i, lanes = low digit of j (contiguous), points = high digit of j
+        NttPass p = pass_base(ctx, is_inv);
+        p.in = src;
+        p.out = w1;
+        p.log_k = a;
+        p.log_g = pick_log_g(a, (uint64_t)1 << lj);
+        p.n_outer = (uint32_t)r;
+        p.in_os = p.out_os = c;
+        p.in_ls = p.out_ls = 1;
+        p.in_ps = p.out_ps = (uint64_t)1 << lj;
+        const uint64_t pts = rd_cols >> lj;  // row_read_cols: a power of two of whole points (or the whole row)
+        p.in_zlog = pts >= 1 && pts < ((uint64_t)1 << a) ? a - log2_ceil_u64(pts) : (pts == 0 ? a : 0);
+        p.tw_tab = d.H;
+        p.tw_log_n = d.log_n;
+        p.tw_oa = 1;       // omega_N^(+-f * (i + r * j_lo))
+        p.tw_la = r;
+        p.tw_fb = 1;
+        if (is_coset && !is_inv) {  // g^(i + r*j) = g_row[i] * g_col[j]
+            p.pre_a = d.g_row;
+            p.pa_o = 1;
+            p.pre_b = d.g_col;
+            p.pb_l = 1;
+            p.pb_m = (uint64_t)1 << lj;
+        }
+        if (is_inv && is_coset) {  // gi_col of pass C carries 1/r
+            p.post_const_on = 1;
+            p.post_const = d.c_inv;
+        }
+        DP_TRY(launch_pass(ctx, p, (uint64_t)1 << lj));
+    }
+    {   // ---- pass B: o = i_lo, lanes = k1' (2^lj apart), points = (i_hi slow, j_lo fast and contiguous)
+        NttPass p = pass_base(ctx, is_inv);
+        p.in = w1;
+        p.out = w2;
+        p.log_k = b;
+        p.log_g = pick_log_g(b, (uint64_t)1 << a);
+        p.n_outer = 1u << il;
+        p.in_os = c;
+        p.in_ls = (uint64_t)1 << lj;
+        p.out_os = c << ih;                    // w2[i_lo][k2'_lo][k1'][k2'_hi]
+        p.out_ls = (uint64_t)1 << ih;
+        p.map_set = 1;
+        p.in_a_log = lj;                       // point m = i_hi + 2^ih * j_lo: j_lo fast
+        p.in_a_hi = 1;
+        p.in_ps_a = 1;
+        p.in_ps_b = c << il;
+        p.out_a_log = ih;                      // frequency f = k2'_lo + 2^lj * k2'_hi: k2'_hi fast
+        p.out_a_hi = 1;
+        p.out_ps_a = 1;
+        p.out_ps_b = (uint64_t)1 << (a + ih);
+        p.in_ps = p.out_ps = 2;                // (unused with map_set; not 1)
+        p.tw_tab = d.H;
+        p.tw_log_n = d.log_n;
+        p.tw_oa = (uint64_t)1 << a;            // omega_N^(+-2^a * f * i_lo)
+        p.tw_fb = 1;
+        DP_TRY(launch_pass(ctx, p, (uint64_t)1 << a));
+    }
+    {   // ---- pass C: o = k2 = k1' + 2^a * k2'_lo, lanes = k2'_hi (contiguous), points = i_lo; out = cols[k2][k1]
+        NttPass p = pass_base(ctx, is_inv);
+        p.in = w2;
+        p.out = dst;
+        p.log_k = il;
+        p.log_g = pick_log_g(il, (uint64_t)1 << ih);
+        p.n_outer = (uint32_t)c;
+        p.in_os = (uint64_t)1 << ih;
+        p.in_ls = 1;
+        p.in_ps = c << ih;
+        p.out_os = r;
+        p.out_ls = 1;                          // k1 = k2'_hi + 2^ih * k3'
+        p.out_ps = (uint64_t)1 << ih;
+        if (is_inv && is_coset) {  // g^-(k2 + c*k1) / r
+            p.post_a = d.gi_col;
+            p.qa_o = 1;
+            p.post_b = d.gi_pt;
+            p.qb_l = 1;
+            p.qb_f = (uint64_t)1 << ih;
+        } else if (is_inv) {
+            p.post_const_on = 1;
+            p.post_const = d.n_inv;
+        }
+        DP_TRY(launch_pass(ctx, p, (uint64_t)1 << ih));
+    }
+    (void)N;
+    return DP_OK;
 }
 
 int plan_row_phase(dp_ctx *ctx, const DomainDev &d, const Fr *src, Fr *dst, Fr *scratch, uint64_t n_rows,
@@ -895,6 +1026,47 @@ void p2p_release_slot(dp_ctx *ctx, const Fr *slot) {
     if (s < 2) ctx->p2p_slot_busy[s] = false;
 }
 
+// rows handed in short (dp_fft1 with len < c, dp_fft1_rows_short): the first pass reads rd columns of every row;
+// whatever lies between a row's own length and rd is zero-filled here (compute stream, after the copy-in), the rest
+// of the tail is never touched.  Returns rd.
+uint64_t fill_short_rows(dp_ctx *ctx, FftTask &t, const DomainDev &d) {
+    const uint64_t c = d.c();
+    uint64_t valid = 1;
+    bool same = true;
+    for (uint64_t i = 0; i < t.n_rows; i++) {
+        if (t.row_len[i] > valid) valid = t.row_len[i];
+        same = same && t.row_len[i] == t.row_len[0];
+    }
+    const uint64_t rd = row_read_cols(ctx, d, valid);
+    if (same) {
+        if (t.n_rows && t.row_len[0] < rd)
+            cudaMemset2DAsync(t.rows + t.row_len[0], c * sizeof(Fr), 0, (rd - t.row_len[0]) * sizeof(Fr), t.n_rows, ctx->stream);
+    } else {
+        for (uint64_t i = 0; i < t.n_rows; i++)
+            if (t.row_len[i] < rd) cudaMemsetAsync(t.rows + i * c + t.row_len[i], 0, (rd - t.row_len[i]) * sizeof(Fr), ctx->stream);
+    }
+    return rd;
+}
+
+// one worker: the whole transform of a task as three passes rows -> scratch -> rows -> cols (plan_single_worker3)
+int run_single_worker(dp_ctx *ctx, FftTask &t) {
+    if (t.exchanged) return fail(ctx, DP_E_STATE, "fft task: the transform of this task was already queued");
+    if (t.rows_filled != t.n_rows) return fail(ctx, DP_E_STATE, "fft task: %llu of %llu rows received", (unsigned long long)t.rows_filled, (unsigned long long)t.n_rows);
+    const DomainDev &d = ctx->dom[t.is_quot ? 1 : 0];
+    const Split3 s3 = single_worker_split(ctx, d);
+    Scratch tmp(ctx->pool);  // stream-ordered: handed back when the kernels that use it are already queued
+    Fr *w1 = tmp.get<Fr>(d.n());
+    if (!t.cols) t.cols = (Fr *)ctx->pool.alloc(t.n_cols * d.r() * sizeof(Fr));
+    if (!w1 || !t.cols) return fail(ctx, DP_E_OOM, "single-worker transform buffers");
+    cudaStreamWaitEvent(ctx->stream, t.ev_in, 0);
+    const uint64_t rd = fill_short_rows(ctx, t, d);
+    DP_TRY(plan_single_worker3(ctx, d, s3, t.rows, w1, t.rows, t.cols, t.is_inv, t.is_coset, rd));
+    DP_CUDA(ctx, cudaEventRecord(t.ev_c, ctx->stream));
+    t.send = t.recv = t.rows;
+    t.row_phase_done = t.exchanged = true;
+    return DP_OK;
+}
+
 int run_row_phase(dp_ctx *ctx, FftTask &t, bool use_p2p = false) {
     if (t.row_phase_done) return DP_OK;
     if (t.rows_filled != t.n_rows) return fail(ctx, DP_E_STATE, "fft task: %llu of %llu rows received", (unsigned long long)t.rows_filled, (unsigned long long)t.n_rows);
@@ -924,22 +1096,7 @@ int run_row_phase(dp_ctx *ctx, FftTask &t, bool use_p2p = false) {
         t.send = t.rows;
     }
     cudaStreamWaitEvent(ctx->stream, t.ev_in, 0);
-    // rows handed in short (dp_fft1 with len < c, dp_fft1_rows_short): the row kernel reads rd columns of every row;
-    // whatever lies between a row's own length and rd is zero-filled here, the rest of the tail is never touched
-    uint64_t valid = 1;
-    bool same = true;
-    for (uint64_t i = 0; i < t.n_rows; i++) {
-        if (t.row_len[i] > valid) valid = t.row_len[i];
-        same = same && t.row_len[i] == t.row_len[0];
-    }
-    const uint64_t rd = row_read_cols(ctx, d, valid);
-    if (same) {
-        if (t.n_rows && t.row_len[0] < rd)
-            cudaMemset2DAsync(t.rows + t.row_len[0], c * sizeof(Fr), 0, (rd - t.row_len[0]) * sizeof(Fr), t.n_rows, ctx->stream);
-    } else {
-        for (uint64_t i = 0; i < t.n_rows; i++)
-            if (t.row_len[i] < rd) cudaMemsetAsync(t.rows + i * c + t.row_len[i], 0, (rd - t.row_len[i]) * sizeof(Fr), ctx->stream);
-    }
+    const uint64_t rd = fill_short_rows(ctx, t, d);
     int rc = plan_row_phase(ctx, d, t.rows, t.send, scratch, t.n_rows, t.row_start, t.is_inv, t.is_coset, ctx->W,
                             use_p2p ? &peers : nullptr, rd);
     ctx->pool.release(scratch);
@@ -995,6 +1152,7 @@ int dp_create(int cuda_device, uint64_t me, uint64_t n_workers, dp_ctx **out) {
     if (const char *e = getenv("DP_MSM_CHUNK")) ctx->msm_chunk = (uint32_t)atoi(e) >= 8 ? (uint32_t)atoi(e) : 0;
     if (const char *e = getenv("DP_NTT_BLOCKS")) ctx->ntt_min_blocks = atoi(e) == 2 ? 2 : 3;
     if (const char *e = getenv("DP_NTT_PREFETCH")) ctx->ntt_tw_prefetch = atoi(e) != 0;
+    if (const char *e = getenv("DP_NTT_NO_3PASS")) ctx->no_three_pass = atoi(e) != 0;
     if (const char *e = getenv("DP_MSM_BLOCKS")) ctx->msm_min_blocks = atoi(e) >= 3 && atoi(e) <= 5 ? atoi(e) : 3;
     ctx->me = me;
     ctx->W = n_workers;
@@ -1567,6 +1725,10 @@ int dp_fft2_prepare(dp_ctx *ctx, uint64_t id) {
         return call_end(ctx, true);
     }
     call_begin(ctx);
+    if (single_worker_split(ctx, ctx->dom[t->is_quot ? 1 : 0]).ok) {
+        DP_TRY(run_single_worker(ctx, *t));
+        return call_end(ctx, false);
+    }
     DP_TRY(run_row_phase(ctx, *t));
     t->recv = t->send;
     DP_TRY(queue_col_phase(ctx, *t));
@@ -1617,9 +1779,15 @@ int dp_fft_dev(dp_ctx *ctx, const void *rows_dev, void *cols_dev, int is_quot, i
     call_begin(ctx);
     Scratch tmp(ctx->pool);
     Fr *work = tmp.get<Fr>(N);
-    const bool need_scratch = d.log_c > ctx->max_contig_log_k;
+    const Split3 s3 = single_worker_split(ctx, d);
+    const bool need_scratch = s3.ok || d.log_c > ctx->max_contig_log_k;
     Fr *scratch = need_scratch ? tmp.get<Fr>(N) : nullptr;
     if (!work || (need_scratch && !scratch)) return fail(ctx, DP_E_OOM, "dp_fft_dev buffers");
+    if (s3.ok) {
+        DP_TRY(plan_single_worker3(ctx, d, s3, (const Fr *)rows_dev, work, scratch, (Fr *)cols_dev, is_inv != 0, is_coset != 0,
+                                   dev_rd_cols(ctx, d, is_quot, is_inv)));
+        return call_end(ctx, true);  // synchronises before the scratch goes back to the pool
+    }
     DP_TRY(plan_row_phase(ctx, d, (const Fr *)rows_dev, work, scratch, d.r(), 0, is_inv != 0, is_coset != 0, 1, nullptr,
                           dev_rd_cols(ctx, d, is_quot, is_inv)));
     DP_TRY(plan_col_phase(ctx, d, work, (Fr *)cols_dev, d.c(), 0, is_inv != 0, is_coset != 0));
@@ -1906,6 +2074,13 @@ int dp_debug_set_limits(dp_ctx *ctx, uint32_t max_contig_log_k, uint32_t max_str
     ctx->max_contig_log_k = max_contig_log_k;
     ctx->max_strided_log_k = max_strided_log_k;
     ctx->msm_force_c = msm_window_bits;
+    return DP_OK;
+}
+
+int dp_debug_set_three_pass(dp_ctx *ctx, uint32_t min_log_n) {
+    if (!ctx) return DP_E_ARG;
+    ctx->no_three_pass = min_log_n == 0;
+    ctx->three_pass_min_log = min_log_n ? min_log_n : 20;
     return DP_OK;
 }
 

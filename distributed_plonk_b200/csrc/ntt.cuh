@@ -93,6 +93,17 @@ struct NttPass {
     // butterfly stages then have a zero upper input each and collapse into ONE product per element,
     // out[j + V*t] = x[j] * omega_K^(j * bitrev(t)), instead of a load and up to three products.
     uint32_t in_zlog;
+    // Order in which the threads of a block walk the tile when it is loaded / stored, and the element address that goes
+    // with it: work item = a + A * (lane + G * b) with A = 2^a_log "fast" point values and the rest "slow" ones;
+    //   point index  = a + A * b                      (a_hi == 0)      or   b + (points / A) * a      (a_hi == 1)
+    //   address      = o * os + lane * ls + a * ps_a + b * ps_b
+    // Threads with consecutive a (then consecutive lanes) touch consecutive addresses when ps_a = 1 and ls = A.
+    // a_log = log2(points): points contiguous (ps_a = 1);  a_log = 0: lanes contiguous, points strided by ps_b;
+    // 0 < a_log < log2(points), a_hi = 1: the point index is made of two digit groups that are contiguous runs of
+    // A elements strided by ps_b - the middle pass of the three-pass single-worker plan.  Filled in by launch_pass()
+    // from in_ps / out_ps unless map_set.
+    uint32_t map_set, in_a_log, in_a_hi, out_a_log, out_a_hi;
+    uint64_t in_ps_a, in_ps_b, out_ps_a, out_ps_b;
     uint32_t tw_prefetch;             // experiment knob: pull the epilogue's omega_N twiddles towards L2 while the tile is transformed
 };
 
@@ -182,6 +193,19 @@ DP_D void cp_async_wait_all() {}
 DP_D void prefetch_l2(const void *) {}
 #endif
 
+// work item -> (point index, lane, fast digit a, slow digit b) for the tile walk described at NttPass::in_a_log
+struct TileIdx {
+    uint32_t pt, g, a, b;
+};
+DP_D TileIdx tile_idx(uint32_t idx, uint32_t a_log, uint32_t a_hi, uint32_t log_g, uint32_t log_pts) {
+    TileIdx t;
+    t.a = idx & ((1u << a_log) - 1);
+    t.g = (idx >> a_log) & ((1u << log_g) - 1);
+    t.b = idx >> (a_log + log_g);
+    t.pt = a_hi ? t.b + (t.a << (log_pts - a_log)) : t.a + (t.b << a_log);
+    return t;
+}
+
 // dynamic shared memory: [lo plane | hi plane] of G*(K+1) uint4 each, [w_lo | w_hi] of K uint4 each,
 // one 8-byte mbarrier
 DP_HD size_t ntt_pass_smem_bytes(uint32_t log_k, uint32_t log_g) {
@@ -225,18 +249,11 @@ __global__ void __launch_bounds__(NTT_TPB, MINB) ntt_tile_kernel(NttPass p) {
     // ---- the omega_N twiddles of the epilogue are known now: optionally pull them towards L2 while the tile is loaded
     // and transformed (the table of a 2^25-point domain is 512 MiB; a demand miss in the store loop costs ~1 us).
     // Measured on B200 (profiles/README.md): DRAM reads of the 2-D twiddle pass grow from 4.3 to 6.8 GB - off by default.
-    const bool out_pts_contig = (p.out_ps == 1 && !p.out_lc);
     if (p.tw_tab && p.tw_prefetch) {
         const uint64_t n_tw = (uint64_t)1 << p.tw_log_n, half_tw = n_tw >> 1;
         for (uint32_t idx = tid; idx < tile; idx += NTT_TPB) {
-            uint32_t f, g;
-            if (out_pts_contig) {
-                f = idx & (K - 1);
-                g = idx >> p.log_k;
-            } else {
-                g = idx & (G - 1);
-                f = idx >> p.log_g;
-            }
+            const TileIdx ti = tile_idx(idx, p.out_a_log, p.out_a_hi, p.log_g, p.log_k);
+            const uint32_t f = ti.pt, g = ti.g;
             const uint64_t lane = lane0 + g;
             uint64_t e = ((p.tw_la * lane + p.tw_oa * o + p.tw_c0) * (p.tw_fb * f + p.tw_lb * lane)) & (n_tw - 1);
             if (p.tw_inverse) e = (n_tw - e) & (n_tw - 1);
@@ -249,18 +266,11 @@ __global__ void __launch_bounds__(NTT_TPB, MINB) ntt_tile_kernel(NttPass p) {
     const uint32_t vlog = p.log_k - p.in_zlog, V = 1u << vlog;  // points >= V of every lane are implicit zeros
     {
         const Fr *src = p.in + (uint64_t)o * p.in_os + (uint64_t)lane0 * p.in_ls;
-        const bool pts_contig = (p.in_ps == 1);
         const uint32_t n_ld = G << vlog;
         for (uint32_t idx = tid; idx < n_ld; idx += NTT_TPB) {
-            uint32_t m, g;
-            if (pts_contig) {
-                m = idx & (V - 1);
-                g = idx >> vlog;
-            } else {
-                g = idx & (G - 1);
-                m = idx >> p.log_g;
-            }
-            const uint4 *q = reinterpret_cast<const uint4 *>(src + (uint64_t)g * p.in_ls + (uint64_t)m * p.in_ps);
+            const TileIdx ti = tile_idx(idx, p.in_a_log, p.in_a_hi, p.log_g, vlog);
+            const uint32_t m = ti.pt, g = ti.g;
+            const uint4 *q = reinterpret_cast<const uint4 *>(src + (uint64_t)g * p.in_ls + (uint64_t)ti.a * p.in_ps_a + (uint64_t)ti.b * p.in_ps_b);
             cp_async16(lo + g * pitch + m, q);
             cp_async16(hi + g * pitch + m, q + 1);
         }
@@ -269,14 +279,8 @@ __global__ void __launch_bounds__(NTT_TPB, MINB) ntt_tile_kernel(NttPass p) {
         // Zero inputs stay zero: whole warps skip both products on padded data.
         if (p.pre_a) {
             for (uint32_t idx = tid; idx < n_ld; idx += NTT_TPB) {
-                uint32_t m, g;
-                if (pts_contig) {
-                    m = idx & (V - 1);
-                    g = idx >> vlog;
-                } else {
-                    g = idx & (G - 1);
-                    m = idx >> p.log_g;
-                }
+                const TileIdx ti = tile_idx(idx, p.in_a_log, p.in_a_hi, p.log_g, vlog);
+                const uint32_t m = ti.pt, g = ti.g;
                 Fr v = smem_ld(lo, hi, g * pitch + m);
                 if (!v.is_zero()) {
                     const uint64_t lane = lane0 + g;
@@ -369,17 +373,10 @@ __global__ void __launch_bounds__(NTT_TPB, MINB) ntt_tile_kernel(NttPass p) {
     // ---- write out (frequency f sits at bit-reversed position), fused twiddle / scaling
     {
         Fr *dst = p.out + (uint64_t)o * p.out_os;
-        const bool pts_contig = out_pts_contig;
 #pragma unroll 2
         for (uint32_t idx = tid; idx < tile; idx += NTT_TPB) {
-            uint32_t f, g;
-            if (pts_contig) {
-                f = idx & (K - 1);
-                g = idx >> p.log_k;
-            } else {
-                g = idx & (G - 1);
-                f = idx >> p.log_g;
-            }
+            const TileIdx ti = tile_idx(idx, p.out_a_log, p.out_a_hi, p.log_g, p.log_k);
+            const uint32_t f = ti.pt, g = ti.g;
             const uint32_t pos = p.log_k ? (__brev(f) >> (32 - p.log_k)) : 0;
             Fr v = smem_ld(lo, hi, g * pitch + pos);
             const uint64_t lane = lane0 + g;
@@ -398,8 +395,12 @@ __global__ void __launch_bounds__(NTT_TPB, MINB) ntt_tile_kernel(NttPass p) {
                 gmem_st(pd + (col & (((uint64_t)1 << p.split_log) - 1)), v);
                 continue;
             }
-            if (p.split_on) col = (col >> p.split_log) * p.split_stride + (col & (((uint64_t)1 << p.split_log) - 1));
-            gmem_st(dst + lane * p.out_ls + col, v);
+            if (p.split_on) {
+                col = (col >> p.split_log) * p.split_stride + (col & (((uint64_t)1 << p.split_log) - 1));
+                gmem_st(dst + lane * p.out_ls + col, v);
+                continue;
+            }
+            gmem_st(dst + lane * p.out_ls + lane * p.out_lc + (uint64_t)ti.a * p.out_ps_a + (uint64_t)ti.b * p.out_ps_b, v);
         }
     }
 }

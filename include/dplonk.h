@@ -281,6 +281,9 @@ int dp_debug_gen_bases(dp_ctx *ctx, uint64_t seed, size_t n, void *out);
  * large enough; 1 = per-window bucket sets with automatic width; c >= 2 = per-window sets of width c)
  * so that small inputs exercise the multi-pass NTT plans and every MSM geometry. */
 int dp_debug_set_limits(dp_ctx *ctx, uint32_t max_contig_log_k, uint32_t max_strided_log_k, int msm_window_bits);
+/* test hook: the single-worker three-pass transform plan is used for domains of at least
+ * 2^min_log_n points (default 20); 0 switches it off (the 2-D row / column plan is used everywhere). */
+int dp_debug_set_three_pass(dp_ctx *ctx, uint32_t min_log_n);
 
 /* device-resident variants used by bench.py to time the kernels with inputs already in HBM.
  * All pointers are DEVICE pointers owned by the caller (e.g. torch tensors). */

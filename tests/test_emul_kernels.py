@@ -451,3 +451,24 @@ def test_whole_ntt_fused_coset_tables_and_short_inputs(orc, emul_lib, limits, do
             assert np.array_equal(buf, ref), f"ntt_dev_padded log_n={log_n} inv={inv} coset={cos}"
     common.check_whole_ntt(orc, c, 3, 77)              # a size that is neither domain: scaling kernel fallback
     c.close()
+
+
+@pytest.mark.parametrize("logn,logq", [(6, 9), (8, 11), (9, 12)])
+def test_single_worker_three_pass_plan(orc, emul_lib, logn, logq):
+    """n_workers == 1: the transform as three passes over digit groups of the element index instead of two row and two
+    column passes (plan_single_worker3) - same rows in, same columns out, every flag combination, full and short rows,
+    the fft1 / fft2 task path and the resident dp_fft_dev path; domains too small for the split fall back"""
+    w = PlonkSlave(emul_lib, 0, 1)
+    w.init([b""], 1 << logn, 1 << logq)
+    w.ctx.debug_set_three_pass(9)
+    common.check_distributed_fft(orc, [w], logq, True, 21, host_copy)
+    common.check_distributed_fft(orc, [w], logn, False, 22, host_copy)
+    common.check_distributed_fft(orc, [w], logq, True, 23, host_copy, n_in=(1 << logq) // 8)
+    c_q = (1 << logq) >> (logq >> 1)
+    for k, row_len in enumerate((c_q // 8, 1, 3, c_q // 2 + 1)):
+        common.check_short_rows(orc, [w], logq, True, row_len, 30 + k)
+    for valid in (c_q // 8, 5, c_q):
+        common.check_dev_valid_cols_hint(orc, w.ctx, logq, True, valid, 40 + valid, _HostBuf)
+    w.ctx.debug_set_three_pass(0)                          # off: the 2-D plan gives the same bytes
+    common.check_distributed_fft(orc, [w], logq, True, 24, host_copy)
+    w.close()

@@ -45,6 +45,7 @@ struct FrParams {
     // m * r[1] = (m << 32) - m need no multiplier: 16 of the 128 multiply-accumulates of a product become
     // additions on the ALU pipe (the multiplier pipe is what bounds the NTT)
     static constexpr bool LOW_LIMBS_ARE_1_AND_FFFFFFFF = true;
+    static constexpr bool DEDICATED_SQR = false;
 };
 
 struct FqParams {
@@ -74,6 +75,7 @@ struct FqParams {
     // slowdown of msm_reduce).  A real call costs ~30 register moves (args travel in registers).
     static constexpr bool OUTLINE_MUL = true;
     static constexpr bool LOW_LIMBS_ARE_1_AND_FFFFFFFF = false;
+    static constexpr bool DEDICATED_SQR = false;   // see Field::sqr()
 };
 
 // ------------------------------------------------------------------------------ field
@@ -234,7 +236,90 @@ struct Field : Limbs<P::N> {
         final_sub(z.l);
         return z;
     }
-    DP_HD Field sqr() const { return (*this) * (*this); }
+    // a^2.  The products a_i * a_j with i != j come in pairs: they are formed once and doubled, then the squares a_i^2
+    // are added and the 2N-word result goes through a word-serial Montgomery reduction.  2N^2 + N(N+1) multiply
+    // instructions of the single-result kind (IMAD / IMAD.HI with carry) instead of N^2 wide ones with carry plus 2N^2
+    // single ones: at Fq size 444 against 576 pipe-equivalents, 27 % less than a general product (two of the ten
+    // products of a mixed addition and three of the nine of a doubling are squarings).
+    DP_HD static Field sqr_inline(const Field &x) {
+        const uint32_t *a = x.l;
+        uint32_t t[2 * N];
+        // ---- sum_{i<j} a_i a_j 2^(32(i+j)): row i holds a_i * (a_{i+1} .. a_{N-1}) at word 2i+1; after row i the partial
+        // sum is below 2^(32(i+N+1)), so a row never carries out of its own top word i+N
+        t[0] = 0;
+#pragma unroll
+        for (int j = 1; j < N; j++) t[j] = ptx::mul_lo(a[0], a[j]);
+        t[N] = 0;
+        t[2] = ptx::mad_hi_cc(a[0], a[1], t[2]);
+#pragma unroll
+        for (int j = 2; j < N - 1; j++) t[j + 1] = ptx::madc_hi_cc(a[0], a[j], t[j + 1]);
+        t[N] = ptx::madc_hi(a[0], a[N - 1], t[N]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) {
+            t[2 * i + 1] = ptx::mad_lo_cc(a[i], a[i + 1], t[2 * i + 1]);
+#pragma unroll
+            for (int j = i + 2; j < N; j++) t[i + j] = ptx::madc_lo_cc(a[i], a[j], t[i + j]);
+            t[i + N] = ptx::addc(0u, 0u);
+            if (i + 2 < N) {
+                t[2 * i + 2] = ptx::mad_hi_cc(a[i], a[i + 1], t[2 * i + 2]);
+#pragma unroll
+                for (int j = i + 2; j < N - 1; j++) t[i + j + 1] = ptx::madc_hi_cc(a[i], a[j], t[i + j + 1]);
+                t[i + N] = ptx::madc_hi(a[i], a[N - 1], t[i + N]);
+            } else {  // last row: the single product a_{N-2} * a_{N-1}
+                t[2 * i + 2] = ptx::mad_hi_cc(a[i], a[i + 1], t[2 * i + 2]);  // (the carry flag it sets is not used)
+            }
+        }
+        // ---- double, add the squares a_i^2 at word 2i (one carry chain over all 2N words)
+        t[2 * N - 1] = t[2 * N - 2] >> 31;
+#pragma unroll
+        for (int k = 2 * N - 2; k >= 1; k--) t[k] = (t[k] << 1) | (t[k - 1] >> 31);
+        t[0] = ptx::mad_lo_cc(a[0], a[0], 0u);
+        t[1] = ptx::madc_hi_cc(a[0], a[0], t[1]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) {
+            t[2 * i] = ptx::madc_lo_cc(a[i], a[i], t[2 * i]);
+            t[2 * i + 1] = ptx::madc_hi_cc(a[i], a[i], t[2 * i + 1]);
+        }
+        t[2 * N - 2] = ptx::madc_lo_cc(a[N - 1], a[N - 1], t[2 * N - 2]);
+        t[2 * N - 1] = ptx::madc_hi(a[N - 1], a[N - 1], t[2 * N - 1]);
+        // ---- word-serial reduction: step i clears word i with m * p; the carries out of the low and the high chain go
+        // into word i+N+1 at the next step (value 0..2)
+        uint32_t pending = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            const uint32_t m = t[i] * P::INV;
+            t[i] = ptx::mad_lo_cc(m, P::mod(0), t[i]);
+#pragma unroll
+            for (int j = 1; j < N; j++) t[i + j] = ptx::madc_lo_cc(m, P::mod(j), t[i + j]);
+            t[i + N] = ptx::addc_cc(t[i + N], pending);
+            const uint32_t c_lo = ptx::addc(0u, 0u);
+            t[i + 1] = ptx::mad_hi_cc(m, P::mod(0), t[i + 1]);
+#pragma unroll
+            for (int j = 1; j < N; j++) t[i + j + 1] = ptx::madc_hi_cc(m, P::mod(j), t[i + j + 1]);
+            pending = c_lo + ptx::addc(0u, 0u);
+        }
+        Field z;
+#pragma unroll
+        for (int i = 0; i < N; i++) z.l[i] = t[N + i];
+        final_sub(z.l);
+        return z;
+    }
+#if defined(__CUDACC__)
+    __device__ __noinline__ static Field sqr_outlined(Field a) { return sqr_inline(a); }
+#endif
+    // MEASURED AND NOT ADOPTED (profiles/r02c_msm_shard_profile.txt): ptxas splits the single-result multiply-adds
+    // with carry into IMAD + IADD3.X pairs, the additions land on the ALU pipe next to the carry work that is already
+    // there, and msm_accumulate got 5 % SLOWER (20.2 against 19.3 ms) although 13 % of its multiplier work is gone.
+    // sqr() therefore stays the general product; sqr_inline() is kept, tested bit for bit (tests/test_emul_field.py).
+    DP_HD Field sqr() const {
+        if (P::DEDICATED_SQR) {
+#if defined(__CUDA_ARCH__)
+            if (P::OUTLINE_MUL) return sqr_outlined(*this);
+#endif
+            return sqr_inline(*this);
+        }
+        return (*this) * (*this);
+    }
 
     DP_HD Field &operator+=(const Field &b) { return *this = *this + b; }
     DP_HD Field &operator-=(const Field &b) { return *this = *this - b; }

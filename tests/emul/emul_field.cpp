@@ -19,6 +19,8 @@ BINOP(emu_fq_add, Fq, +)
 BINOP(emu_fq_sub, Fq, -)
 void emu_fr_inverse(const void *a, void *o) { *(Fr *)o = ((const Fr *)a)->inverse(); }
 void emu_fq_inverse(const void *a, void *o) { *(Fq *)o = ((const Fq *)a)->inverse(); }
+void emu_fr_sqr(const void *a, void *o, uint64_t n) { for (uint64_t i = 0; i < n; i++) ((Fr *)o)[i] = Fr::sqr_inline(((const Fr *)a)[i]); }
+void emu_fq_sqr(const void *a, void *o, uint64_t n) { for (uint64_t i = 0; i < n; i++) ((Fq *)o)[i] = Fq::sqr_inline(((const Fq *)a)[i]); }
 void emu_fr_inverse_vartime(const void *a, void *o) { *(Fr *)o = ((const Fr *)a)->inverse_vartime(); }
 void emu_fq_inverse_vartime(const void *a, void *o) { *(Fq *)o = ((const Fq *)a)->inverse_vartime(); }
 void emu_fr_pow(const void *a, uint64_t e, void *o) { *(Fr *)o = ((const Fr *)a)->pow(e); }

@@ -56,6 +56,10 @@ def test_field_ops_random_and_edges(E, name):
     ys = list(reversed(edge)) + [rng.randrange(mod) for _ in range(4000)]
     rinv = pow(R, -1, mod)
     assert binop(E, name, "mul", xs, ys, nl) == [x * y * rinv % mod for x, y in zip(xs, ys)]
+    # the dedicated squaring (symmetric partial products + separate reduction) against Python and against the product
+    A, O = arr(xs + ys, nl), np.empty((len(xs) + len(ys), nl), dtype=np.uint64)
+    getattr(E, f"emu_{name}_sqr")(A.ctypes.data_as(C.c_void_p), O.ctypes.data_as(C.c_void_p), C.c_uint64(A.shape[0]))
+    assert ints(O) == [x * x * rinv % mod for x in xs + ys]
     assert binop(E, name, "add", xs, ys, nl) == [(x + y) % mod for x, y in zip(xs, ys)]
     assert binop(E, name, "sub", xs, ys, nl) == [(x - y) % mod for x, y in zip(xs, ys)]
     for x in (1, 2, mod - 1, rng.randrange(1, mod)):

@@ -602,13 +602,20 @@ def main():
         "ntt_tile_8n_frac": (macs_ntt / (statistics.mean(stats["ntt_m_ms"]) * 1e-3) / mac_peak) if stats["ntt_m_ms"] else None,
         "carry_form_ceiling_frac": 28.3 / 61.9,
     }
+    ntt_traffic = None
+    try:
+        ent = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("ntt_tile_kernel", {}).get(str(log_m))
+        if W == 1 and ent:
+            ntt_traffic = ent["bytes"]
+    except (OSError, ValueError, KeyError):
+        pass
     ntt_hbm = None
     if stats["ntt_m_ms"]:
         per_tr = statistics.mean(stats["ntt_m_ms"])
         per = per_tr / n_pass
         ntt_hbm = {"kernel": "ntt_tile_kernel(8n)", "achieved": 64 * m / (per * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                    "frac": 64 * m / (per * 1e-3) / 1e9 / peak, "avg_launch_ms": per, "algorithmic_bytes_per_launch": 64 * m,
-                   "passes_per_transform": n_pass, "transform_ms": per_tr,
+                   "passes_per_transform": n_pass, "transform_ms": per_tr, "traffic": ntt_traffic,
                    # against SURVEY 8d's bytes_min = 64 N for the WHOLE transform (one read + one write of every element)
                    "per_transform_frac_of_bytes_min": 64 * m / (per_tr * 1e-3) / 1e9 / peak}
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -14,9 +14,13 @@ timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -30 > $out/${tag}_py
 timeout 600 python bench.py --steps 3 --warmup 3 > $out/${tag}_bench_1gpu.json 2> $out/${tag}_bench_1gpu.err
 quick="python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-verify"
 timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $out/${tag}_launches_bench.csv $quick > /dev/null 2>&1
-# the four passes of one 2^25 coset transform (launches 0-20 of ntt_tile_kernel are the 2^22 passes of the warm-up step)
-timeout 240 ncu --set full --clock-control none --import-source on -k regex:ntt_tile_kernel -s 25 -c 4 -f -o $out/${tag}_ntt_tile_2p25 $quick > /dev/null 2>&1
-for k in msm_accumulate_kernel quotient_kernel msm_reduce_kernel; do
+# the three passes of one 2^25 coset transform (launches 0-20 of ntt_tile_kernel are the 7 x 3 passes of the 2^22 transforms
+# of the warm-up step; 21-23 the first 2^25 transform)
+timeout 240 ncu --set full --clock-control none --import-source on -k regex:ntt_tile_kernel -s 24 -c 3 -f -o $out/${tag}_ntt_tile_2p25 $quick > /dev/null 2>&1
+for k in msm_accumulate_kernel msm_reduce_kernel; do
     timeout 200 ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -f -o $out/${tag}_$k $quick > /dev/null 2>&1
 done
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:quotient_kernel -s 1 -c 1 -f -o $out/${tag}_quotient_kernel $quick > /dev/null 2>&1
+# BASELINE config 1 (2^20 gates, one GPU) as a bench line
+timeout 300 python bench.py --steps 3 --warmup 3 --log-n 20 --no-cpu > $out/${tag}_bench_1gpu_2p20.json 2> /dev/null
 ls -la $out | tail -20

@@ -391,7 +391,7 @@ def main():
             barrier()
             t0 = time.perf_counter()
         k = 0
-        for cnt in ROUNDS if not record else ROUNDS:
+        for cnt in ROUNDS:
             ctx.msm_dev_batch([(lo, hi, scal[(k + j) % 3].data_ptr(), hi - lo, msm_outs[j].data_ptr()) for j in range(cnt)])
             k += cnt
         if record:

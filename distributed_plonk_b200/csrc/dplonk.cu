@@ -159,7 +159,10 @@ struct dp_ctx {
     uint64_t arena_bytes = 0;
     Fr *peer_arena[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     uint64_t p2p_seq = 0;           // exchanges issued so far; must advance identically on every rank
-    bool p2p_slot_busy[2] = {false, false};  // receive slot written by a row phase whose column phase has not consumed it yet
+    // receive slots of the arena: as many as fit (one slot = the receive matrix of the larger domain, at least two);
+    // busy = written by a row phase whose column phase has not consumed it yet
+    static constexpr uint32_t P2P_MAX_SLOTS = 64;
+    bool p2p_slot_busy[P2P_MAX_SLOTS] = {};
     uint32_t bar_seq = 0;           // device-side barriers issued so far (p2p_barrier_kernel)
     // worker-resident polynomials (dp_poly_*): id -> device buffer of `cap` Fr, zero beyond what was written
     struct Poly {
@@ -997,33 +1000,56 @@ bool p2p_ready(const dp_ctx *ctx) {
     return true;
 }
 
-// Receive slot of the next exchange in every rank's arena (same sequence number on all ranks).  The arena
-// holds TWO slots, so at most two fused exchanges may be between their row phase and their column phase per
-// context: a third one would overwrite a receive matrix nobody has read yet.  The slot is only reserved here;
-// p2p_commit_slot() consumes the sequence number once the row kernels were queued without error, so a
-// failed call leaves every rank's sequence where it was.
+// Receive slots of the arena.  One slot holds the receive matrix [r][c/W] of the LARGER of the two domains; the arena
+// holds as many as fit (every rank creates it with the same size and has the same domains, so every rank computes
+// the same geometry), at least two.  Exchange number k uses slot k mod n_slots on every rank - the ranks issue their
+// exchanges in the same order, as they would for a collective - so at most n_slots fused exchanges may be between
+// their row phase and their column phase per context: one more would overwrite a receive matrix nobody has read
+// yet.  The reference dispatcher keeps up to 26 transforms in flight (join_all, dispatcher2.rs:382-414): a worker
+// serving it creates an arena of 32 slots (rust/worker_gpu.rs); bench.py's resident path needs two.
+// The slot is only reserved here; p2p_commit_slot() consumes the sequence number once the row kernels were queued
+// without error, so a failed call leaves every rank's sequence where it was.
+struct SlotGeom {
+    uint64_t slot_elems, n_slots;
+};
+SlotGeom p2p_slot_geom(const dp_ctx *ctx) {
+    uint64_t need = 0;
+    for (int k = 0; k < 2; k++) {
+        const uint64_t b = ctx->dom[k].n() / ctx->W;  // r * (c / W) elements
+        if (ctx->dom[k].H && b > need) need = b;
+    }
+    SlotGeom g{need, 0};
+    if (need == 0 || !ctx->arena) return g;
+    g.n_slots = (ctx->arena_bytes - ARENA_HEADER_BYTES) / (need * sizeof(Fr));
+    if (g.n_slots > dp_ctx::P2P_MAX_SLOTS) g.n_slots = dp_ctx::P2P_MAX_SLOTS;
+    return g;
+}
 int p2p_next_slot(dp_ctx *ctx, uint64_t recv_bytes, PeerDst &dst, Fr *&my_slot, uint64_t row_off) {
-    const uint64_t slot_bytes = (ctx->arena_bytes - ARENA_HEADER_BYTES) / 2;
-    if (recv_bytes > slot_bytes) return fail(ctx, DP_E_COMM, "peer arena slot %llu B < receive matrix %llu B", (unsigned long long)slot_bytes, (unsigned long long)recv_bytes);
-    const uint64_t s = ctx->p2p_seq & 1;
+    const SlotGeom g = p2p_slot_geom(ctx);
+    if (g.n_slots < 2 || recv_bytes > g.slot_elems * sizeof(Fr))
+        return fail(ctx, DP_E_COMM, "peer arena of %llu B holds %llu receive matrices of %llu B: at least 2 are needed", (unsigned long long)ctx->arena_bytes,
+                    (unsigned long long)g.n_slots, (unsigned long long)(g.slot_elems * sizeof(Fr)));
+    const uint64_t s = ctx->p2p_seq % g.n_slots;
     if (ctx->p2p_slot_busy[s])
-        return fail(ctx, DP_E_STATE, "fused exchange: both receive slots hold transforms whose column phase has not run (at most 2 "
-                                     "between fft2_prepare and fft2 per context); finish one with dp_fft2 or use dp_fft_exchange_begin/_end");
-    const uint64_t off = ARENA_HEADER_BYTES / sizeof(Fr) + s * (slot_bytes / sizeof(Fr));
+        return fail(ctx, DP_E_STATE, "fused exchange: all %llu receive slots hold transforms whose column phase has not run (that many may sit "
+                                     "between fft2_prepare and fft2 per context); finish one with dp_fft2, create a larger arena, or use dp_fft_exchange_begin/_end",
+                    (unsigned long long)g.n_slots);
+    const uint64_t off = ARENA_HEADER_BYTES / sizeof(Fr) + s * g.slot_elems;
     for (uint64_t q = 0; q < ctx->W; q++) dst.base[q] = ctx->peer_arena[q] + off;
     dst.row_off = row_off;
     my_slot = ctx->arena + off;
     return DP_OK;
 }
 void p2p_commit_slot(dp_ctx *ctx) {
-    ctx->p2p_slot_busy[ctx->p2p_seq & 1] = true;
+    ctx->p2p_slot_busy[ctx->p2p_seq % p2p_slot_geom(ctx).n_slots] = true;
     ctx->p2p_seq++;
 }
 void p2p_release_slot(dp_ctx *ctx, const Fr *slot) {
     if (!slot || !ctx->arena) return;
-    const uint64_t slot_elems = (ctx->arena_bytes - ARENA_HEADER_BYTES) / 2 / sizeof(Fr);
-    const uint64_t s = (uint64_t)(slot - (ctx->arena + ARENA_HEADER_BYTES / sizeof(Fr))) / slot_elems;
-    if (s < 2) ctx->p2p_slot_busy[s] = false;
+    const SlotGeom g = p2p_slot_geom(ctx);
+    if (!g.slot_elems) return;
+    const uint64_t s = (uint64_t)(slot - (ctx->arena + ARENA_HEADER_BYTES / sizeof(Fr))) / g.slot_elems;
+    if (s < dp_ctx::P2P_MAX_SLOTS) ctx->p2p_slot_busy[s] = false;
 }
 
 // rows handed in short (dp_fft1 with len < c, dp_fft1_rows_short): the first pass reads rd columns of every row;
@@ -1257,6 +1283,8 @@ static int init_impl(dp_ctx *ctx, const void *bases, size_t n_bases, uint64_t do
     cudaStreamSynchronize(ctx->s_out);
     for (auto &kv : ctx->tasks) free_task(ctx, kv.second);
     ctx->tasks.clear();
+    for (bool &b : ctx->p2p_slot_busy) b = false;  // (the slot geometry follows the new domains; every rank re-initialises alike)
+    ctx->dev_p2p_slot = nullptr;
     cudaStreamSynchronize(ctx->s_tail);
     drop_pending_msms(ctx);
     ctx->pool.release(ctx->bases);

@@ -246,14 +246,16 @@ int dp_commit_dev(dp_ctx *ctx, const void *coeffs_dev, size_t n, void *out144);
  * Exchange arena shared between the GPUs of one box through CUDA IPC: every rank exports a
  * handle, the ranks swap them out of band (torch.distributed / the capnp control plane) and attach
  * the others'.  Afterwards dp_fft2_prepare stores the row-phase output straight into the owners'
- * arenas over NVLink (two slots, alternating per exchange: every rank must issue its exchanges in
- * the same order) and returns when its stores are complete; the caller provides the barrier across
+ * arenas over NVLink and returns when its stores are complete; the caller provides the barrier across
  * ranks between fft2Prepare and fft2 - the dispatcher's join over the fft2Prepare replies is one.
- * In-flight limit: the arena holds TWO receive slots, so at most two tasks per context may sit between
- * dp_fft2_prepare and dp_fft2 on the fused path; a third dp_fft2_prepare returns DP_E_STATE (nothing is
- * consumed: call dp_fft2 on an earlier task, then retry - or use dp_fft_exchange_begin/_end, which has
- * per-task buffers and no limit).  The slot sequence only advances on success, identically on all ranks.
- * arena_bytes >= 2 * (r * c / n_workers) * 32 for the largest domain. */
+ * Slots: the arena holds as many receive matrices ([r][c/n_workers] Fr of the LARGER domain given to dp_init) as fit
+ * into arena_bytes, at least two are required; exchange number k uses slot k mod n_slots on every rank, so every rank
+ * must issue its exchanges in the same order (as for a collective) and at most n_slots tasks per context may sit
+ * between dp_fft2_prepare and dp_fft2: one more dp_fft2_prepare returns DP_E_STATE (nothing is consumed: call dp_fft2
+ * on an earlier task, then retry - or use dp_fft_exchange_begin/_end, which has per-task buffers and no limit).
+ * The slot sequence only advances on success.  A worker behind the reference dispatcher (up to 26 transforms in
+ * flight, dispatcher2.rs:382-414) creates 32 slots; two are enough for one transform at a time.
+ * arena_bytes >= n_slots * (r * c / n_workers) * 32 for the largest domain; the same on every rank. */
 #define DP_IPC_HANDLE_BYTES 64
 int dp_peer_arena_create(dp_ctx *ctx, uint64_t arena_bytes, void *handle_out /* DP_IPC_HANDLE_BYTES */);
 int dp_peer_attach(dp_ctx *ctx, uint64_t peer, const void *handle /* DP_IPC_HANDLE_BYTES */);

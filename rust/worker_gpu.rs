@@ -20,9 +20,11 @@
 //! PlonkPeer.fftExchange RPC with the reserved task id u64::MAX (`from` = sender, `v` = [handle]) - the schema is
 //! untouched.  After that `fft2Prepare` needs no peer RPC at all: it returns when this worker's stores into the
 //! owners' receive matrices are complete, and the dispatcher's join over all fft2Prepare replies
-//! (dispatcher2.rs:767-772) is the barrier before `fft2`.  At most two tasks may sit between fft2Prepare and fft2
-//! per worker (two receive slots); the dispatcher of the reference issues up to 25 concurrently (join_all,
-//! dispatcher2.rs:382-414), so `fft2_prepare` below queues the rest and retries them from `fft2`.
+//! (dispatcher2.rs:767-772) is the barrier before `fft2`.  The arena holds ARENA_SLOTS receive matrices: exchange
+//! number k lands in slot k mod ARENA_SLOTS on every worker, which is consistent because the dispatcher's single
+//! thread writes each task's fft2Prepare to all connections at once (every worker sees the same order).  The
+//! dispatcher of the reference keeps at most 26 transforms in flight (join_all over 25 + 1, dispatcher2.rs:382-414);
+//! 32 slots of 2^25 * 32 / W bytes are 16 / 8 / 4 GiB per worker at W = 2 / 4 / 8.
 #![feature(int_roundings)]
 
 use ark_bls12_381::Fr;
@@ -38,7 +40,7 @@ use hello_world::{
 };
 use rand::{rngs::ThreadRng, thread_rng};
 use std::{
-    collections::{HashMap, VecDeque},
+    collections::HashMap,
     fs::File,
     ptr,
     sync::Arc,
@@ -48,6 +50,7 @@ const FR_BYTES: usize = 32; // size_of::<Fr>()            (utils.rs:27-43 raw st
 const G1_AFFINE_BYTES: usize = 104; // size_of::<G1Affine>()
 const G1_PROJECTIVE_BYTES: usize = 144; // size_of::<G1Projective>()
 const HANDSHAKE_ID: u64 = u64::MAX;
+const ARENA_SLOTS: usize = 32;
 
 struct State {
     rng: ThreadRng,
@@ -58,11 +61,9 @@ struct State {
     dims: HashMap<u64, (usize, usize)>,
     r: [usize; 2], // r of the gate / quotient domain (worker.rs:144-154)
     c: [usize; 2],
-    /// fused exchange: handles that arrived before this worker created its own arena; tasks waiting for a free slot
+    /// fused exchange: handles that arrived before this worker created its own arena
     early_handles: Vec<(u64, Vec<u8>)>,
     arena_ready: bool,
-    in_flight: usize,
-    waiting: VecDeque<u64>,
 }
 
 #[derive(Clone)]
@@ -127,10 +128,10 @@ impl plonk_slave::Server for PlonkImpl {
         if n_workers == 1 || st.arena_ready {
             return Promise::ok(());
         }
-        // one-time: receive arena of two slots of r*c/W Fr each (the larger domain), handle to every peer
+        // one-time: receive arena of ARENA_SLOTS matrices of r*c/W Fr each (the larger domain), handle to every peer
         let slot = (st.r[1] * st.c[1]).max(st.r[0] * st.c[0]) / n_workers * FR_BYTES;
         let mut handle = vec![0u8; DP_IPC_HANDLE_BYTES];
-        let rc = unsafe { dp_peer_arena_create(st.ctx, 2 * slot as u64, handle.as_mut_ptr()) };
+        let rc = unsafe { dp_peer_arena_create(st.ctx, (ARENA_SLOTS * slot) as u64, handle.as_mut_ptr()) };
         if let Err(e) = check(st.ctx, rc) {
             return Promise::err(e);
         }
@@ -205,16 +206,13 @@ impl plonk_slave::Server for PlonkImpl {
     fn fft2_prepare(&mut self, params: plonk_slave::Fft2PrepareParams, _: plonk_slave::Fft2PrepareResults) -> Promise<(), capnp::Error> {
         let id = params.get().unwrap().get_id();
         let st = self.st();
-        if st.network.peers.len() > 1 && st.in_flight == 2 {
-            st.waiting.push_back(id); // both receive slots taken: started from fft2 of an earlier task
-            return Promise::ok(());
-        }
+        // one worker: the whole transform is queued; several: the row kernels store into the peers' arenas and the call
+        // returns when they are done (DP_E_STATE if all ARENA_SLOTS slots are waiting for their fft2)
         let rc = unsafe { dp_fft2_prepare(st.ctx, id) };
-        if let Err(e) = check(st.ctx, rc) {
-            return Promise::err(e);
+        match check(st.ctx, rc) {
+            Ok(()) => Promise::ok(()),
+            Err(e) => Promise::err(e),
         }
-        st.in_flight += 1;
-        Promise::ok(())
     }
 
     fn fft2(&mut self, params: plonk_slave::Fft2Params, mut results: plonk_slave::Fft2Results) -> Promise<(), capnp::Error> {
@@ -224,23 +222,11 @@ impl plonk_slave::Server for PlonkImpl {
             Some(d) => d,
             None => return Promise::err(capnp::Error::failed(format!("fft2: unknown task {}", id))),
         };
-        if let Some(pos) = st.waiting.iter().position(|&w| w == id) {
-            // this task's fft2Prepare was deferred and every earlier one has been collected: run it now.  Every worker
-            // defers and releases the same tasks in the same order, so the slot sequences stay aligned; the peers'
-            // stores into this worker's slot are ordered by the dispatcher, which sends fft2 only after all replies.
-            st.waiting.remove(pos);
-            let rc = unsafe { dp_fft2_prepare(st.ctx, id) };
-            if let Err(e) = check(st.ctx, rc) {
-                return Promise::err(e);
-            }
-            st.in_flight += 1;
-        }
         let mut buf = vec![0u8; n_cols * r * FR_BYTES];
-        let rc = unsafe { dp_fft2(st.ctx, id, buf.as_mut_ptr(), buf.len()) };
+        let rc = unsafe { dp_fft2(st.ctx, id, buf.as_mut_ptr(), buf.len()) }; // column kernels + copy-out; frees the slot
         if let Err(e) = check(st.ctx, rc) {
             return Promise::err(e);
         }
-        st.in_flight = st.in_flight.saturating_sub(1);
         let mut builder = results.get().init_v(n_cols as u32);
         for (k, col) in buf.chunks(r * FR_BYTES).enumerate() {
             builder.set(k as u32, col); // one Data per column, as worker.rs:365,375
@@ -331,8 +317,6 @@ pub async fn main() -> Result<(), Box<dyn std::error::Error>> {
         c: [1, 1],
         early_handles: vec![],
         arena_ready: false,
-        in_flight: 0,
-        waiting: VecDeque::new(),
     });
     let local = tokio::task::LocalSet::new();
     let s = state.clone();

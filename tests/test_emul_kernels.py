@@ -330,6 +330,39 @@ def test_round1_default_blinders_come_from_the_os(orc, emul_lib):
     assert len(seen) == 8                                      # 2 contexts x 2 calls x 2 blinders, all distinct
 
 
+def test_fused_exchange_many_slots(orc, emul_lib):
+    """an arena of five receive slots: five tasks between fft2_prepare and fft2 (the reference dispatcher keeps up to 26
+    in flight), collected out of order, a sixth refused"""
+    W, L, S = 2, 9, 5
+    workers = [PlonkSlave(emul_lib, p, W) for p in range(W)]
+    for w in workers:
+        w.init([b""], 1 << 6, 1 << L)
+    common.attach_in_process(workers, S * (1 << L) * 32 // W)
+    wl = disp.fft_workloads(L, W)
+    xs = [orc.gen_fr(740 + t, 1 << L) for t in range(S + 1)]
+    for t in range(S + 1):
+        rows = disp.dispatcher_rows(xs[t], L)
+        for p, w in enumerate(workers):
+            w.fft_init(t, wl, True, True, True)
+            w.ctx.fft1_rows(t, 0, np.ascontiguousarray(rows[wl[p][0]:wl[p][1]]), wl[p][1] - wl[p][0])
+    for t in range(S):
+        for w in workers:
+            w.fft2_prepare(t)
+    for w in workers:
+        with pytest.raises(DpError) as e:
+            w.fft2_prepare(S)
+        assert e.value.code == -2
+    for t in (3, 0, 4, 1, 2):
+        got = disp.assemble(np.concatenate([w.fft2_array(t) for w in workers], axis=0))
+        assert np.array_equal(got, orc.fft(xs[t], True, True)), f"task {t}"
+    for w in workers:
+        w.fft2_prepare(S)
+    got = disp.assemble(np.concatenate([w.fft2_array(S) for w in workers], axis=0))
+    assert np.array_equal(got, orc.fft(xs[S], True, True))
+    for w in workers:
+        w.close()
+
+
 def test_fused_exchange_in_flight_limit(orc, emul_lib):
     """two receive slots per arena: a third fft2_prepare before any fft2 is refused (DP_E_STATE) without
     consuming a slot; after an fft2 it goes through and every task still yields the right transform"""

@@ -155,7 +155,7 @@ struct dp_ctx {
     Fr *wire = nullptr;
     uint64_t wire_len = 0;
     // fused peer-memory exchange (dp_peer_arena_create / dp_peer_attach)
-    Fr *arena = nullptr;            // my receive arena: two slots, alternating per exchange
+    Fr *arena = nullptr;            // my receive arena: header + n >= 2 receive slots, used round-robin (p2p_slot_geom)
     uint64_t arena_bytes = 0;
     Fr *peer_arena[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     uint64_t p2p_seq = 0;           // exchanges issued so far; must advance identically on every rank
@@ -991,7 +991,7 @@ FftTask *find_task(dp_ctx *ctx, uint64_t id) {
     return it == ctx->tasks.end() ? nullptr : &it->second;
 }
 
-constexpr uint64_t ARENA_HEADER_BYTES = 1024;  // arrival counter of the device-side barrier, then the two slots
+constexpr uint64_t ARENA_HEADER_BYTES = 1024;  // arrival counter of the device-side barrier, then the receive slots
 
 bool p2p_ready(const dp_ctx *ctx) {
     if (ctx->W <= 1 || !ctx->arena) return false;

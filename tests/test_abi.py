@@ -44,10 +44,11 @@ def test_sass_is_sm100a_and_uses_tma(real_lib):
     if not os.path.exists(cuobjdump):
         pytest.skip("cuobjdump not available")
     import subprocess
-    out = subprocess.run([cuobjdump, "-sass", "-fun", "_ZN2dp15ntt_tile_kernelENS_7NttPassE", dp.library_path()],
+    out = subprocess.run([cuobjdump, "-sass", "-fun", "_ZN2dp15ntt_tile_kernelILi3EEEvNS_7NttPassE", dp.library_path()],
                          capture_output=True, text=True).stdout
     assert "sm_100a" in out
     assert "UBLKCP" in out            # cp.async.bulk (TMA) staging of the twiddle tile
+    assert "LDGSTS" in out            # cp.async: the tile is copied global -> shared without passing through registers
     assert "IMAD.WIDE.U32" in out     # fused 32x32->64 multiply-accumulate chains
 
 

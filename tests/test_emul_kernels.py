@@ -486,7 +486,7 @@ def test_whole_ntt_fused_coset_tables_and_short_inputs(orc, emul_lib, limits, do
     c.close()
 
 
-@pytest.mark.parametrize("logn,logq", [(6, 9), (8, 11), (9, 12)])
+@pytest.mark.parametrize("logn,logq", [(6, 9), (8, 11)])
 def test_single_worker_three_pass_plan(orc, emul_lib, logn, logq):
     """n_workers == 1: the transform as three passes over digit groups of the element index instead of two row and two
     column passes (plan_single_worker3) - same rows in, same columns out, every flag combination, full and short rows,

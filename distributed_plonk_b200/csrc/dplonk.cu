@@ -188,6 +188,11 @@ struct dp_ctx {
     uint32_t msm_chunk = 0;    // experiment knob (env DP_MSM_CHUNK): digits per accumulate thread, 0 = default
     int msm_force_c = 0;       // 0 auto, 1 = windowed path with automatic c, >= 2 forced c (windowed)
     bool pre_disabled = false;
+    // 1 / (x_i - 1) over the quotient coset (rounds.cuh: quotient_kernel<true>): depends on the domain only, built by the
+    // first dp_quotient_evals after dp_init when it fits (32 B per point), dropped by the next dp_init
+    Fr *quot_inv = nullptr;
+    uint32_t quot_inv_log = 0;
+    int quot_table = -1;       // knob (env DP_QUOT_TABLE): -1 auto (table when it is at most 1/8 of the free memory), 0 never, 1 always
 };
 
 namespace {
@@ -1180,6 +1185,7 @@ int dp_create(int cuda_device, uint64_t me, uint64_t n_workers, dp_ctx **out) {
     if (const char *e = getenv("DP_NTT_PREFETCH")) ctx->ntt_tw_prefetch = atoi(e) != 0;
     if (const char *e = getenv("DP_NTT_NO_3PASS")) ctx->no_three_pass = atoi(e) != 0;
     if (const char *e = getenv("DP_MSM_BLOCKS")) ctx->msm_min_blocks = atoi(e) >= 3 && atoi(e) <= 5 ? atoi(e) : 3;
+    if (const char *e = getenv("DP_QUOT_TABLE")) ctx->quot_table = atoi(e) != 0 ? 1 : 0;
     ctx->me = me;
     ctx->W = n_workers;
     int rc = DP_OK;
@@ -1295,6 +1301,8 @@ static int init_impl(dp_ctx *ctx, const void *bases, size_t n_bases, uint64_t do
     ctx->pre_lo = ctx->pre_hi = 0;
     free_domain(ctx, ctx->dom[0]);
     free_domain(ctx, ctx->dom[1]);
+    ctx->pool.release(ctx->quot_inv);
+    ctx->quot_inv = nullptr;
     ctx->inited = false;
     ctx->n_bases = n_bases;
     if (n_bases) {
@@ -1630,7 +1638,7 @@ int dp_fft1_rows(dp_ctx *ctx, uint64_t id, uint64_t i_first, uint64_t n_rows, co
     FftTask *t = find_task(ctx, id);
     if (!t) return fail(ctx, DP_E_ARG, "dp_fft1: unknown task %llu", (unsigned long long)id);
     if (t->row_phase_done) return fail(ctx, DP_E_STATE, "dp_fft1 after fft2_prepare");
-    if (i_first + n_rows > t->n_rows) return fail(ctx, DP_E_ARG, "dp_fft1: rows [%llu,%llu) of %llu", (unsigned long long)i_first, (unsigned long long)(i_first + n_rows), (unsigned long long)t->n_rows);
+    if (i_first > t->n_rows || n_rows > t->n_rows - i_first) return fail(ctx, DP_E_ARG, "dp_fft1: rows [%llu,%llu) of %llu", (unsigned long long)i_first, (unsigned long long)(i_first + n_rows), (unsigned long long)t->n_rows);
     DP_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint64_t c = ctx->dom[t->is_quot ? 1 : 0].c();
     DP_CUDA(ctx, cudaMemcpyAsync(t->rows + i_first * c, rows, n_rows * c * sizeof(Fr), cudaMemcpyHostToDevice, ctx->s_in));
@@ -1649,7 +1657,7 @@ int dp_fft1_rows_short(dp_ctx *ctx, uint64_t id, uint64_t i_first, uint64_t n_ro
     FftTask *t = find_task(ctx, id);
     if (!t) return fail(ctx, DP_E_ARG, "dp_fft1_rows_short: unknown task %llu", (unsigned long long)id);
     if (t->row_phase_done) return fail(ctx, DP_E_STATE, "dp_fft1 after fft2_prepare");
-    if (i_first + n_rows > t->n_rows) return fail(ctx, DP_E_ARG, "dp_fft1_rows_short: rows [%llu,%llu) of %llu", (unsigned long long)i_first, (unsigned long long)(i_first + n_rows), (unsigned long long)t->n_rows);
+    if (i_first > t->n_rows || n_rows > t->n_rows - i_first) return fail(ctx, DP_E_ARG, "dp_fft1_rows_short: rows [%llu,%llu) of %llu", (unsigned long long)i_first, (unsigned long long)(i_first + n_rows), (unsigned long long)t->n_rows);
     const uint64_t c = ctx->dom[t->is_quot ? 1 : 0].c();
     if (row_len == 0 || row_len > c) return fail(ctx, DP_E_ARG, "dp_fft1_rows_short: row length %zu outside 1..%llu", row_len, (unsigned long long)c);
     DP_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -2328,13 +2336,44 @@ int quotient_device(dp_ctx *ctx, const dp_quotient_args &a, const Fr *const *arr
     // all blocks' 1 / prod(x_i - 1) up front, one thread per block, instead of one serial inversion inside each block
     const unsigned n_blocks = blocks_for(m, QUO_TPB);
     Scratch tmp(ctx->pool);
-    Fr *prod = tmp.get<Fr>(n_blocks);
-    if (!prod) return fail(ctx, DP_E_OOM, "quotient scratch");
-    DP_LAUNCH(quotient_xm1_products_kernel, dim3(n_blocks), dim3(QUO_TPB), 0, ctx->stream, q.gen, q.H, q.log_m, m, prod);
-    DP_LAUNCH(fr_invert_kernel, dim3(blocks_for(n_blocks, 128)), dim3(128), 0, ctx->stream, prod, (uint64_t)n_blocks);
-    q.prod_inv = prod;
-    DP_LAUNCH(quotient_kernel, dim3(n_blocks), dim3(QUO_TPB), 0, ctx->stream, q);
-    ctx->launches += 3;
+    // the 1/(x_i - 1) are the same for every proof on this domain: keep them when the table fits
+    bool want_table = ctx->quot_table == 1;
+    if (ctx->quot_table < 0) {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        want_table = (ctx->quot_inv && ctx->quot_inv_log == dq.log_n) || m * sizeof(Fr) <= free_b / 8;
+    }
+    if (want_table && !(ctx->quot_inv && ctx->quot_inv_log == dq.log_n)) {
+        ctx->pool.release(ctx->quot_inv);
+        ctx->quot_inv = (Fr *)ctx->pool.alloc(m * sizeof(Fr));
+        if (ctx->quot_inv) {
+            Fr *prod = tmp.get<Fr>(n_blocks);
+            if (!prod) return fail(ctx, DP_E_OOM, "quotient scratch");
+            DP_LAUNCH(quotient_xm1_products_kernel, dim3(n_blocks), dim3(QUO_TPB), 0, ctx->stream, q.gen, q.H, q.log_m, m, prod);
+            DP_LAUNCH(fr_invert_kernel, dim3(blocks_for(n_blocks, 128)), dim3(128), 0, ctx->stream, prod, (uint64_t)n_blocks);
+            DP_LAUNCH(quotient_inv_table_kernel, dim3(n_blocks), dim3(QUO_TPB), 0, ctx->stream, q.gen, q.H, q.log_m, m, (const Fr *)prod,
+                      ctx->quot_inv);
+            ctx->launches += 3;
+            ctx->quot_inv_log = dq.log_n;
+        } else if (ctx->quot_table == 1) {
+            return fail(ctx, DP_E_OOM, "quotient: table of 1/(x - 1) over 2^%u points", dq.log_n);
+        }
+    }
+    q.prod_inv = nullptr;
+    q.inv_xm1 = nullptr;
+    if (want_table && ctx->quot_inv) {
+        q.inv_xm1 = ctx->quot_inv;
+        DP_LAUNCH(quotient_kernel<true>, dim3(n_blocks), dim3(QUO_TPB), 0, ctx->stream, q);
+        ctx->launches += 1;
+    } else {
+        Fr *prod = tmp.get<Fr>(n_blocks);
+        if (!prod) return fail(ctx, DP_E_OOM, "quotient scratch");
+        DP_LAUNCH(quotient_xm1_products_kernel, dim3(n_blocks), dim3(QUO_TPB), 0, ctx->stream, q.gen, q.H, q.log_m, m, prod);
+        DP_LAUNCH(fr_invert_kernel, dim3(blocks_for(n_blocks, 128)), dim3(128), 0, ctx->stream, prod, (uint64_t)n_blocks);
+        q.prod_inv = prod;
+        DP_LAUNCH(quotient_kernel<false>, dim3(n_blocks), dim3(QUO_TPB), 0, ctx->stream, q);
+        ctx->launches += 3;
+    }
     DP_CUDA(ctx, cudaGetLastError());
     return DP_OK;
 }

@@ -87,6 +87,7 @@ struct QuotientArgs {
     Fr zh_inv[RND_MAX_RATIO];  // 1 / (x_i^n - 1), i < ratio
     const Fr *H;        // omega_m^e, e < m/2
     const Fr *prod_inv; // per block: 1 / product of (x_i - 1), from the pre-pass
+    const Fr *inv_xm1;  // TABLE variant: 1 / (x_i - 1) for every point of the coset (cached per quotient domain)
     uint64_t m;
     uint32_t log_m, ratio;
     Fr *out;
@@ -112,15 +113,37 @@ __global__ void __launch_bounds__(QUO_TPB) quotient_xm1_products_kernel(Fr gen, 
     if (t == 0) gmem_st(prod + blockIdx.x, sh[0]);
 }
 
-__global__ void __launch_bounds__(QUO_TPB) quotient_kernel(QuotientArgs q) {
+// The 1/(x_i - 1) depend on the quotient domain only, not on the proof: with a worker that keeps its polynomials
+// resident they are computed ONCE per dp_init (first quotient call) into a table of m Fr - the per-block product
+// tree, its 14 block-wide barriers and the pre-pass (one inversion per block) leave the per-proof path, which
+// becomes straight-line code without shared memory (r02 ncu: 25 % of the warp samples of the tree variant sat at
+// those barriers).  dplonk.cu falls back to the tree variant when the table (32 B per point) does not fit.
+__global__ void __launch_bounds__(QUO_TPB) quotient_inv_table_kernel(Fr gen, const Fr *H, uint32_t log_m, uint64_t m, const Fr *prod_inv,
+                                                                     Fr *table) {
     __shared__ Fr tree[2 * QUO_TPB];
+    const uint64_t i = (uint64_t)blockIdx.x * QUO_TPB + threadIdx.x;
+    Fr x;
+    const Fr xm1 = quotient_xm1(gen, H, log_m, m, i, x);
+    const Fr inv = block_batch_invert<QUO_TPB>(xm1, tree, prod_inv + blockIdx.x);
+    if (i < m) gmem_st(table + i, inv);
+}
+
+template <bool TABLE>
+__global__ void __launch_bounds__(QUO_TPB) quotient_kernel(QuotientArgs q) {
     const uint64_t i = (uint64_t)blockIdx.x * QUO_TPB + threadIdx.x;
     const bool live = i < q.m;
     const Fr one = Fr::one();
-    Fr x;
-    const Fr xm1 = quotient_xm1(q.gen, q.H, q.log_m, q.m, i, x);
-    const Fr inv_xm1 = block_batch_invert<QUO_TPB>(xm1, tree, q.prod_inv ? q.prod_inv + blockIdx.x : nullptr);
-    if (!live) return;
+    Fr x, inv_xm1;
+    if (TABLE) {
+        if (!live) return;
+        x = q.gen * tw_lookup(q.H, i, q.log_m, 0);
+        inv_xm1 = gmem_ld(q.inv_xm1 + i);
+    } else {
+        __shared__ Fr tree[2 * QUO_TPB];
+        const Fr xm1 = quotient_xm1(q.gen, q.H, q.log_m, q.m, i, x);
+        inv_xm1 = block_batch_invert<QUO_TPB>(xm1, tree, q.prod_inv ? q.prod_inv + blockIdx.x : nullptr);
+        if (!live) return;
+    }
     const Fr a = gmem_ld(q.w[0] + i), b = gmem_ld(q.w[1] + i), c = gmem_ld(q.w[2] + i), d = gmem_ld(q.w[3] + i), e = gmem_ld(q.w[4] + i);
     const Fr ab = qmul(a, b), cd = qmul(c, d);
     // gate constraint (lines 451-472)

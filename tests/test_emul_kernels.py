@@ -275,6 +275,18 @@ def test_rounds_quotient_domain_ratios(orc, emul_lib):
         c.close()
 
 
+def test_quotient_inverse_table_cache(orc, emul_lib):
+    """the cached 1/(x_i - 1) table (quotient_kernel<true>) serves repeated proofs on one domain and is rebuilt
+    when dp_init changes the quotient domain under the same context"""
+    c = Context(emul_lib, 0, 0, 1)
+    bases = orc.gen_bases(5, 40, 8, False)
+    for n, m, seeds in ((4, 32, (961, 962, 963)), (64, 512, (964, 965)), (8, 16, (966,)), (4, 32, (967,))):
+        c.init(bases, n, m)
+        for seed in seeds:
+            common.check_quotient(orc, c, n, m, seed)
+    c.close()
+
+
 def test_error_behaviour(orc, emul_lib):
     c = Context(emul_lib, 0, 0, 1)
     with pytest.raises(DpError) as e:

@@ -451,6 +451,12 @@ def main():
     # ---- e2e through the host-buffer API (pinned host memory, copies inside the timed region)
     e2e = None
     if not args.no_e2e:
+        # staging buffers next to the GPU: pinned pages land on the NUMA node of the CPU that allocates them, and with
+        # one process per GPU about half of the ranks would otherwise copy across the inter-socket link
+        import contextlib
+        aff_stack = contextlib.ExitStack()
+        host_aff = aff_stack.enter_context(parallel.near_gpu(local)) if os.environ.get("DP_BENCH_NO_AFFINITY", "0") != "1" else "unchanged (DP_BENCH_NO_AFFINITY)"
+
         def pinned(t):
             return t.cpu().pin_memory()
 
@@ -503,7 +509,7 @@ def main():
                "ms_per_step": dt_e / e_steps * 1e3, "steps": e_steps, "schedule": e2e_mode,
                "exchange": "none" if W == 1 else ("all_to_all_single enqueued on the compute stream" if getattr(e2e_exchange, "stream_ordered", False)
                                                   else "all_to_all_single, host-synchronised"),
-               "timing": "host clock between barrier+synchronize (copies run on three streams)"}
+               "timing": "host clock between barrier+synchronize (copies run on three streams)", "host_affinity": host_aff}
         del h_scal, h_in_n, h_in_m, h_in_m_full, h_out_n, h_out_m
 
     # ---- the same proof with every polynomial resident on the worker: witness in once, commitments and
@@ -516,6 +522,9 @@ def main():
         except Exception as e:  # the headline numbers above must survive a failure of this extra
             e2e_res = {"error": str(e)[:300]}
             ctx.sync()
+
+    if not args.no_e2e:
+        aff_stack.close()   # back on every host CPU (the CPU baseline below uses all of them)
 
     # ---- "next" row, measured beside the schedule (not part of the step): round-2 grand product
     perm = None

@@ -11,7 +11,9 @@ The same code runs on CPU under the `gloo` backend against the kernel-logic emul
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -88,3 +90,59 @@ def attach_peers(ctx, arena_bytes: int, group=None):
             ctx.peer_attach(q, h)
     dist.barrier(group=group)
     return ctx.peer_ready()
+
+
+def parse_cpulist(text: str):
+    """'0-3,8,10-11' (sysfs cpulist format) -> {0, 1, 2, 3, 8, 10, 11}"""
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_local_cpus(device_index: int, sysfs: str = "/sys/bus/pci/devices"):
+    """CPUs of the NUMA node the GPU hangs off (its PCIe root complex), from sysfs; None when unknown
+    (no such file, a single-node box, or a VM that hides the topology)."""
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        path = f"{sysfs}/{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0/local_cpulist"
+        with open(path) as f:
+            cpus = parse_cpulist(f.read())
+    except (OSError, ValueError, AttributeError, RuntimeError, AssertionError):
+        return None
+    return cpus or None
+
+
+@contextlib.contextmanager
+def near_gpu(device_index: int, cpus=None):
+    """Run the calling thread on the CPUs next to its GPU while it allocates, fills and hands over pinned
+    host buffers.  One process per GPU on a two-socket box otherwise leaves about half of the ranks with their
+    staging buffers on the far socket (first touch decides the node), and every host<->device copy of those ranks
+    crosses the inter-socket link, which all of them share.  Yields a description of what was done; the previous
+    affinity is restored on exit (threads that already exist, e.g. an OpenMP pool, keep theirs)."""
+    try:
+        before = os.sched_getaffinity(0)
+    except (AttributeError, OSError):
+        yield "unchanged (no sched_getaffinity)"
+        return
+    local = cpus if cpus is not None else gpu_local_cpus(device_index)
+    want = (local & before) if local else set()
+    if not want or want == before:
+        yield "unchanged (" + ("GPU-local CPU list unknown" if not local else "GPU-local CPUs outside this process's set" if not want
+                               else "already local / single node") + ")"
+        return
+    try:
+        os.sched_setaffinity(0, want)
+    except OSError as exc:
+        yield f"unchanged (sched_setaffinity: {exc})"
+        return
+    try:
+        yield f"{len(want)} of {len(before)} CPUs: the GPU's NUMA node"
+    finally:
+        try:
+            os.sched_setaffinity(0, before)
+        except OSError:
+            pass

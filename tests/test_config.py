@@ -32,3 +32,27 @@ def test_reference_shaped_file_and_rejects(tmp_path):
         p.write_text(json.dumps(bad))
         with pytest.raises(ValueError):
             NetworkConfig.load(str(p))
+
+
+def test_gpu_numa_affinity_helper(tmp_path):
+    """parallel.near_gpu: the bench's staging buffers are allocated on the CPUs next to the GPU (sysfs cpulist)
+    and the previous affinity comes back afterwards"""
+    import os
+
+    from distributed_plonk_b200 import parallel
+
+    assert parallel.parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert parallel.parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    one = {min(before)}
+    with parallel.near_gpu(0, cpus=one) as what:
+        inside = os.sched_getaffinity(0)
+    assert os.sched_getaffinity(0) == before
+    if len(before) > 1:
+        assert inside == one and "NUMA" in what
+    with parallel.near_gpu(0, cpus=set(before)) as what:          # nothing to narrow: left alone
+        assert os.sched_getaffinity(0) == before and what.startswith("unchanged")
+    with parallel.near_gpu(0, cpus={1 << 20}) as what:            # a list that shares no CPU with ours: left alone
+        assert os.sched_getaffinity(0) == before and what.startswith("unchanged")
+    with parallel.near_gpu(0) as what:                            # no GPU here: unknown topology, left alone
+        assert os.sched_getaffinity(0) == before

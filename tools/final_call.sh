@@ -8,7 +8,7 @@ tag=${1:-r02h}
 out=gpurun_out
 mkdir -p $out
 date +%s > $out/${tag}_t0
-timeout 200 python -m pytest tests/test_zz_gpu_rounds.py tests/test_resident.py -m gpu -x -q -k "quotient or resident or rounds or satisfied" 2>&1 | tail -8 > $out/${tag}_pytest_rounds.txt
+timeout 200 python -m pytest tests/test_zz_gpu_rounds.py tests/test_zzz_gpu_round2.py -m gpu -x -q -k "quotient or resident or rounds or satisfied" 2>&1 | tail -8 > $out/${tag}_pytest_rounds.txt
 date +%s > $out/${tag}_t1
 timeout 240 python bench.py --steps 3 --warmup 3 > $out/${tag}_bench_1gpu.json 2> $out/${tag}_bench_1gpu.err
 date +%s > $out/${tag}_t2

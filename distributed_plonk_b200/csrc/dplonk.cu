@@ -132,7 +132,7 @@ struct dp_ctx {
     uint64_t me = 0, W = 1;
     // Three streams so that consecutive tasks overlap: rows of task k+1 stream in (s_in) while task k
     // computes (stream) and the columns of task k-1 stream out (s_out); PCIe is full duplex.
-    cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr, s_tail = nullptr;
+    cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr, s_tail = nullptr, s_sort = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_msm[4] = {nullptr, nullptr, nullptr, nullptr};  // sort done | accumulate done | tail done
     float msm_ms[3] = {0.f, 0.f, 0.f};
@@ -847,11 +847,22 @@ void free_task(dp_ctx *ctx, FftTask &t) {
 // normalisation: narrow, latency-bound kernels) on s_tail, so that in a batch the tail of MSM k
 // overlaps the head of MSM k+1 - the dispatcher issues the commitments of a round concurrently
 // (join_all, dispatcher2.rs:316-321, 526-532).
+// The digit sort of a job (histogram, scan, scatter: atomics and memory traffic, no multiplier work) runs on a third
+// stream, s_sort, so that in a batch the sort of MSM k+1 runs under the accumulation of MSM k (which is bound by the
+// integer multiplier and leaves the memory system idle) instead of in front of it.
 struct MsmJob {
     std::vector<void *> scratch;
     uint32_t *err = nullptr;
-    cudaEvent_t ev_head = nullptr;
+    cudaEvent_t ev_head = nullptr;    // accumulate + collapse done (compute stream) -> tail stream
+    cudaEvent_t ev_ready = nullptr;   // inputs complete and recycled scratch free (compute stream) -> sort stream
+    cudaEvent_t ev_sorted = nullptr;  // digits sorted (sort stream) -> compute stream
 };
+void job_destroy_events(MsmJob &j) {
+    if (j.ev_head) cudaEventDestroy(j.ev_head);
+    if (j.ev_ready) cudaEventDestroy(j.ev_ready);
+    if (j.ev_sorted) cudaEventDestroy(j.ev_sorted);
+    j.ev_head = j.ev_ready = j.ev_sorted = nullptr;
+}
 
 // an MSM between dp_msm_submit and dp_msm_collect
 constexpr uint32_t MSM_SLOTS = 64, MSM_SLOT_BYTES = 256;  // pinned: 144 B result at 0, error flag at 192
@@ -863,9 +874,12 @@ struct MsmPending {
     uint32_t slot = 0;
 };
 
+// `ready`: an event after which the scalars are complete AND every earlier user of the pool blocks this job may be
+// handed has finished (a batch records one on the compute stream before it queues anything, so that the sorts of all
+// its jobs can run ahead); nullptr = the compute stream as it stands now.
 int msm_enqueue(dp_ctx *ctx, uint64_t start, const uint4 *scalars_dev, uint64_t n, G1JacobianOut *out_dev, MsmJob &job,
-                bool record_breakdown) {
-    cudaStream_t st = ctx->stream, tl = ctx->s_tail;
+                bool record_breakdown, cudaEvent_t ready = nullptr) {
+    cudaStream_t st = ctx->stream, tl = ctx->s_tail, so = ctx->s_sort;
     if (n == 0) {
         static const G1JacobianOut id = G1JacobianOut::from_affine(G1Affine::inf());
         DP_CUDA(ctx, cudaMemcpyAsync(out_dev, &id, sizeof id, cudaMemcpyHostToDevice, st));
@@ -904,18 +918,27 @@ int msm_enqueue(dp_ctx *ctx, uint64_t start, const uint4 *scalars_dev, uint64_t 
     job.err = (uint32_t *)grab(4);
     if (oom) return fail(ctx, DP_E_OOM, "msm scratch for %llu points", (unsigned long long)n);
     if (!job.ev_head) DP_CUDA(ctx, cudaEventCreateWithFlags(&job.ev_head, cudaEventDisableTiming));
+    if (!job.ev_sorted) DP_CUDA(ctx, cudaEventCreateWithFlags(&job.ev_sorted, cudaEventDisableTiming));
     if (record_breakdown) cudaEventRecord(ctx->ev_msm[0], st);
-    cudaMemsetAsync(counts, 0, (g.n_keys + 1) * 4ull, st);
-    cudaMemsetAsync(job.err, 0, 4, st);
-    cudaMemsetAsync(multi_keys, 0, 4, st);
-    DP_LAUNCH(msm_count_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, scalars_dev, n, g, counts, job.err);
-    DP_LAUNCH(scan_block_sums_kernel, dim3(n_scan_blocks), dim3(SCAN_TPB), 0, st, counts, g.n_keys, block_sums);
-    DP_LAUNCH(scan_block_offsets_kernel, dim3(1), dim3(SCAN_TPB), 0, st, block_sums, n_scan_blocks, offsets, g.n_keys);
-    DP_LAUNCH(scan_write_kernel, dim3(n_scan_blocks), dim3(SCAN_TPB), 0, st, counts, g.n_keys, block_sums, offsets);
-    cudaMemcpyAsync(cursor, offsets, (g.n_keys + 1) * 4ull, cudaMemcpyDeviceToDevice, st);
-    DP_LAUNCH(msm_scatter_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, scalars_dev, n, g, cursor, sorted);
-    DP_LAUNCH(msm_find_big_kernel, dim3(blocks_for(g.n_keys, 256)), dim3(256), 0, st, offsets, g.n_keys, g.chunk, multi_keys + 1,
+    if (!ready) {
+        if (!job.ev_ready) DP_CUDA(ctx, cudaEventCreateWithFlags(&job.ev_ready, cudaEventDisableTiming));
+        DP_CUDA(ctx, cudaEventRecord(job.ev_ready, st));
+        ready = job.ev_ready;
+    }
+    DP_CUDA(ctx, cudaStreamWaitEvent(so, ready, 0));
+    cudaMemsetAsync(counts, 0, (g.n_keys + 1) * 4ull, so);
+    cudaMemsetAsync(job.err, 0, 4, so);
+    cudaMemsetAsync(multi_keys, 0, 4, so);
+    DP_LAUNCH(msm_count_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, so, scalars_dev, n, g, counts, job.err);
+    DP_LAUNCH(scan_block_sums_kernel, dim3(n_scan_blocks), dim3(SCAN_TPB), 0, so, counts, g.n_keys, block_sums);
+    DP_LAUNCH(scan_block_offsets_kernel, dim3(1), dim3(SCAN_TPB), 0, so, block_sums, n_scan_blocks, offsets, g.n_keys);
+    DP_LAUNCH(scan_write_kernel, dim3(n_scan_blocks), dim3(SCAN_TPB), 0, so, counts, g.n_keys, block_sums, offsets);
+    cudaMemcpyAsync(cursor, offsets, (g.n_keys + 1) * 4ull, cudaMemcpyDeviceToDevice, so);
+    DP_LAUNCH(msm_scatter_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, so, scalars_dev, n, g, cursor, sorted);
+    DP_LAUNCH(msm_find_big_kernel, dim3(blocks_for(g.n_keys, 256)), dim3(256), 0, so, offsets, g.n_keys, g.chunk, multi_keys + 1,
               multi_keys);
+    DP_CUDA(ctx, cudaEventRecord(job.ev_sorted, so));
+    DP_CUDA(ctx, cudaStreamWaitEvent(st, job.ev_sorted, 0));
     if (record_breakdown) cudaEventRecord(ctx->ev_msm[1], st);
     if (ctx->msm_min_blocks == 4)
         DP_LAUNCH(msm_accumulate_kernel<4>, dim3(blocks_for(max_chunks, MSM_TPB)), dim3(MSM_TPB), 0, st, offsets, g.n_keys, g.chunk, sorted,
@@ -942,7 +965,8 @@ int msm_enqueue(dp_ctx *ctx, uint64_t start, const uint4 *scalars_dev, uint64_t 
 
 // wait for every job, collect the error flags, give the scratch back
 int msm_finish(dp_ctx *ctx, std::vector<MsmJob> &jobs, bool breakdown) {
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->s_sort);  // (only matters when a job failed between its sort and its accumulation)
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_tail);
     uint32_t bad = 0;
     for (MsmJob &j : jobs) {
@@ -953,8 +977,7 @@ int msm_finish(dp_ctx *ctx, std::vector<MsmJob> &jobs, bool breakdown) {
         }
         for (void *p : j.scratch) ctx->pool.release(p);
         j.scratch.clear();
-        if (j.ev_head) cudaEventDestroy(j.ev_head);
-        j.ev_head = nullptr;
+        job_destroy_events(j);
     }
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ctx, DP_E_CUDA, "msm kernels: %s", cudaGetErrorString(e));
@@ -976,7 +999,7 @@ int msm_device(dp_ctx *ctx, uint64_t start, const uint4 *scalars_dev, uint64_t n
 // give back everything a pending MSM holds; the caller has made sure its kernels are done
 void release_pending(dp_ctx *ctx, MsmPending *p) {
     for (void *q : p->job.scratch) ctx->pool.release(q);
-    if (p->job.ev_head) cudaEventDestroy(p->job.ev_head);
+    job_destroy_events(p->job);
     ctx->pool_io.release(p->scalars);
     ctx->pool.release(p->out);
     if (p->ev_in) cudaEventDestroy(p->ev_in);
@@ -1195,6 +1218,7 @@ int dp_create(int cuda_device, uint64_t me, uint64_t n_workers, dp_ctx **out) {
         if (cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking) != cudaSuccess) { rc = DP_E_CUDA; break; }
         if (cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking) != cudaSuccess) { rc = DP_E_CUDA; break; }
         if (cudaStreamCreateWithFlags(&ctx->s_tail, cudaStreamNonBlocking) != cudaSuccess) { rc = DP_E_CUDA; break; }
+        if (cudaStreamCreateWithFlags(&ctx->s_sort, cudaStreamNonBlocking) != cudaSuccess) { rc = DP_E_CUDA; break; }
         cudaEventCreate(&ctx->ev0);
         cudaEventCreate(&ctx->ev1);
         for (int k = 0; k < 4; k++) cudaEventCreate(&ctx->ev_msm[k]);
@@ -1235,6 +1259,7 @@ int dp_destroy(dp_ctx *ctx) {
         if (kv.second.ev_in) cudaEventDestroy(kv.second.ev_in);
         if (kv.second.ev_c) cudaEventDestroy(kv.second.ev_c);
     }
+    cudaStreamSynchronize(ctx->s_sort);
     cudaStreamSynchronize(ctx->s_tail);
     drop_pending_msms(ctx);
     if (ctx->msm_pinned) cudaFreeHost(ctx->msm_pinned);
@@ -1246,6 +1271,7 @@ int dp_destroy(dp_ctx *ctx) {
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     if (ctx->s_tail) cudaStreamDestroy(ctx->s_tail);
+    if (ctx->s_sort) cudaStreamDestroy(ctx->s_sort);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (int k = 0; k < 4; k++)
@@ -1259,6 +1285,7 @@ static int p2p_check_timeout(dp_ctx *ctx);
 int dp_sync(dp_ctx *ctx) {
     if (!ctx) return DP_E_ARG;
     DP_CUDA(ctx, cudaStreamSynchronize(ctx->s_in));
+    DP_CUDA(ctx, cudaStreamSynchronize(ctx->s_sort));
     DP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     DP_CUDA(ctx, cudaStreamSynchronize(ctx->s_tail));
     DP_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
@@ -1291,6 +1318,7 @@ static int init_impl(dp_ctx *ctx, const void *bases, size_t n_bases, uint64_t do
     ctx->tasks.clear();
     for (bool &b : ctx->p2p_slot_busy) b = false;  // (the slot geometry follows the new domains; every rank re-initialises alike)
     ctx->dev_p2p_slot = nullptr;
+    cudaStreamSynchronize(ctx->s_sort);
     cudaStreamSynchronize(ctx->s_tail);
     drop_pending_msms(ctx);
     ctx->pool.release(ctx->bases);
@@ -1427,11 +1455,17 @@ int dp_msm_dev_batch(dp_ctx *ctx, size_t n_jobs, const uint64_t *starts, const u
     call_begin(ctx);
     std::vector<MsmJob> jobs(n_jobs);
     int rc = DP_OK;
+    // every job's scalars are complete where the compute stream stands now (the caller's contract for *_dev inputs), and so
+    // is every earlier user of the pool blocks the jobs will be handed: one event lets all the sorts run ahead
+    cudaEvent_t ev_batch = nullptr;
+    if (cudaEventCreateWithFlags(&ev_batch, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(ev_batch, ctx->stream) != cudaSuccess)
+        rc = fail(ctx, DP_E_CUDA, "dp_msm_dev_batch: event");
     for (size_t k = 0; k < n_jobs && rc == DP_OK; k++) {
         const uint64_t n = (ends[k] - starts[k]) < n_scalars[k] ? (ends[k] - starts[k]) : n_scalars[k];
-        rc = msm_enqueue(ctx, starts[k], (const uint4 *)scalars_dev[k], n, (G1JacobianOut *)outs_dev[k], jobs[k], false);
+        rc = msm_enqueue(ctx, starts[k], (const uint4 *)scalars_dev[k], n, (G1JacobianOut *)outs_dev[k], jobs[k], false, ev_batch);
     }
     int rc2 = msm_finish(ctx, jobs, false);
+    if (ev_batch) cudaEventDestroy(ev_batch);
     if (rc != DP_OK) return rc;
     if (rc2 != DP_OK) return rc2;
     return call_end(ctx, true);
@@ -1463,12 +1497,18 @@ int dp_msm_batch(dp_ctx *ctx, size_t n_jobs, const uint64_t *starts, const uint6
         if (e == cudaSuccess) e = cudaEventRecord(ev[k], ctx->s_in);
         if (e != cudaSuccess) rc = fail(ctx, DP_E_CUDA, "dp_msm_batch H2D: %s", cudaGetErrorString(e));
     }
+    // the sorts wait for their own copy-in (s_in) and for whatever the compute stream held when the batch began (earlier
+    // users of recycled scratch); then they run ahead of the accumulations
+    cudaEvent_t ev_batch = nullptr;
+    if (rc == DP_OK && (cudaEventCreateWithFlags(&ev_batch, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(ev_batch, ctx->stream) != cudaSuccess))
+        rc = fail(ctx, DP_E_CUDA, "dp_msm_batch: event");
     for (size_t k = 0; k < n_jobs && rc == DP_OK; k++) {
         const uint64_t n = (ends[k] - starts[k]) < n_scalars[k] ? (ends[k] - starts[k]) : n_scalars[k];
-        cudaStreamWaitEvent(ctx->stream, ev[k], 0);
-        rc = msm_enqueue(ctx, starts[k], sc[k], n, od + k, jobs[k], false);
+        cudaStreamWaitEvent(ctx->s_sort, ev[k], 0);
+        rc = msm_enqueue(ctx, starts[k], sc[k], n, od + k, jobs[k], false, ev_batch);
     }
-    int rc2 = msm_finish(ctx, jobs, false);   // drains the compute and tail streams
+    int rc2 = msm_finish(ctx, jobs, false);   // drains the sort, compute and tail streams
+    if (ev_batch) cudaEventDestroy(ev_batch);
     if (rc == DP_OK) rc = rc2;
     if (rc == DP_OK) {
         std::vector<G1JacobianOut> host(n_jobs);
@@ -1527,6 +1567,7 @@ int dp_msm_submit(dp_ctx *ctx, uint64_t id, uint64_t start, uint64_t end, const 
     if (rc == DP_OK && e != cudaSuccess) rc = fail(ctx, DP_E_CUDA, "dp_msm_submit: %s", cudaGetErrorString(e));
     if (rc != DP_OK) {  // nothing of this job may still be running when its buffers go back
         cudaStreamSynchronize(ctx->s_in);
+        cudaStreamSynchronize(ctx->s_sort);
         cudaStreamSynchronize(ctx->stream);
         cudaStreamSynchronize(ctx->s_tail);
         release_pending(ctx, p);
@@ -1549,6 +1590,7 @@ int dp_msm_collect(dp_ctx *ctx, uint64_t id, void *out) {
     memcpy(out, pin, sizeof(G1JacobianOut));
     memcpy(&bad, pin + 192, 4);
     if (e != cudaSuccess) {  // make sure nothing is running before the buffers go back
+        cudaStreamSynchronize(ctx->s_sort);
         cudaStreamSynchronize(ctx->stream);
         cudaStreamSynchronize(ctx->s_tail);
     }

@@ -200,7 +200,7 @@ inline unsigned jitter_us() {
     return v;
 }
 // adversarial schedule: DP_EMUL_SLOW="i:us" delays every operation of the streams whose creation index is
-// i mod 4 by `us` microseconds (a context creates compute, copy-in, copy-out, tail in that order), so an
+// i mod 5 by `us` microseconds (a context creates compute, copy-in, copy-out, tail, sort in that order), so an
 // operation that should have waited for that stream and does not is practically certain to run too early
 inline std::atomic<unsigned> g_stream_counter{0};
 inline unsigned slow_us(unsigned index) {
@@ -211,7 +211,7 @@ inline unsigned slow_us(unsigned index) {
         if (e && sscanf(e, "%d:%u", &i, &us) != 2) i = -1;
         return std::make_pair(i, us);
     }();
-    return cfg.first >= 0 && (int)(index % 4) == cfg.first ? cfg.second : 0u;
+    return cfg.first >= 0 && (int)(index % 5) == cfg.first ? cfg.second : 0u;
 }
 }  // namespace dp_emul
 struct dp_emul_stream {

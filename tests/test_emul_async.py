@@ -2,11 +2,11 @@
 
 tests/emul/build.py --async builds the kernel-logic emulator with REAL asynchronous streams (every
 stream is a worker thread, events carry record / completion generations, every operation gets a random
-delay).  DP_EMUL_SLOW="i:us" additionally makes one of the context's four streams (0 compute, 1 copy-in,
-2 copy-out, 3 MSM tail) pathologically slow, so anything that should have waited for it and does not is
+delay).  DP_EMUL_SLOW="i:us" additionally makes one of the context's five streams (0 compute, 1 copy-in,
+2 copy-out, 3 MSM tail, 4 MSM digit sort) pathologically slow, so anything that should have waited for it and does not is
 practically certain to run too early and produce a wrong result.  (Removing any one of the library's
 cudaStreamWaitEvent calls makes these tests fail; the pipeline-heavy emulator tests are re-run under each
-of the four adversarial schedules.)  TEST INFRASTRUCTURE ONLY, like the rest of tests/emul."""
+of the five adversarial schedules.)  TEST INFRASTRUCTURE ONLY, like the rest of tests/emul."""
 import os
 import subprocess
 import sys
@@ -26,7 +26,7 @@ def test_pipeline_under_adversarial_stream_schedules():
     from tests.emul import build as emul_build
     emul_build.build(async_streams=True)            # build once, before the children race for it
     procs = []
-    for slow in range(4):
+    for slow in range(5):
         env = dict(os.environ, DP_TEST_EMUL_ASYNC="1", DP_EMUL_SLOW=f"{slow}:1500")
         procs.append(subprocess.Popen(
             [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_emul_kernels.py"), "-q", "-x", "-p", "no:cacheprovider",

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Last GPU call of round 2 (a few minutes of budget): in order of importance
-#   1. the GPU tests that cover what changed since r02g (quotient table variant, resident prover)
+#   1. the GPU tests that cover what changed since r02g (MSM digit sort on its own stream, quotient table variant, resident prover)
 #   2. the bench line of the final build
 #   3. ncu --set full captures of the "next"-row kernels, which round 2 had only for quotient_kernel
 #   /usr/local/graft/bin/gpurun --timeout 540 -- 'bash tools/final_call.sh r02h'
@@ -8,7 +8,7 @@ tag=${1:-r02h}
 out=gpurun_out
 mkdir -p $out
 date +%s > $out/${tag}_t0
-timeout 200 python -m pytest tests/test_zz_gpu_rounds.py tests/test_zzz_gpu_round2.py -m gpu -x -q -k "quotient or resident or rounds or satisfied" 2>&1 | tail -8 > $out/${tag}_pytest_rounds.txt
+timeout 240 python -m pytest tests/test_gpu_parity.py tests/test_zz_gpu_rounds.py tests/test_zzz_gpu_round2.py -m gpu -x -q -k "(msm or commit or quotient or resident or rounds or satisfied or host_schedules) and not full_size" 2>&1 | tail -8 > $out/${tag}_pytest_changed.txt
 date +%s > $out/${tag}_t1
 timeout 240 python bench.py --steps 3 --warmup 3 > $out/${tag}_bench_1gpu.json 2> $out/${tag}_bench_1gpu.err
 date +%s > $out/${tag}_t2

@@ -192,6 +192,7 @@ struct dp_ctx {
     // first dp_quotient_evals after dp_init when it fits (32 B per point), dropped by the next dp_init
     Fr *quot_inv = nullptr;
     uint32_t quot_inv_log = 0;
+    bool msm_sort_own_stream = true;  // knob (env DP_MSM_SORT_STREAM=0): digit sorts queue on the compute stream, in front of their accumulation
     int quot_table = -1;       // knob (env DP_QUOT_TABLE): -1 auto (table when it is at most 1/8 of the free memory), 0 never, 1 always
 };
 
@@ -879,7 +880,7 @@ struct MsmPending {
 // its jobs can run ahead); nullptr = the compute stream as it stands now.
 int msm_enqueue(dp_ctx *ctx, uint64_t start, const uint4 *scalars_dev, uint64_t n, G1JacobianOut *out_dev, MsmJob &job,
                 bool record_breakdown, cudaEvent_t ready = nullptr) {
-    cudaStream_t st = ctx->stream, tl = ctx->s_tail, so = ctx->s_sort;
+    cudaStream_t st = ctx->stream, tl = ctx->s_tail, so = ctx->msm_sort_own_stream ? ctx->s_sort : ctx->stream;
     if (n == 0) {
         static const G1JacobianOut id = G1JacobianOut::from_affine(G1Affine::inf());
         DP_CUDA(ctx, cudaMemcpyAsync(out_dev, &id, sizeof id, cudaMemcpyHostToDevice, st));
@@ -1209,6 +1210,7 @@ int dp_create(int cuda_device, uint64_t me, uint64_t n_workers, dp_ctx **out) {
     if (const char *e = getenv("DP_NTT_NO_3PASS")) ctx->no_three_pass = atoi(e) != 0;
     if (const char *e = getenv("DP_MSM_BLOCKS")) ctx->msm_min_blocks = atoi(e) >= 3 && atoi(e) <= 5 ? atoi(e) : 3;
     if (const char *e = getenv("DP_QUOT_TABLE")) ctx->quot_table = atoi(e) != 0 ? 1 : 0;
+    if (const char *e = getenv("DP_MSM_SORT_STREAM")) ctx->msm_sort_own_stream = atoi(e) != 0;
     ctx->me = me;
     ctx->W = n_workers;
     int rc = DP_OK;
@@ -1504,7 +1506,7 @@ int dp_msm_batch(dp_ctx *ctx, size_t n_jobs, const uint64_t *starts, const uint6
         rc = fail(ctx, DP_E_CUDA, "dp_msm_batch: event");
     for (size_t k = 0; k < n_jobs && rc == DP_OK; k++) {
         const uint64_t n = (ends[k] - starts[k]) < n_scalars[k] ? (ends[k] - starts[k]) : n_scalars[k];
-        cudaStreamWaitEvent(ctx->s_sort, ev[k], 0);
+        cudaStreamWaitEvent(ctx->msm_sort_own_stream ? ctx->s_sort : ctx->stream, ev[k], 0);
         rc = msm_enqueue(ctx, starts[k], sc[k], n, od + k, jobs[k], false, ev_batch);
     }
     int rc2 = msm_finish(ctx, jobs, false);   // drains the sort, compute and tail streams

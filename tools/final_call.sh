@@ -12,6 +12,7 @@ timeout 240 python -m pytest tests/test_gpu_parity.py tests/test_zz_gpu_rounds.p
 date +%s > $out/${tag}_t1
 timeout 240 python bench.py --steps 3 --warmup 3 > $out/${tag}_bench_1gpu.json 2> $out/${tag}_bench_1gpu.err
 date +%s > $out/${tag}_t2
+timeout 90 python tools/ab_sort_stream.py > $out/${tag}_ab_sort_stream.txt 2>&1
 timeout 60 ./tools/microbench6 24 > $out/${tag}_microbench_affine2.txt 2>&1
 timeout 60 python tools/f_kernels.py > $out/${tag}_f_kernels.txt 2>&1
 timeout 150 ncu --set full --clock-control none --import-source on -k regex:'perm_|poly_|quotient_kernel|quotient_inv|g1_decompress' -c 26 -f -o $out/${tag}_f_kernels python tools/f_kernels.py > $out/${tag}_f_kernels_ncu.log 2>&1

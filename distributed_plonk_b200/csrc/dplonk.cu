@@ -192,7 +192,11 @@ struct dp_ctx {
     // first dp_quotient_evals after dp_init when it fits (32 B per point), dropped by the next dp_init
     Fr *quot_inv = nullptr;
     uint32_t quot_inv_log = 0;
-    bool msm_sort_own_stream = true;  // knob (env DP_MSM_SORT_STREAM=0): digit sorts queue on the compute stream, in front of their accumulation
+    // knob (env DP_MSM_SORT_STREAM=1): the digit sorts of a batch run on their own stream, ahead of / under the accumulations.
+    // MEASURED AND NOT ADOPTED (profiles/r02h_ab_sort_stream.txt): 22.43 against 22.13 ms per MSM in a batch of five at 2^22 points,
+    // 3.78 against 3.76 for a 2^19-point shard - the sort's atomics and its blocks taking SM slots cost the accumulation more
+    // than the 1.0 ms (0.27 ms) of sort time that leaves the critical path.  Default: sorts queue in front of their accumulation.
+    bool msm_sort_own_stream = false;
     int quot_table = -1;       // knob (env DP_QUOT_TABLE): -1 auto (table when it is at most 1/8 of the free memory), 0 never, 1 always
 };
 
@@ -848,9 +852,9 @@ void free_task(dp_ctx *ctx, FftTask &t) {
 // normalisation: narrow, latency-bound kernels) on s_tail, so that in a batch the tail of MSM k
 // overlaps the head of MSM k+1 - the dispatcher issues the commitments of a round concurrently
 // (join_all, dispatcher2.rs:316-321, 526-532).
-// The digit sort of a job (histogram, scan, scatter: atomics and memory traffic, no multiplier work) runs on a third
-// stream, s_sort, so that in a batch the sort of MSM k+1 runs under the accumulation of MSM k (which is bound by the
-// integer multiplier and leaves the memory system idle) instead of in front of it.
+// The digit sort of a job (histogram, scan, scatter: atomics and memory traffic, no multiplier work) can run on a third
+// stream, s_sort, so that in a batch the sort of MSM k+1 runs under the accumulation of MSM k instead of in front of it
+// (dp_ctx::msm_sort_own_stream; off by default - measured slower, see there).
 struct MsmJob {
     std::vector<void *> scratch;
     uint32_t *err = nullptr;

@@ -25,7 +25,9 @@ for W in (1, 8):
         ctx.init_ptr(bases.data_ptr(), nb, n, 8 * n)
         del bases
         lo, hi = 0, nb // W
-        sc = [torch.randint(-(1 << 63), (1 << 63) - 1, (hi - lo, 4), dtype=torch.int64, device="cuda") for _ in range(3)]
+        gen = torch.Generator(device="cuda")
+        gen.manual_seed(1234 + W)                  # the same scalars for both settings: the results must then be identical
+        sc = [torch.randint(-(1 << 63), (1 << 63) - 1, (hi - lo, 4), dtype=torch.int64, device="cuda", generator=gen) for _ in range(3)]
         for s in sc:
             s[:, 3] &= (1 << 62) - 1
         outs = [torch.zeros(18, dtype=torch.int64, device="cuda") for _ in range(5)]

@@ -257,6 +257,13 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     W = world
     lib = dp.load()                       # raises if the CUDA extension is missing: no fallback
+    # batched-affine MSM levels: opt in per run, and only if a child process on this GPU found them identical and faster for
+    # this rank's shard (distributed_plonk_b200/tune.py); DP_MSM_AFFINE in the environment overrides the probe
+    tune_probe = None
+    if "DP_MSM_AFFINE" not in os.environ and os.environ.get("DP_BENCH_NO_MSM_PROBE", "0") != "1":
+        from distributed_plonk_b200 import tune
+        tune_probe = tune.probe(local, rank, W, args.log_n)
+        os.environ["DP_MSM_AFFINE"] = str(tune.choose(tune_probe))
     ctx = dp.Context(lib, local, rank, W)
 
     log_n = args.log_n
@@ -603,7 +610,12 @@ def main():
     # the carry form IMAD.WIDE.U32.X that multi-precision chains need sustains 28.3 (r01_microbench_carry_chains.txt)
     sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
     mac_peak = 61.9 * 148 * sm_clk * 1e6
-    macs_msm = (hi - lo) * 1.0 * ((256 + 19) // 20) * 10 * 288        # digits x (8M+2S) x 12x12x2 MACs
+    tuning = ctx.msm_tuning()                                          # dp_init's choice: plain XYZZ chunks or batched-affine tree levels first
+    lv = tuning["levels"]
+    # Fq products per bucket addition: 10 (XYZZ mixed addition), or with L tree levels 6.4 for the (1 - 2^-L) of the additions the
+    # levels do and 10 for the rest
+    prod_per_add = 10.0 if lv == 0 else 6.4 * (1 - 0.5 ** lv) + 10.0 * 0.5 ** lv
+    macs_msm = (hi - lo) * 1.0 * ((256 + 19) // 20) * prod_per_add * 288   # digits x Fq products x 12x12x2 MACs
     macs_ntt = (m / 2) * log_m * 128 + 4 * m * 128                     # butterflies + twiddle/coset products, 8x8x2 MACs
     compute = {
         "bound": "int32 multiply-add pipe", "peak_mac_per_s": mac_peak, "peak_source": "measured IMAD.WIDE.U32 rate x 148 SMs x sampled SM clock",
@@ -627,10 +639,14 @@ def main():
                    "passes_per_transform": n_pass, "transform_ms": per_tr, "traffic": ntt_traffic,
                    # against SURVEY 8d's bytes_min = 64 N for the WHOLE transform (one read + one write of every element)
                    "per_transform_frac_of_bytes_min": 64 * m / (per_tr * 1e-3) / 1e9 / peak}
+    if lv and dominant.startswith("msm"):
+        traffic = None          # the committed ncu capture is of the plain accumulation kernel, not of the tree levels
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(alg_bytes), "avg_launch_ms": per_launch_ms,
-                "note": "both kernels are bound by the INT32 multiply pipe, not HBM (DESIGN.md); HBM fraction reported as BASELINE asks",
+                "note": "both kernels are bound by the INT32 multiply pipe, not HBM (DESIGN.md); HBM fraction reported as BASELINE asks"
+                        + ("" if lv == 0 or not dominant.startswith("msm") else
+                           f"; the accumulation phase timed here is {lv} batched-affine tree levels (aff_k1/k2/k3) + msm_accumulate_kernel, chosen by dp_init's tuning"),
                 "step_share_ms": shares}
     exch = {"single": "none", "devbarrier": "fused peer-memory stores + device-side barrier kernel, transforms queued asynchronously",
             "hostbarrier": "fused peer-memory stores, host barrier per transform", "nccl": "nccl all_to_all_single"}[mode]
@@ -646,6 +662,10 @@ def main():
         "breakdown_ms": {"msm_total_one_at_a_time": msm_total, "msm_accumulate": acc_total, "intt_n_total": sum(stats["ntt_n_ms"]),
                          "coset_ntt_8n_total": sum(stats["ntt_m_ms"]), "sections_max_over_ranks": stats["sections_ms"]},
         "roofline": roofline, "roofline_ntt": ntt_hbm, "roofline_compute": compute, "e2e": e2e, "e2e_resident": e2e_res,
+        "msm_tuning": {"levels_used": lv, "probe": tune_probe,
+                       "what": "a child process timed one MSM over this rank's window table with the plain pipeline and with 2 batched-affine tree "
+                               "levels in front of it (dp_init with DP_MSM_TUNE=1); the levels are used in this run only if both results were "
+                               "identical and the levels >= 2 % faster"},
         "next_row_perm_product": perm, "next_row_rounds_3_to_5": rounds,
     }
     if not args.no_cpu and W == 1:

@@ -6,6 +6,7 @@
 
 #include <sys/random.h>
 
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <map>
@@ -192,6 +193,18 @@ struct dp_ctx {
     // first dp_quotient_evals after dp_init when it fits (32 B per point), dropped by the next dp_init
     Fr *quot_inv = nullptr;
     uint32_t quot_inv_log = 0;
+    // batched-affine tree levels in front of the XYZZ chunks (msm.cuh): 0 = none (default), else L.  env DP_MSM_AFFINE=L forces L
+    // levels; env DP_MSM_TUNE=1 lets dp_init choose by msm_tune() - one MSM over the context's own window table either way,
+    // results compared, the levels kept if identical and faster.  The levels were written after the round's GPU budget was
+    // spent (their kernels ran on hardware only in microbenchmark form, profiles/r02h_microbench_affine2.txt), so nothing
+    // selects them silently: bench.py probes them in a child process and opts in per run (distributed_plonk_b200/tune.py).
+    // MSMs of fewer than msm_affine_min_digits digits stay on the plain path (env DP_MSM_AFFINE_MIN).
+    uint32_t msm_affine_levels = 0;
+    int msm_affine_forced = -1;             // -1 = not forced
+    bool msm_tune_enabled = false;          // env DP_MSM_TUNE=1: dp_init runs msm_tune(); otherwise the plain pipeline unless forced
+    uint64_t msm_affine_min_digits = (uint64_t)1 << 22;
+    float tune_ms[2] = {0.f, 0.f};          // msm_tune(): plain / with levels (0 = not measured)
+    int tune_equal = -1;                    // msm_tune(): results identical (1), different (0), not run (-1)
     // knob (env DP_MSM_SORT_STREAM=1): the digit sorts of a batch run on their own stream, ahead of / under the accumulations.
     // MEASURED AND NOT ADOPTED (profiles/r02h_ab_sort_stream.txt): 22.43 against 22.13 ms per MSM in a batch of five at 2^22 points,
     // 3.78 against 3.76 for a 2^19-point shard - the sort's atomics and its blocks taking SM slots cost the accumulation more
@@ -899,7 +912,12 @@ int msm_enqueue(dp_ctx *ctx, uint64_t start, const uint4 *scalars_dev, uint64_t 
     if (ctx->msm_chunk) g.chunk = ctx->msm_chunk;
     const G1Affine *bases = use_pre ? ctx->pre_table + (start - ctx->pre_lo) : ctx->bases + start;
     const uint64_t max_digits = n * g.n_windows;
-    const uint64_t max_chunks = max_digits / g.chunk + 1;
+    // L batched-affine tree levels in front of the XYZZ chunks (msm.cuh): every bucket's slice of the sorted array is padded
+    // to a multiple of 2^L entries, the chunk kernel then sees 1 / 2^L of the entries
+    uint32_t L = max_digits >= ctx->msm_affine_min_digits ? ctx->msm_affine_levels : 0;
+    if (max_digits + ((uint64_t)g.n_keys << L) >= ((uint64_t)1 << 32)) L = 0;  // offsets are 32-bit
+    const uint64_t max_entries = max_digits + (L ? (uint64_t)g.n_keys * (((uint64_t)1 << L) - 1) : 0);
+    const uint64_t max_chunks = (max_entries >> L) / g.chunk + 1;
     const uint64_t n_slots = max_chunks + g.n_keys;  // partial (chunk j, bucket b) lives in slot j + b
     const uint32_t n_segs = g.red_windows * g.segs_per_window;
     const uint32_t n_scan_blocks = (g.n_keys + SCAN_BLOCK - 1) / SCAN_BLOCK;
@@ -914,7 +932,27 @@ int msm_enqueue(dp_ctx *ctx, uint64_t start, const uint4 *scalars_dev, uint64_t 
     uint32_t *counts = (uint32_t *)grab((g.n_keys + 1) * 4ull);
     uint32_t *offsets = (uint32_t *)grab((g.n_keys + 1) * 4ull);
     uint32_t *cursor = (uint32_t *)grab((g.n_keys + 1) * 4ull);
-    uint32_t *sorted = (uint32_t *)grab(max_digits * 4ull);
+    uint32_t *sorted = (uint32_t *)grab(max_entries * 4ull);
+    uint32_t *offsets_l = L ? (uint32_t *)grab((g.n_keys + 1) * 4ull) : offsets;  // bucket starts after the tree levels
+    // level buffers: outputs of the levels, prefix products, block roots and their inverses.  Only the compute stream touches
+    // them and the last of them is consumed by the chunk kernel queued below, so they go back to the pool when this function
+    // returns (stream-ordered reuse by the next job) - unless sorts run on their own stream and could be handed the blocks
+    Scratch level_tmp(ctx->pool);
+    auto grab_level = [&](size_t bytes) -> void * {
+        if (ctx->msm_sort_own_stream) return grab(bytes);
+        void *p = level_tmp.get<uint8_t>(bytes);
+        if (!p) oom = true;
+        return p;
+    };
+    G1Affine *lvl_out[4] = {nullptr, nullptr, nullptr, nullptr};
+    Fq *lvl_pre = nullptr, *lvl_root = nullptr, *lvl_inv = nullptr;
+    const uint32_t lvl_blocks = L ? blocks_for(max_entries >> 1, AFF_BLOCK_PAIRS) : 0;
+    if (L) {
+        for (uint32_t l = 0; l < L; l++) lvl_out[l] = (G1Affine *)grab_level((max_entries >> (l + 1)) * sizeof(G1Affine) + 512);
+        lvl_pre = (Fq *)grab_level((max_entries >> 1) * sizeof(Fq) + 512);
+        lvl_root = (Fq *)grab_level((size_t)lvl_blocks * sizeof(Fq));
+        lvl_inv = (Fq *)grab_level((size_t)lvl_blocks * sizeof(Fq));
+    }
     G1XYZZ *partials = (G1XYZZ *)grab(n_slots * sizeof(G1XYZZ));
     G1XYZZ *seg_sums = (G1XYZZ *)grab((uint64_t)n_segs * sizeof(G1XYZZ));
     G1XYZZ *win_sums = (G1XYZZ *)grab((uint64_t)g.red_windows * g.slices * sizeof(G1XYZZ));
@@ -935,17 +973,44 @@ int msm_enqueue(dp_ctx *ctx, uint64_t start, const uint4 *scalars_dev, uint64_t 
     cudaMemsetAsync(job.err, 0, 4, so);
     cudaMemsetAsync(multi_keys, 0, 4, so);
     DP_LAUNCH(msm_count_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, so, scalars_dev, n, g, counts, job.err);
+    if (L) {  // bucket slices padded to multiples of 2^L; the holes keep the filler = infinity
+        DP_LAUNCH(msm_pad_counts_kernel, dim3(blocks_for(g.n_keys, 256)), dim3(256), 0, so, counts, g.n_keys, L);
+        cudaMemsetAsync(sorted, 0xff, max_entries * 4ull, so);
+    }
     DP_LAUNCH(scan_block_sums_kernel, dim3(n_scan_blocks), dim3(SCAN_TPB), 0, so, counts, g.n_keys, block_sums);
     DP_LAUNCH(scan_block_offsets_kernel, dim3(1), dim3(SCAN_TPB), 0, so, block_sums, n_scan_blocks, offsets, g.n_keys);
     DP_LAUNCH(scan_write_kernel, dim3(n_scan_blocks), dim3(SCAN_TPB), 0, so, counts, g.n_keys, block_sums, offsets);
     cudaMemcpyAsync(cursor, offsets, (g.n_keys + 1) * 4ull, cudaMemcpyDeviceToDevice, so);
     DP_LAUNCH(msm_scatter_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, so, scalars_dev, n, g, cursor, sorted);
-    DP_LAUNCH(msm_find_big_kernel, dim3(blocks_for(g.n_keys, 256)), dim3(256), 0, so, offsets, g.n_keys, g.chunk, multi_keys + 1,
-              multi_keys);
+    if (!L)
+        DP_LAUNCH(msm_find_big_kernel, dim3(blocks_for(g.n_keys, 256)), dim3(256), 0, so, offsets, g.n_keys, g.chunk, multi_keys + 1,
+                  multi_keys);
     DP_CUDA(ctx, cudaEventRecord(job.ev_sorted, so));
     DP_CUDA(ctx, cudaStreamWaitEvent(st, job.ev_sorted, 0));
     if (record_breakdown) cudaEventRecord(ctx->ev_msm[1], st);
-    if (ctx->msm_min_blocks == 4)
+    if (L) {
+        AffSrc src{sorted, bases};
+        const uint32_t *n_elems = offsets + g.n_keys;  // total entries of the padded array (device side)
+        for (uint32_t l = 0; l < L; l++) {
+            const uint32_t nb = blocks_for(max_entries >> (l + 1), AFF_BLOCK_PAIRS);
+            if (l == 0) {
+                DP_LAUNCH(aff_k1_kernel<true>, dim3(nb), dim3(AFF_TPB), 0, st, src, n_elems, l, lvl_pre, lvl_root);
+                DP_LAUNCH(aff_k2_kernel, dim3(blocks_for(nb, 32)), dim3(32), 0, st, (const Fq *)lvl_root, lvl_inv, nb);
+                DP_LAUNCH(aff_k3_kernel<true>, dim3(nb), dim3(AFF_TPB), 0, st, src, n_elems, l, (const Fq *)lvl_pre, (const Fq *)lvl_inv, lvl_out[l]);
+            } else {
+                DP_LAUNCH(aff_k1_kernel<false>, dim3(nb), dim3(AFF_TPB), 0, st, src, n_elems, l, lvl_pre, lvl_root);
+                DP_LAUNCH(aff_k2_kernel, dim3(blocks_for(nb, 32)), dim3(32), 0, st, (const Fq *)lvl_root, lvl_inv, nb);
+                DP_LAUNCH(aff_k3_kernel<false>, dim3(nb), dim3(AFF_TPB), 0, st, src, n_elems, l, (const Fq *)lvl_pre, (const Fq *)lvl_inv, lvl_out[l]);
+            }
+            src = AffSrc{nullptr, lvl_out[l]};
+        }
+        DP_LAUNCH(msm_shift_offsets_kernel, dim3(blocks_for(g.n_keys + 1, 256)), dim3(256), 0, st, (const uint32_t *)offsets, g.n_keys, L, offsets_l);
+        DP_LAUNCH(msm_find_big_kernel, dim3(blocks_for(g.n_keys, 256)), dim3(256), 0, st, (const uint32_t *)offsets_l, g.n_keys, g.chunk,
+                  multi_keys + 1, multi_keys);
+        DP_LAUNCH((msm_accumulate_kernel<3, true>), dim3(blocks_for(max_chunks, MSM_TPB)), dim3(MSM_TPB), 0, st, (const uint32_t *)offsets_l, g.n_keys,
+                  g.chunk, (const uint32_t *)nullptr, (const G1Affine *)lvl_out[L - 1], partials);
+        ctx->launches += 3 * L + 2;
+    } else if (ctx->msm_min_blocks == 4)
         DP_LAUNCH(msm_accumulate_kernel<4>, dim3(blocks_for(max_chunks, MSM_TPB)), dim3(MSM_TPB), 0, st, offsets, g.n_keys, g.chunk, sorted,
                   bases, partials);
     else if (ctx->msm_min_blocks == 5)
@@ -955,11 +1020,11 @@ int msm_enqueue(dp_ctx *ctx, uint64_t start, const uint4 *scalars_dev, uint64_t 
         DP_LAUNCH(msm_accumulate_kernel<3>, dim3(blocks_for(max_chunks, MSM_TPB)), dim3(MSM_TPB), 0, st, offsets, g.n_keys, g.chunk, sorted,
                   bases, partials);
     DP_LAUNCH(msm_collapse_kernel, dim3(max_multi * 32 < 148ull * 8 * MSM_TPB ? blocks_for(max_multi * 32, MSM_TPB) : 148 * 8),
-              dim3(MSM_TPB), 0, st, multi_keys + 1, multi_keys, offsets, g.chunk, partials);
+              dim3(MSM_TPB), 0, st, multi_keys + 1, multi_keys, (const uint32_t *)offsets_l, g.chunk, partials);
     if (record_breakdown) cudaEventRecord(ctx->ev_msm[2], st);
     DP_CUDA(ctx, cudaEventRecord(job.ev_head, st));
     DP_CUDA(ctx, cudaStreamWaitEvent(tl, job.ev_head, 0));
-    DP_LAUNCH(msm_reduce_kernel, dim3(blocks_for(n_segs, MSM_TPB)), dim3(MSM_TPB), 0, tl, partials, offsets, g, seg_sums);
+    DP_LAUNCH(msm_reduce_kernel, dim3(blocks_for(n_segs, MSM_TPB)), dim3(MSM_TPB), 0, tl, partials, (const uint32_t *)offsets_l, g, seg_sums);
     DP_LAUNCH(msm_window_sum_kernel, dim3(g.red_windows * g.slices), dim3(MSM_TPB), 0, tl, seg_sums, g, win_sums);
     DP_LAUNCH(msm_final_kernel, dim3(1), dim3(32), 0, tl, win_sums, g, out_dev);
     if (record_breakdown) cudaEventRecord(ctx->ev_msm[3], tl);
@@ -999,6 +1064,58 @@ int msm_device(dp_ctx *ctx, uint64_t start, const uint4 *scalars_dev, uint64_t n
     int rc = msm_enqueue(ctx, start, scalars_dev, n, out_dev, jobs[0], n != 0);
     int rc2 = msm_finish(ctx, jobs, rc == DP_OK && n != 0);
     return rc != DP_OK ? rc : rc2;
+}
+
+// dp_init's choice between the plain MSM pipeline and L = 2 batched-affine tree levels in front of it: one MSM over the
+// context's own window-multiple table either way (pseudo-random scalars, warm-up + best of two), the results compared
+// byte for byte, the levels kept only when they agree AND are at least 2 % faster.  Only the geometry of the hot path is
+// tuned (the whole table range); a worker's shard of a multi-GPU MSM is its own context and tunes itself.
+int msm_tune(dp_ctx *ctx) {
+    ctx->tune_ms[0] = ctx->tune_ms[1] = 0.f;
+    ctx->tune_equal = -1;
+    if (ctx->msm_affine_forced >= 0) {
+        ctx->msm_affine_levels = (uint32_t)ctx->msm_affine_forced;
+        return DP_OK;
+    }
+    ctx->msm_affine_levels = 0;
+    const uint64_t span = ctx->pre_hi - ctx->pre_lo, digits = span * ctx->pre_nw;
+    if (!ctx->msm_tune_enabled || !ctx->pre_table || digits < ctx->msm_affine_min_digits) return DP_OK;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    if (digits * 200ull > free_b / 2) return DP_OK;  // level buffers: ~ 150 B per digit on top of the plain pipeline's 12
+    Scratch tmp(ctx->pool);
+    uint4 *sc = tmp.get<uint4>(2 * span);
+    G1JacobianOut *out = tmp.get<G1JacobianOut>(2);
+    if (!sc || !out) return DP_OK;  // not enough memory to try: stay on the plain pipeline
+    DP_LAUNCH(msm_tune_scalars_kernel, dim3(blocks_for(span, 256)), dim3(256), 0, ctx->stream, sc, span, 0x7A11E5ull);
+    ctx->launches++;
+    DP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int mode = 0; mode < 2; mode++) {
+        ctx->msm_affine_levels = mode ? 2u : 0u;
+        double best = 1e30;
+        for (int rep = 0; rep < 3; rep++) {
+            const auto t0 = std::chrono::steady_clock::now();
+            const int rc = msm_device(ctx, ctx->pre_lo, sc, span, out + mode, nullptr);
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            if (rc != DP_OK) {
+                ctx->msm_affine_levels = 0;
+                if (mode == 0) return rc;
+                // the candidate failed where the plain pipeline had just worked: keep the plain pipeline and say so
+                // (tune_equal = 0); a sticky CUDA error will surface again at the caller's next call
+                cudaGetLastError();
+                ctx->tune_ms[1] = 0.f;
+                ctx->tune_equal = 0;
+                return DP_OK;
+            }
+            if (rep && ms < best) best = ms;
+        }
+        ctx->tune_ms[mode] = (float)best;
+    }
+    G1JacobianOut host[2];
+    DP_CUDA(ctx, cudaMemcpy(host, out, sizeof host, cudaMemcpyDeviceToHost));
+    ctx->tune_equal = memcmp(&host[0], &host[1], sizeof(G1JacobianOut)) == 0 ? 1 : 0;
+    ctx->msm_affine_levels = ctx->tune_equal == 1 && ctx->tune_ms[1] < 0.98f * ctx->tune_ms[0] ? 2u : 0u;
+    return DP_OK;
 }
 
 // give back everything a pending MSM holds; the caller has made sure its kernels are done
@@ -1215,6 +1332,12 @@ int dp_create(int cuda_device, uint64_t me, uint64_t n_workers, dp_ctx **out) {
     if (const char *e = getenv("DP_MSM_BLOCKS")) ctx->msm_min_blocks = atoi(e) >= 3 && atoi(e) <= 5 ? atoi(e) : 3;
     if (const char *e = getenv("DP_QUOT_TABLE")) ctx->quot_table = atoi(e) != 0 ? 1 : 0;
     if (const char *e = getenv("DP_MSM_SORT_STREAM")) ctx->msm_sort_own_stream = atoi(e) != 0;
+    if (const char *e = getenv("DP_MSM_AFFINE")) {
+        ctx->msm_affine_forced = atoi(e) < 0 ? 0 : atoi(e) > 3 ? 3 : atoi(e);
+        ctx->msm_affine_levels = (uint32_t)ctx->msm_affine_forced;
+    }
+    if (const char *e = getenv("DP_MSM_AFFINE_MIN")) ctx->msm_affine_min_digits = strtoull(e, nullptr, 10);
+    if (const char *e = getenv("DP_MSM_TUNE")) ctx->msm_tune_enabled = atoi(e) != 0;
     ctx->me = me;
     ctx->W = n_workers;
     int rc = DP_OK;
@@ -1394,6 +1517,7 @@ static int init_impl(dp_ctx *ctx, const void *bases, size_t n_bases, uint64_t do
             return fail(ctx, DP_E_ARG, "dp_init: domain 2^%u too small to split over %llu workers", d.log_n, (unsigned long long)ctx->W);
     }
     DP_TRY(call_end(ctx, true));
+    DP_TRY(msm_tune(ctx));
     ctx->inited = true;
     return DP_OK;
 }
@@ -2132,6 +2256,15 @@ int dp_last_msm_breakdown(const dp_ctx *ctx, float *sort_ms, float *accumulate_m
     if (sort_ms) *sort_ms = ctx->msm_ms[0];
     if (accumulate_ms) *accumulate_ms = ctx->msm_ms[1];
     if (reduce_ms) *reduce_ms = ctx->msm_ms[2];
+    return DP_OK;
+}
+
+int dp_msm_tuning(const dp_ctx *ctx, float *plain_ms, float *affine_ms, int *levels, int *equal) {
+    if (!ctx) return DP_E_ARG;
+    if (plain_ms) *plain_ms = ctx->tune_ms[0];
+    if (affine_ms) *affine_ms = ctx->tune_ms[1];
+    if (levels) *levels = (int)ctx->msm_affine_levels;
+    if (equal) *equal = ctx->tune_equal;
     return DP_OK;
 }
 

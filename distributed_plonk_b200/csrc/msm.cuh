@@ -414,7 +414,9 @@ DP_D G1Affine load_affine(const G1Affine *p) {
 // MINB: resident blocks per SM the register allocation aims for (3: 152 registers, no spills; 4: 128 registers and a
 // few hundred bytes of spills around the outlined multiplications).  The kernel is bound by the dependent carry
 // chains of the Fq products (ncu r02a: 52 % of the warp samples are fixed-latency waits at 3 warps per scheduler).
-template <int MINB>
+// DIRECT: the points to add are bases[e] themselves, in bucket order (the output of the batched-affine tree levels below)
+// instead of bases[sorted[e]] with the sign in bit 31.
+template <int MINB, bool DIRECT = false>
 __global__ void __launch_bounds__(MSM_TPB, MINB) msm_accumulate_kernel(const uint32_t *offsets, uint32_t n_keys, uint32_t chunk,
                                                                         const uint32_t *sorted, const G1Affine *bases, G1XYZZ *partials) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -439,12 +441,243 @@ __global__ void __launch_bounds__(MSM_TPB, MINB) msm_accumulate_kernel(const uin
                 next = offsets[b + 1];
             } while (next == e);
         }
-        const uint32_t v = sorted[e];
-        G1Affine p = load_affine(bases + (v & 0x7fffffffu));
-        if (v >> 31) p = p.neg();
+        G1Affine p;
+        if (DIRECT) {
+            p = load_affine(bases + e);
+        } else {
+            const uint32_t v = sorted[e];
+            p = load_affine(bases + (v & 0x7fffffffu));
+            if (v >> 31) p = p.neg();
+        }
         acc = acc.add_mixed(p);
     }
     partials[j + b] = acc;
+}
+
+// ------------------------------------------------------------------ batched-affine tree levels
+// Before the XYZZ chunks, L levels of a pairwise tree inside every bucket: level l replaces the elements (2k, 2k+1) of
+// the bucket-ordered sequence by their sum, an AFFINE addition whose field inversion is shared by a whole thread block
+// (Montgomery's trick): 6.4 field products per addition at 16 pairs per thread against 10 for the XYZZ mixed addition
+// (measured per level on B200, tools/microbench6.cu -> profiles/r02h_microbench_affine2.txt: 0.83x the time on gathered
+// operands, 0.79x on contiguous ones).  For pairs never to straddle two buckets every bucket's slice of the sorted index
+// array is padded to a multiple of 2^L entries (msm_pad_counts_kernel; the holes keep the 0xffffffff the array was
+// filled with = the point at infinity), so all levels are plain strided passes and bucket b's survivors sit at
+// offsets[b] >> L afterwards.  One level = three kernels:
+//   aff_k1  per pair the denominator d (x2 - x1; 2y for a doubling; 1 when a partner is infinity or the sum is), each
+//           thread chains the products of its KP pairs (exclusive prefixes -> global), block tree over the thread totals
+//   aff_k2  one inversion per block (binary extended Euclid per lane)
+//   aff_k3  the tree again, inverses pushed down to the threads, then per pair 1/d = inv_run * prefix, lambda, x3, y3
+constexpr int AFF_TPB = 128;
+constexpr int AFF_KP = 16;                                  // pairs per thread
+constexpr uint32_t AFF_BLOCK_PAIRS = AFF_TPB * AFF_KP;
+constexpr uint32_t AFF_HOLE = 0xffffffffu;                  // padding entry of the sorted index array
+
+DP_D Fq load_fq(const Fq *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    Fq r;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const uint4 v = q[k];
+        r.l[4 * k] = v.x; r.l[4 * k + 1] = v.y; r.l[4 * k + 2] = v.z; r.l[4 * k + 3] = v.w;
+    }
+    return r;
+}
+DP_D void store_fq(Fq *p, const Fq &v) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+#pragma unroll
+    for (int k = 0; k < 3; k++) q[k] = make_uint4(v.l[4 * k], v.l[4 * k + 1], v.l[4 * k + 2], v.l[4 * k + 3]);
+}
+
+// counts[key] rounded up to a multiple of 2^log_pad (before the scan turns them into offsets)
+__global__ void msm_pad_counts_kernel(uint32_t *counts, uint32_t n_keys, uint32_t log_pad) {
+    const uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
+    if (key >= n_keys) return;
+    const uint32_t m = (1u << log_pad) - 1;
+    counts[key] = (counts[key] + m) & ~m;
+}
+// out[i] = offsets[i] >> shift, i <= n_keys: where the buckets start after `shift` tree levels
+__global__ void msm_shift_offsets_kernel(const uint32_t *offsets, uint32_t n_keys, uint32_t shift, uint32_t *out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n_keys) out[i] = offsets[i] >> shift;
+}
+
+// where a level reads its operands: GATHER = the window-multiple table through the sorted index array, else the previous level
+struct AffSrc {
+    const uint32_t *sorted;
+    const G1Affine *pts;
+};
+// element e of the level's input; `hole` = padding entry.  x only: the y coordinate is fetched by aff_y when needed.
+template <bool GATHER>
+DP_D Fq aff_x(const AffSrc &s, uint64_t e, uint32_t &v, bool &hole) {
+    if (GATHER) {
+        v = s.sorted[e];
+        hole = v == AFF_HOLE;
+        return hole ? Fq::zero() : load_fq(&s.pts[v & 0x7fffffffu].x);
+    }
+    v = 0;
+    hole = false;
+    return load_fq(&s.pts[e].x);
+}
+template <bool GATHER>
+DP_D Fq aff_y(const AffSrc &s, uint64_t e, uint32_t v, bool hole) {
+    if (GATHER) {
+        if (hole) return Fq::zero();
+        const Fq y = load_fq(&s.pts[v & 0x7fffffffu].y);
+        return (v >> 31) && !y.is_zero() ? y.neg() : y;   // (x, 0) only when x = 0 too: infinity stays (0, 0)
+    }
+    return load_fq(&s.pts[e].y);
+}
+
+// What pair k = elements (2k, 2k+1) needs: kind 0 = chord addition (d = x2 - x1), 1 = doubling (d = 2 y1), 2 = the sum is the
+// first point, 3 = the second, 4 = infinity (kinds 2-4: d = 1).  d is never zero.  With LAZY the y coordinates are loaded
+// only when x1 = x2 or an x is zero (a hole, infinity, or one of the two curve points with x = 0); the classification
+// does not depend on LAZY, so aff_k1 (LAZY) and aff_k3 compute the same d for the same pair.
+struct AffPair {
+    Fq x1, y1, x2, y2, d;
+    uint32_t kind;
+};
+template <bool GATHER, bool LAZY>
+DP_D void aff_pair(const AffSrc &s, uint64_t k, AffPair &p) {
+    uint32_t v1, v2;
+    bool h1, h2;
+    p.x1 = aff_x<GATHER>(s, 2 * k, v1, h1);
+    p.x2 = aff_x<GATHER>(s, 2 * k + 1, v2, h2);
+    const bool plain = !h1 && !h2 && !p.x1.is_zero() && !p.x2.is_zero() && p.x1 != p.x2;
+    if (!(LAZY && plain)) {
+        p.y1 = aff_y<GATHER>(s, 2 * k, v1, h1);
+        p.y2 = aff_y<GATHER>(s, 2 * k + 1, v2, h2);
+    }
+    if (plain) {
+        p.kind = 0;
+        p.d = p.x2 - p.x1;
+        return;
+    }
+    const bool inf1 = h1 || (p.x1.is_zero() && p.y1.is_zero()), inf2 = h2 || (p.x2.is_zero() && p.y2.is_zero());
+    p.d = Fq::one();
+    if (inf1 && inf2) {
+        p.kind = 4;
+    } else if (inf2) {
+        p.kind = 2;
+    } else if (inf1) {
+        p.kind = 3;
+    } else if (p.x1 != p.x2) {
+        p.kind = 0;
+        p.d = p.x2 - p.x1;
+    } else if (p.y1 == p.y2 && !p.y1.is_zero()) {
+        p.kind = 1;
+        p.d = p.y1.dbl();
+    } else {
+        p.kind = 4;   // P + (-P), or the doubling of a point of order two
+    }
+}
+
+// product of the block's thread totals -> tree[1]; leaves at tree[AFF_TPB + t]
+DP_D void aff_tree_up(Fq *tree, const Fq &mine) {
+    const uint32_t t = threadIdx.x;
+    tree[AFF_TPB + t] = mine;
+    __syncthreads();
+    for (uint32_t w = AFF_TPB >> 1; w >= 1; w >>= 1) {
+        if (t < w) tree[w + t] = tree[2 * (w + t)] * tree[2 * (w + t) + 1];
+        __syncthreads();
+    }
+}
+
+// number of pairs of this level: (*n_elems >> level_shift) / 2, n_elems = total entries of the padded sorted array
+DP_D uint64_t aff_pairs(const uint32_t *n_elems, uint32_t level_shift) { return ((uint64_t)*n_elems >> level_shift) >> 1; }
+
+template <bool GATHER>
+__global__ void __launch_bounds__(AFF_TPB) aff_k1_kernel(AffSrc src, const uint32_t *n_elems, uint32_t level_shift, Fq *pre, Fq *root) {
+    __shared__ Fq tree[2 * AFF_TPB];
+    const uint32_t t = threadIdx.x;
+    const uint64_t m = aff_pairs(n_elems, level_shift), first = (uint64_t)blockIdx.x * AFF_BLOCK_PAIRS;
+    if (first >= m) {  // (block-uniform) nothing here: the inversion kernel still reads this block's root
+        if (t == 0) store_fq(root + blockIdx.x, Fq::one());
+        return;
+    }
+    Fq run = Fq::one();
+    for (int j = 0; j < AFF_KP; j++) {
+        const uint64_t k = first + (uint64_t)j * AFF_TPB + t;
+        if (k < m) {
+            AffPair p;
+            aff_pair<GATHER, true>(src, k, p);
+            store_fq(pre + k, run);  // product of this thread's earlier denominators
+            run = run * p.d;
+        }
+    }
+    aff_tree_up(tree, run);
+    if (t == 0) store_fq(root + blockIdx.x, tree[1]);
+}
+
+// inv[i] = 1 / root[i]; one root per lane, data-dependent iteration counts (the warp takes the slowest lane's)
+__global__ void __launch_bounds__(32) aff_k2_kernel(const Fq *root, Fq *inv, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Fq r = load_fq(root + i);
+    store_fq(inv + i, r.is_zero() ? r : r.inverse_vartime());  // (a root is never zero; zero would not terminate)
+}
+
+template <bool GATHER>
+__global__ void __launch_bounds__(AFF_TPB) aff_k3_kernel(AffSrc src, const uint32_t *n_elems, uint32_t level_shift, const Fq *pre,
+                                                         const Fq *root_inv, G1Affine *out) {
+    __shared__ Fq tree[2 * AFF_TPB];
+    const uint32_t t = threadIdx.x;
+    const uint64_t m = aff_pairs(n_elems, level_shift), first = (uint64_t)blockIdx.x * AFF_BLOCK_PAIRS;
+    if (first >= m) return;  // block-uniform
+    // this thread's total again: the prefix of its last pair times that pair's denominator
+    int last = -1;
+    for (int j = AFF_KP - 1; j >= 0 && last < 0; j--)
+        if (first + (uint64_t)j * AFF_TPB + t < m) last = j;
+    Fq total = Fq::one();
+    if (last >= 0) {
+        const uint64_t k = first + (uint64_t)last * AFF_TPB + t;
+        AffPair p;
+        aff_pair<GATHER, true>(src, k, p);
+        total = load_fq(pre + k) * p.d;
+    }
+    aff_tree_up(tree, total);
+    if (t == 0) tree[1] = load_fq(root_inv + blockIdx.x);
+    __syncthreads();
+    for (uint32_t w = 1; w < AFF_TPB; w <<= 1) {
+        if (t < w) {
+            const uint32_t node = w + t;
+            const Fq iv = tree[node], l = tree[2 * node], r = tree[2 * node + 1];
+            tree[2 * node] = iv * r;
+            tree[2 * node + 1] = iv * l;
+        }
+        __syncthreads();
+    }
+    Fq inv_run = tree[AFF_TPB + t];  // 1 / (product of this thread's denominators)
+    for (int j = last; j >= 0; j--) {
+        const uint64_t k = first + (uint64_t)j * AFF_TPB + t;
+        AffPair p;
+        aff_pair<GATHER, false>(src, k, p);
+        const Fq inv_d = inv_run * load_fq(pre + k);
+        inv_run = inv_run * p.d;
+        G1Affine r;
+        if (p.kind <= 1) {
+            Fq num;
+            if (p.kind == 0) {
+                num = p.y2 - p.y1;
+            } else {
+                const Fq xx = p.x1.sqr();
+                num = xx.dbl() + xx;  // 3 x^2 (a = 0)
+                p.x2 = p.x1;
+            }
+            const Fq lambda = num * inv_d;
+            r.x = lambda.sqr() - p.x1 - p.x2;
+            r.y = lambda * (p.x1 - r.x) - p.y1;
+        } else if (p.kind == 2) {
+            r.x = p.x1;
+            r.y = p.y1;
+        } else if (p.kind == 3) {
+            r.x = p.x2;
+            r.y = p.y2;
+        } else {
+            r = G1Affine::inf();
+        }
+        store_fq(&out[k].x, r.x);
+        store_fq(&out[k].y, r.y);
+    }
 }
 
 // Buckets cut into several tasks (skewed scalars: one bucket can hold a large share of all points)
@@ -548,6 +781,24 @@ __global__ void msm_final_kernel(const G1XYZZ *slice_sums, MsmGeom g, G1Jacobian
         total = total.add(part);
     }
     if (lane == 0) *out = G1JacobianOut::from_affine(total.to_affine(true));
+}
+
+// pseudo-random canonical scalars below 2^254 (< r) for msm_tune(): SplitMix64 per limb
+__global__ void msm_tune_scalars_kernel(uint4 *scalars, uint64_t n, uint64_t seed) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[8];
+    for (int k = 0; k < 4; k++) {
+        uint64_t z = seed + (4 * i + k + 1) * 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        w[2 * k] = (uint32_t)z;
+        w[2 * k + 1] = (uint32_t)(z >> 32);
+    }
+    w[7] &= 0x3fffffffu;
+    scalars[2 * i] = make_uint4(w[0], w[1], w[2], w[3]);
+    scalars[2 * i + 1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
 // ------------------------------------------------------------------ precomputed window multiples

@@ -273,6 +273,12 @@ int dp_sync(dp_ctx *ctx);
  * bucket accumulation (the dominant kernel), bucket reduction + window combine + normalise */
 int dp_last_msm_breakdown(const dp_ctx *ctx, float *sort_ms, float *accumulate_ms, float *reduce_ms);
 
+/* what dp_init's MSM tuning found: one MSM over the context's own window-multiple table with the plain pipeline
+ * (XYZZ chunks) and one with `levels` batched-affine tree levels in front of it; *equal = the two results were the same
+ * 144 bytes (1), differed (0: the plain pipeline is kept), or the tuning did not run (-1: small SRS, or DP_MSM_AFFINE set);
+ * *levels = what MSMs of this context use (0 = plain).  Replaces nothing in the reference: ark-ec has one algorithm. */
+int dp_msm_tuning(const dp_ctx *ctx, float *plain_ms, float *affine_ms, int *levels, int *equal);
+
 /* synthetic SRS: n distinct points k_i*G (k_i = SplitMix64(seed, i)), raw 104-byte G1Affine each,
  * computed on the device and written to `out` (host memory, or device memory of the same GPU); feeds
  * dp_init in benches and tests */

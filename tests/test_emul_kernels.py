@@ -123,6 +123,86 @@ def test_msm_precomputed_window_multiples(orc, emul_lib):
     c.close()
 
 
+@pytest.mark.parametrize("levels", [1, 2, 3])
+def test_msm_batched_affine_levels(orc, emul_lib, monkeypatch, levels):
+    """the batched-affine tree levels in front of the XYZZ chunks (DP_MSM_AFFINE): every scalar distribution, both
+    bucket layouts (per window / one shared set over the window-multiple table), the additions that are not chords -
+    holes, infinity, P + P, P + (-P) - and a batch"""
+    monkeypatch.setenv("DP_MSM_AFFINE", str(levels))
+    monkeypatch.setenv("DP_MSM_AFFINE_MIN", "0")
+    bases = orc.gen_bases(5, 600, 64, True)                  # 64 distinct points tiled: equal points meet in the buckets
+    c = Context(emul_lib, 0, 0, 1)
+    c.init(bases, 1 << 4, 1 << 7)
+    assert c.msm_tuning()["levels"] == levels and c.msm_tuning()["equal"] == -1       # forced: nothing was tuned
+    l0 = c.launch_count()
+    which = None if levels == 2 else ("witness-like", "all r-1")
+    common.check_msm(orc, c, bases, 200, 21, which=which)
+    assert c.launch_count() - l0 == (5 if levels == 2 else 2) * (11 + 3 * levels + 2)
+    for cbits in (4, 13) if levels == 2 else (7,):
+        c.debug_set_limits(11, 9, cbits)
+        common.check_msm(orc, c, bases, 150, 30 + cbits, which=("witness-like",))
+    c.debug_set_limits(11, 9, 0)
+    sc = orc.gen_fr(9, 600, False)
+    common.assert_point_eq(orc, c.msm(3, 4, sc[:1]), orc.msm(bases[3:4], sc[:1]), "infinity base")
+    s2 = np.zeros((65, 4), dtype=np.uint64)
+    s2[0] = common.u256(5)
+    s2[64] = common.u256(common.R_MOD - 5)
+    assert orc.normalize(c.msm(0, 65, s2))[96] == 1           # P + (-P)
+    s2[64] = common.u256(5)
+    common.assert_point_eq(orc, c.msm(0, 65, s2), orc.msm(bases[:65], s2), "same point twice")
+    if levels == 2:
+        scs = [np.ascontiguousarray(orc.gen_fr(70 + k, 300, False)) for k in range(3)]
+        outs = c.msm_batch([(0, 300, scs[0], 300), (100, 250, scs[1], 150), (0, 0, scs[2], 0)])
+        for k, (lo, hi) in enumerate([(0, 300), (100, 250), (0, 0)]):
+            common.assert_point_eq(orc, outs[k], orc.msm(bases[lo:hi], scs[k][: hi - lo]), f"host batch job {k}")
+    c.close()
+    if levels == 2:                                            # the shared bucket set over the window-multiple table
+        n = 2048
+        bases = orc.gen_bases(11, n, 64, True)
+        c = Context(emul_lib, 0, 0, 1)
+        c.init(bases, 1 << 4, 1 << 7)
+        common.check_msm(orc, c, bases, n, 61, which=("witness-like", "all one"))
+        c.close()
+
+
+def test_msm_tuning_at_init(orc, emul_lib, monkeypatch):
+    """dp_init times the plain pipeline against two tree levels over the context's own table and keeps the levels only
+    if both give the same 144 bytes; whatever it chose, MSMs agree with the oracle"""
+    monkeypatch.delenv("DP_MSM_AFFINE", raising=False)
+    monkeypatch.setenv("DP_MSM_AFFINE_MIN", "0")
+    monkeypatch.setenv("DP_MSM_TUNE", "1")
+    n = 2048
+    bases = orc.gen_bases(11, n, 64, True)
+    c = Context(emul_lib, 0, 0, 1)
+    c.init(bases, 1 << 4, 1 << 7)
+    t = c.msm_tuning()
+    assert t["equal"] == 1 and t["plain_ms"] > 0 and t["affine_ms"] > 0 and t["levels"] in (0, 2)
+    common.check_msm(orc, c, bases, n, 63, which=("uniform",))
+    c.init(orc.gen_bases(5, 100, 64, True), 1 << 4, 1 << 7)   # a small SRS has no table: nothing to tune, plain pipeline
+    assert c.msm_tuning() == {"plain_ms": 0.0, "affine_ms": 0.0, "levels": 0, "equal": -1}
+    c.close()
+    monkeypatch.delenv("DP_MSM_TUNE")                          # without the opt-in dp_init never tunes and never selects the levels
+    c = Context(emul_lib, 0, 0, 1)
+    c.init(bases, 1 << 4, 1 << 7)
+    assert c.msm_tuning() == {"plain_ms": 0.0, "affine_ms": 0.0, "levels": 0, "equal": -1}
+    c.close()
+
+
+def test_msm_probe_is_a_guarded_opt_in():
+    """tune.probe runs dp_init's tuning in a child process; whatever happens there, the caller only opts in on
+    "identical and faster" (here the child cannot even create a context: no GPU)"""
+    from distributed_plonk_b200 import tune
+    assert tune.choose({"plain_ms": 23.0, "affine_ms": 21.0, "levels": 2, "equal": 1}) == 2
+    assert tune.choose({"plain_ms": 23.0, "affine_ms": 24.0, "levels": 0, "equal": 1}) == 0      # slower: the tuning said 0
+    assert tune.choose({"plain_ms": 23.0, "affine_ms": 21.0, "levels": 2, "equal": 0}) == 0      # different results
+    assert tune.choose({"plain_ms": 0.0, "affine_ms": 0.0, "levels": 0, "equal": -1}) == 0       # not tuned
+    assert tune.choose({"error": "probe exited with -11"}) == 0
+    import torch
+    if not torch.cuda.is_available():
+        res = tune.probe(0, 0, 1, 12, timeout=120)
+        assert "error" in res and tune.choose(res) == 0
+
+
 def test_msm_dev_batch(orc, ctx):
     """dp_msm_dev_batch: three MSMs in flight (tails on their own stream), device pointers in/out
     (host memory under the emulator)"""

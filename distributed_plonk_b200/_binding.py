@@ -13,7 +13,7 @@ EXPORTS = [
     "dp_fft1", "dp_fft1_rows", "dp_fft2_prepare", "dp_fft_exchange_begin", "dp_fft_exchange_end", "dp_fft2",
     "dp_ntt", "dp_round1", "dp_get_wire", "dp_peer_arena_create", "dp_peer_attach", "dp_last_timing",
     "dp_launch_count", "dp_sync", "dp_msm_dev", "dp_ntt_dev", "dp_fft_dev", "dp_debug_set_limits",
-    "dp_last_msm_breakdown", "dp_msm_tuning", "dp_debug_gen_bases", "dp_fft_dev_rows", "dp_fft_dev_cols", "dp_peer_ready", "dp_fft_dev_rows_p2p", "dp_fft_dev_p2p", "dp_msm_dev_batch", "dp_perm_product", "dp_msm_batch", "dp_perm_product_dev",
+    "dp_last_msm_breakdown", "dp_msm_tuning", "dp_msm_tuning_all", "dp_debug_gen_bases", "dp_fft_dev_rows", "dp_fft_dev_cols", "dp_peer_ready", "dp_fft_dev_rows_p2p", "dp_fft_dev_p2p", "dp_msm_dev_batch", "dp_perm_product", "dp_msm_batch", "dp_perm_product_dev",
     "dp_quotient_evals", "dp_quotient_evals_dev", "dp_poly_eval", "dp_poly_eval_dev", "dp_poly_lincomb", "dp_poly_lincomb_dev",
     "dp_poly_div_linear", "dp_poly_div_linear_dev", "dp_init_compressed", "dp_get_bases",
     "dp_msm_submit", "dp_msm_collect", "dp_poly_put", "dp_poly_ptr", "dp_poly_get", "dp_poly_free", "dp_commit_dev",
@@ -73,6 +73,7 @@ def bind(cdll: C.CDLL) -> C.CDLL:
         "dp_debug_set_limits": (i, [vp, u32, u32, i]),
         "dp_last_msm_breakdown": (i, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
         "dp_msm_tuning": (i, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "dp_msm_tuning_all": (i, [vp, C.POINTER(C.c_float)]),
         "dp_debug_gen_bases": (i, [vp, u64, sz, vp]),
         "dp_fft_dev_rows": (i, [vp, vp, i, i, i, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]),
         "dp_fft_dev_cols": (i, [vp, vp]),
@@ -454,7 +455,12 @@ class Context:
         {"plain_ms", "affine_ms", "levels", "equal"} (equal: 1 same result, 0 different, -1 not run)"""
         a, b, lv, eq = C.c_float(), C.c_float(), C.c_int(), C.c_int()
         self._ck(self.lib.dp_msm_tuning(self.h, C.byref(a), C.byref(b), C.byref(lv), C.byref(eq)))
-        return {"plain_ms": a.value, "affine_ms": b.value, "levels": lv.value, "equal": eq.value}
+        out = {"plain_ms": a.value, "affine_ms": b.value, "levels": lv.value, "equal": eq.value}
+        allms = (C.c_float * 4)()
+        self._ck(self.lib.dp_msm_tuning_all(self.h, allms))
+        if any(v > 0 for v in allms):
+            out["ms_by_levels"] = [round(float(v), 4) for v in allms]
+        return out
 
     def gen_bases(self, seed: int, n: int) -> np.ndarray:
         out = np.zeros((n, G1_AFFINE_BYTES), dtype=np.uint8)

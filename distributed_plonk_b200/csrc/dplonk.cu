@@ -203,7 +203,8 @@ struct dp_ctx {
     int msm_affine_forced = -1;             // -1 = not forced
     bool msm_tune_enabled = false;          // env DP_MSM_TUNE=1: dp_init runs msm_tune(); otherwise the plain pipeline unless forced
     uint64_t msm_affine_min_digits = (uint64_t)1 << 22;
-    float tune_ms[2] = {0.f, 0.f};          // msm_tune(): plain / with levels (0 = not measured)
+    float tune_ms[2] = {0.f, 0.f};          // msm_tune(): plain / best candidate with levels (0 = not measured)
+    float tune_all_ms[4] = {0.f, 0.f, 0.f, 0.f};  // msm_tune(): 0, 1, 2, 3 levels
     int tune_equal = -1;                    // msm_tune(): results identical (1), different (0), not run (-1)
     // knob (env DP_MSM_SORT_STREAM=1): the digit sorts of a batch run on their own stream, ahead of / under the accumulations.
     // MEASURED AND NOT ADOPTED (profiles/r02h_ab_sort_stream.txt): 22.43 against 22.13 ms per MSM in a batch of five at 2^22 points,
@@ -1066,12 +1067,14 @@ int msm_device(dp_ctx *ctx, uint64_t start, const uint4 *scalars_dev, uint64_t n
     return rc != DP_OK ? rc : rc2;
 }
 
-// dp_init's choice between the plain MSM pipeline and L = 2 batched-affine tree levels in front of it: one MSM over the
-// context's own window-multiple table either way (pseudo-random scalars, warm-up + best of two), the results compared
-// byte for byte, the levels kept only when they agree AND are at least 2 % faster.  Only the geometry of the hot path is
-// tuned (the whole table range); a worker's shard of a multi-GPU MSM is its own context and tunes itself.
+// dp_init's choice (DP_MSM_TUNE=1) between the plain MSM pipeline and 1, 2 or 3 batched-affine tree levels in front of it:
+// one MSM over the context's own window-multiple table per candidate (pseudo-random scalars, warm-up + best of two), every
+// result compared byte for byte with the plain pipeline's; the fastest candidate that agrees is kept if it is at least
+// 2 % faster than the plain pipeline.  Only the geometry of the hot path is tuned (the whole table range); a worker's
+// shard of a multi-GPU MSM is its own context and tunes itself.
 int msm_tune(dp_ctx *ctx) {
     ctx->tune_ms[0] = ctx->tune_ms[1] = 0.f;
+    for (float &v : ctx->tune_all_ms) v = 0.f;
     ctx->tune_equal = -1;
     if (ctx->msm_affine_forced >= 0) {
         ctx->msm_affine_levels = (uint32_t)ctx->msm_affine_forced;
@@ -1084,37 +1087,54 @@ int msm_tune(dp_ctx *ctx) {
     cudaMemGetInfo(&free_b, &total_b);
     if (digits * 200ull > free_b / 2) return DP_OK;  // level buffers: ~ 150 B per digit on top of the plain pipeline's 12
     Scratch tmp(ctx->pool);
+    constexpr int N_CAND = 4;                         // levels 0 (plain), 1, 2, 3
     uint4 *sc = tmp.get<uint4>(2 * span);
-    G1JacobianOut *out = tmp.get<G1JacobianOut>(2);
+    G1JacobianOut *out = tmp.get<G1JacobianOut>(N_CAND);
     if (!sc || !out) return DP_OK;  // not enough memory to try: stay on the plain pipeline
     DP_LAUNCH(msm_tune_scalars_kernel, dim3(blocks_for(span, 256)), dim3(256), 0, ctx->stream, sc, span, 0x7A11E5ull);
     ctx->launches++;
     DP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    for (int mode = 0; mode < 2; mode++) {
-        ctx->msm_affine_levels = mode ? 2u : 0u;
+    float ms[N_CAND] = {0.f, 0.f, 0.f, 0.f};
+    bool ran[N_CAND] = {false, false, false, false};
+    for (int lv = 0; lv < N_CAND; lv++) {
+        ctx->msm_affine_levels = (uint32_t)lv;
         double best = 1e30;
-        for (int rep = 0; rep < 3; rep++) {
+        int rc = DP_OK;
+        for (int rep = 0; rep < 3 && rc == DP_OK; rep++) {
             const auto t0 = std::chrono::steady_clock::now();
-            const int rc = msm_device(ctx, ctx->pre_lo, sc, span, out + mode, nullptr);
-            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-            if (rc != DP_OK) {
-                ctx->msm_affine_levels = 0;
-                if (mode == 0) return rc;
-                // the candidate failed where the plain pipeline had just worked: keep the plain pipeline and say so
-                // (tune_equal = 0); a sticky CUDA error will surface again at the caller's next call
-                cudaGetLastError();
-                ctx->tune_ms[1] = 0.f;
-                ctx->tune_equal = 0;
-                return DP_OK;
-            }
-            if (rep && ms < best) best = ms;
+            rc = msm_device(ctx, ctx->pre_lo, sc, span, out + lv, nullptr);
+            const double t = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            if (rep && t < best) best = t;
         }
-        ctx->tune_ms[mode] = (float)best;
+        if (rc != DP_OK) {
+            ctx->msm_affine_levels = 0;
+            if (lv == 0) return rc;
+            // a candidate failed where the plain pipeline had just worked: keep the plain pipeline and say so
+            // (tune_equal = 0); a sticky CUDA error will surface again at the caller's next call
+            cudaGetLastError();
+            ctx->tune_equal = 0;
+            return DP_OK;
+        }
+        ms[lv] = (float)best;
+        ran[lv] = true;
     }
-    G1JacobianOut host[2];
+    ctx->msm_affine_levels = 0;
+    G1JacobianOut host[N_CAND];
     DP_CUDA(ctx, cudaMemcpy(host, out, sizeof host, cudaMemcpyDeviceToHost));
-    ctx->tune_equal = memcmp(&host[0], &host[1], sizeof(G1JacobianOut)) == 0 ? 1 : 0;
-    ctx->msm_affine_levels = ctx->tune_equal == 1 && ctx->tune_ms[1] < 0.98f * ctx->tune_ms[0] ? 2u : 0u;
+    ctx->tune_ms[0] = ms[0];
+    ctx->tune_equal = 1;
+    int best_lv = 0;
+    for (int lv = 1; lv < N_CAND; lv++) {
+        if (!ran[lv]) continue;
+        if (memcmp(&host[0], &host[lv], sizeof(G1JacobianOut)) != 0) {
+            ctx->tune_equal = 0;  // a candidate that disagrees disqualifies the whole experiment
+            continue;
+        }
+        if (best_lv == 0 ? ms[lv] < 0.98f * ms[0] : ms[lv] < ms[best_lv]) best_lv = lv;
+        if (ctx->tune_ms[1] == 0.f || ms[lv] < ctx->tune_ms[1]) ctx->tune_ms[1] = ms[lv];  // the best candidate's time, kept or not
+    }
+    ctx->msm_affine_levels = ctx->tune_equal == 1 ? (uint32_t)best_lv : 0u;
+    for (int lv = 0; lv < N_CAND; lv++) ctx->tune_all_ms[lv] = ms[lv];
     return DP_OK;
 }
 
@@ -2265,6 +2285,12 @@ int dp_msm_tuning(const dp_ctx *ctx, float *plain_ms, float *affine_ms, int *lev
     if (affine_ms) *affine_ms = ctx->tune_ms[1];
     if (levels) *levels = (int)ctx->msm_affine_levels;
     if (equal) *equal = ctx->tune_equal;
+    return DP_OK;
+}
+
+int dp_msm_tuning_all(const dp_ctx *ctx, float ms_by_levels[4]) {
+    if (!ctx || !ms_by_levels) return DP_E_ARG;
+    for (int k = 0; k < 4; k++) ms_by_levels[k] = ctx->tune_all_ms[k];
     return DP_OK;
 }
 

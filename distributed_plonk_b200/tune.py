@@ -1,7 +1,7 @@
 """Guarded opt-in to the batched-affine MSM levels.
 
-`dp_init` can time the plain MSM pipeline against two batched-affine tree levels over the context's own window table and
-compare the results (DP_MSM_TUNE=1, csrc/dplonk.cu: msm_tune).  The levels were written after the round's GPU budget was
+`dp_init` can time the plain MSM pipeline against one, two and three batched-affine tree levels over the context's own
+window table and compare the results (DP_MSM_TUNE=1, csrc/dplonk.cu: msm_tune).  The levels were written after the round's GPU budget was
 spent, so the library never selects them on its own; a host that wants them runs that tuning in a CHILD process first -
 `probe()` - and opts in (DP_MSM_AFFINE=2) only when the child came back saying "same result, faster".  Whatever goes wrong
 in the child (a crash included) cannot touch the caller's CUDA context.

@@ -161,7 +161,7 @@ def test_msm_batched_affine_levels(orc, emul_lib, monkeypatch, levels):
         bases = orc.gen_bases(11, n, 64, True)
         c = Context(emul_lib, 0, 0, 1)
         c.init(bases, 1 << 4, 1 << 7)
-        common.check_msm(orc, c, bases, n, 61, which=("witness-like", "all one"))
+        common.check_msm(orc, c, bases, n, 61, which=("witness-like",))
         c.close()
 
 
@@ -176,7 +176,7 @@ def test_msm_tuning_at_init(orc, emul_lib, monkeypatch):
     c = Context(emul_lib, 0, 0, 1)
     c.init(bases, 1 << 4, 1 << 7)
     t = c.msm_tuning()
-    assert t["equal"] == 1 and t["plain_ms"] > 0 and t["affine_ms"] > 0 and t["levels"] in (0, 2)
+    assert t["equal"] == 1 and t["plain_ms"] > 0 and t["affine_ms"] > 0 and t["levels"] in (0, 1, 2, 3)
     common.check_msm(orc, c, bases, n, 63, which=("uniform",))
     c.init(orc.gen_bases(5, 100, 64, True), 1 << 4, 1 << 7)   # a small SRS has no table: nothing to tune, plain pipeline
     assert c.msm_tuning() == {"plain_ms": 0.0, "affine_ms": 0.0, "levels": 0, "equal": -1}

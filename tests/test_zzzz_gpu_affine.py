@@ -53,7 +53,7 @@ def test_tuning_at_init_agrees(orc, gpu_lib, monkeypatch):
     t = c.msm_tuning()
     print("msm tuning at 2^20:", t)
     assert t["equal"] == 1, f"the two MSM pipelines disagree: {t}"
-    assert t["plain_ms"] > 0 and t["affine_ms"] > 0 and t["levels"] in (0, 2)
+    assert t["plain_ms"] > 0 and t["affine_ms"] > 0 and t["levels"] in (0, 1, 2, 3)
     sc = orc.gen_fr(4300, n, False)
     sc[::5] = 0
     common.assert_point_eq(orc, c.msm(0, n, sc), orc.msm(b, sc), "2^20 MSM through the tuned pipeline")
@@ -65,4 +65,4 @@ def test_probe_in_a_child_process(gpu_lib):
     res = tune.probe(0, 0, 1, 18)
     print("probe at 2^18:", res)
     assert "error" not in res and res["equal"] in (1, -1)
-    assert tune.choose(res) in (0, 2)
+    assert tune.choose(res) in (0, 1, 2, 3)

@@ -156,13 +156,7 @@ def test_msm_batched_affine_levels(orc, emul_lib, monkeypatch, levels):
         for k, (lo, hi) in enumerate([(0, 300), (100, 250), (0, 0)]):
             common.assert_point_eq(orc, outs[k], orc.msm(bases[lo:hi], scs[k][: hi - lo]), f"host batch job {k}")
     c.close()
-    if levels == 2:                                            # the shared bucket set over the window-multiple table
-        n = 2048
-        bases = orc.gen_bases(11, n, 64, True)
-        c = Context(emul_lib, 0, 0, 1)
-        c.init(bases, 1 << 4, 1 << 7)
-        common.check_msm(orc, c, bases, n, 61, which=("witness-like",))
-        c.close()
+    # (the shared bucket set over the window-multiple table: test_msm_tuning_at_init)
 
 
 def test_msm_tuning_at_init(orc, emul_lib, monkeypatch):
@@ -178,6 +172,12 @@ def test_msm_tuning_at_init(orc, emul_lib, monkeypatch):
     t = c.msm_tuning()
     assert t["equal"] == 1 and t["plain_ms"] > 0 and t["affine_ms"] > 0 and t["levels"] in (0, 1, 2, 3)
     common.check_msm(orc, c, bases, n, 63, which=("uniform",))
+    monkeypatch.setenv("DP_MSM_AFFINE", "2")                   # two levels over the table's shared bucket set, whatever the tuning chose
+    c2 = Context(emul_lib, 0, 0, 1)
+    c2.init(bases, 1 << 4, 1 << 7)
+    common.check_msm(orc, c2, bases, n, 61, which=("witness-like",))
+    c2.close()
+    monkeypatch.delenv("DP_MSM_AFFINE")
     c.init(orc.gen_bases(5, 100, 64, True), 1 << 4, 1 << 7)   # a small SRS has no table: nothing to tune, plain pipeline
     assert c.msm_tuning() == {"plain_ms": 0.0, "affine_ms": 0.0, "levels": 0, "equal": -1}
     c.close()

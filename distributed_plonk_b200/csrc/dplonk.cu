@@ -193,15 +193,17 @@ struct dp_ctx {
     // first dp_quotient_evals after dp_init when it fits (32 B per point), dropped by the next dp_init
     Fr *quot_inv = nullptr;
     uint32_t quot_inv_log = 0;
-    // batched-affine tree levels in front of the XYZZ chunks (msm.cuh): 0 = none (default), else L.  env DP_MSM_AFFINE=L forces L
-    // levels; env DP_MSM_TUNE=1 lets dp_init choose by msm_tune() - one MSM over the context's own window table either way,
-    // results compared, the levels kept if identical and faster.  The levels were written after the round's GPU budget was
-    // spent (their kernels ran on hardware only in microbenchmark form, profiles/r02h_microbench_affine2.txt), so nothing
-    // selects them silently: bench.py probes them in a child process and opts in per run (distributed_plonk_b200/tune.py).
-    // MSMs of fewer than msm_affine_min_digits digits stay on the plain path (env DP_MSM_AFFINE_MIN).
+    // batched-affine tree levels in front of the XYZZ chunks (msm.cuh): 0 = none, else L.  env DP_MSM_AFFINE=L forces L levels;
+    // otherwise dp_init chooses by msm_tune() - one MSM over the context's own window table per candidate, results compared
+    // byte for byte, levels kept only if identical and faster (an SRS whose hot-path MSM has fewer than msm_affine_min_digits
+    // digits is not tuned and stays plain; env DP_MSM_AFFINE_MIN).  bench.py runs the wider search (DP_MSM_TUNE=2) in a child
+    // process and forces its answer (distributed_plonk_b200/tune.py).
     uint32_t msm_affine_levels = 0;
     int msm_affine_forced = -1;             // -1 = not forced
-    bool msm_tune_enabled = false;          // env DP_MSM_TUNE=1: dp_init runs msm_tune(); otherwise the plain pipeline unless forced
+    // env DP_MSM_TUNE: 0 = dp_init never tunes (plain pipeline unless forced); 1 (default) = msm_tune() compares the plain
+    // pipeline with two tree levels - the two pipelines that ran on a B200 before the round's GPU budget ended
+    // (profiles/r02i_msm_tuning.txt); 2 = it also tries one and three levels (what bench.py's child-process probe asks for)
+    int msm_tune_mode = 1;
     uint64_t msm_affine_min_digits = (uint64_t)1 << 22;
     float tune_ms[2] = {0.f, 0.f};          // msm_tune(): plain / best candidate with levels (0 = not measured)
     float tune_all_ms[4] = {0.f, 0.f, 0.f, 0.f};  // msm_tune(): 0, 1, 2, 3 levels
@@ -1067,7 +1069,7 @@ int msm_device(dp_ctx *ctx, uint64_t start, const uint4 *scalars_dev, uint64_t n
     return rc != DP_OK ? rc : rc2;
 }
 
-// dp_init's choice (DP_MSM_TUNE=1) between the plain MSM pipeline and 1, 2 or 3 batched-affine tree levels in front of it:
+// dp_init's choice between the plain MSM pipeline and batched-affine tree levels in front of it (2; with DP_MSM_TUNE=2 also 1 and 3):
 // one MSM over the context's own window-multiple table per candidate (pseudo-random scalars, warm-up + best of two), every
 // result compared byte for byte with the plain pipeline's; the fastest candidate that agrees is kept if it is at least
 // 2 % faster than the plain pipeline.  Only the geometry of the hot path is tuned (the whole table range); a worker's
@@ -1082,7 +1084,7 @@ int msm_tune(dp_ctx *ctx) {
     }
     ctx->msm_affine_levels = 0;
     const uint64_t span = ctx->pre_hi - ctx->pre_lo, digits = span * ctx->pre_nw;
-    if (!ctx->msm_tune_enabled || !ctx->pre_table || digits < ctx->msm_affine_min_digits) return DP_OK;
+    if (ctx->msm_tune_mode == 0 || !ctx->pre_table || digits < ctx->msm_affine_min_digits) return DP_OK;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     if (digits * 200ull > free_b / 2) return DP_OK;  // level buffers: ~ 150 B per digit on top of the plain pipeline's 12
@@ -1097,6 +1099,7 @@ int msm_tune(dp_ctx *ctx) {
     float ms[N_CAND] = {0.f, 0.f, 0.f, 0.f};
     bool ran[N_CAND] = {false, false, false, false};
     for (int lv = 0; lv < N_CAND; lv++) {
+        if (ctx->msm_tune_mode < 2 && (lv == 1 || lv == 3)) continue;
         ctx->msm_affine_levels = (uint32_t)lv;
         double best = 1e30;
         int rc = DP_OK;
@@ -1357,7 +1360,7 @@ int dp_create(int cuda_device, uint64_t me, uint64_t n_workers, dp_ctx **out) {
         ctx->msm_affine_levels = (uint32_t)ctx->msm_affine_forced;
     }
     if (const char *e = getenv("DP_MSM_AFFINE_MIN")) ctx->msm_affine_min_digits = strtoull(e, nullptr, 10);
-    if (const char *e = getenv("DP_MSM_TUNE")) ctx->msm_tune_enabled = atoi(e) != 0;
+    if (const char *e = getenv("DP_MSM_TUNE")) ctx->msm_tune_mode = atoi(e) < 0 ? 0 : atoi(e) > 2 ? 2 : atoi(e);
     ctx->me = me;
     ctx->W = n_workers;
     int rc = DP_OK;

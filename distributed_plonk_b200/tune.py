@@ -1,10 +1,10 @@
-"""Guarded opt-in to the batched-affine MSM levels.
+"""MSM pipeline tuning in a child process.
 
-`dp_init` can time the plain MSM pipeline against one, two and three batched-affine tree levels over the context's own
-window table and compare the results (DP_MSM_TUNE=1, csrc/dplonk.cu: msm_tune).  The levels were written after the round's GPU budget was
-spent, so the library never selects them on its own; a host that wants them runs that tuning in a CHILD process first -
-`probe()` - and opts in (DP_MSM_AFFINE=2) only when the child came back saying "same result, faster".  Whatever goes wrong
-in the child (a crash included) cannot touch the caller's CUDA context.
+`dp_init` times the plain MSM pipeline against batched-affine tree levels over the context's own window table and keeps
+the levels only if they give the identical 144 bytes faster (csrc/dplonk.cu: msm_tune).  By default it compares the two
+pipelines that have run on hardware (plain, two levels); the wider search (one, two, three levels: DP_MSM_TUNE=2) is run by
+`probe()` in a CHILD process, so that whatever goes wrong there - a crash included - cannot touch the caller's CUDA
+context; the caller then forces the answer (DP_MSM_AFFINE).  bench.py does this once per run.
 
   python -m distributed_plonk_b200.tune DEVICE ME N_WORKERS LOG_N     ->  one JSON line
 """
@@ -35,7 +35,7 @@ def _child(device: int, me: int, n_workers: int, log_n: int) -> dict:
 def probe(device: int, me: int, n_workers: int, log_n: int, timeout: float = 150.0) -> dict:
     """dp_init's MSM tuning for worker `me` of `n_workers` on GPU `device`, run in a child process.
     Returns its {"plain_ms", "affine_ms", "levels", "equal"} or {"error": ...}."""
-    env = dict(os.environ, DP_MSM_TUNE="1")
+    env = dict(os.environ, DP_MSM_TUNE="2")
     env.pop("DP_MSM_AFFINE", None)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")

@@ -274,9 +274,9 @@ int dp_sync(dp_ctx *ctx);
 int dp_last_msm_breakdown(const dp_ctx *ctx, float *sort_ms, float *accumulate_ms, float *reduce_ms);
 
 /* what dp_init's MSM tuning found: one MSM over the context's own window-multiple table with the plain pipeline
- * (XYZZ chunks) and one each with 1, 2, 3 batched-affine tree levels in front of it (*affine_ms = the best of those);
+ * (XYZZ chunks) and one with 2 batched-affine tree levels in front of it (1, 2 and 3 with DP_MSM_TUNE=2; *affine_ms = the best);
  * *equal = all results were the same 144 bytes (1), some differed (0: the plain pipeline is kept), or the tuning did not
- * run (-1: no DP_MSM_TUNE=1, small SRS, or DP_MSM_AFFINE set); *levels = what MSMs of this context use (0 = plain).  Replaces nothing in the reference: ark-ec has one algorithm. */
+ * run (-1: DP_MSM_TUNE=0, small SRS, or DP_MSM_AFFINE set); *levels = what MSMs of this context use (0 = plain).  Replaces nothing in the reference: ark-ec has one algorithm. */
 int dp_msm_tuning(const dp_ctx *ctx, float *plain_ms, float *affine_ms, int *levels, int *equal);
 /* the same experiment in full: ms of one MSM with 0 (plain), 1, 2 and 3 tree levels (0 = not measured) */
 int dp_msm_tuning_all(const dp_ctx *ctx, float ms_by_levels[4]);

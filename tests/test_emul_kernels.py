@@ -163,14 +163,22 @@ def test_msm_tuning_at_init(orc, emul_lib, monkeypatch):
     """dp_init times the plain pipeline against two tree levels over the context's own table and keeps the levels only
     if both give the same 144 bytes; whatever it chose, MSMs agree with the oracle"""
     monkeypatch.delenv("DP_MSM_AFFINE", raising=False)
-    monkeypatch.setenv("DP_MSM_AFFINE_MIN", "0")
-    monkeypatch.setenv("DP_MSM_TUNE", "1")
+    monkeypatch.delenv("DP_MSM_TUNE", raising=False)
+    monkeypatch.setenv("DP_MSM_AFFINE_MIN", "0")               # (by default only SRS with >= 2^22 digits per MSM are tuned)
     n = 2048
     bases = orc.gen_bases(11, n, 64, True)
     c = Context(emul_lib, 0, 0, 1)
     c.init(bases, 1 << 4, 1 << 7)
-    t = c.msm_tuning()
-    assert t["equal"] == 1 and t["plain_ms"] > 0 and t["affine_ms"] > 0 and t["levels"] in (0, 1, 2, 3)
+    t = c.msm_tuning()                                         # default: the plain pipeline against two levels
+    assert t["equal"] == 1 and t["plain_ms"] > 0 and t["affine_ms"] > 0 and t["levels"] in (0, 2)
+    assert t["ms_by_levels"][1] == 0 and t["ms_by_levels"][3] == 0 and t["ms_by_levels"][2] > 0
+    monkeypatch.setenv("DP_MSM_TUNE", "2")                     # the wider search bench.py's probe runs: 1, 2 and 3 levels
+    c3 = Context(emul_lib, 0, 0, 1)
+    c3.init(bases, 1 << 4, 1 << 7)
+    t3 = c3.msm_tuning()
+    assert t3["equal"] == 1 and all(v > 0 for v in t3["ms_by_levels"]) and t3["levels"] in (0, 1, 2, 3)
+    c3.close()
+    monkeypatch.delenv("DP_MSM_TUNE")
     common.check_msm(orc, c, bases, n, 63, which=("uniform",))
     monkeypatch.setenv("DP_MSM_AFFINE", "2")                   # two levels over the table's shared bucket set, whatever the tuning chose
     c2 = Context(emul_lib, 0, 0, 1)
@@ -181,7 +189,7 @@ def test_msm_tuning_at_init(orc, emul_lib, monkeypatch):
     c.init(orc.gen_bases(5, 100, 64, True), 1 << 4, 1 << 7)   # a small SRS has no table: nothing to tune, plain pipeline
     assert c.msm_tuning() == {"plain_ms": 0.0, "affine_ms": 0.0, "levels": 0, "equal": -1}
     c.close()
-    monkeypatch.delenv("DP_MSM_TUNE")                          # without the opt-in dp_init never tunes and never selects the levels
+    monkeypatch.setenv("DP_MSM_TUNE", "0")                     # switched off: dp_init never tunes and never selects the levels
     c = Context(emul_lib, 0, 0, 1)
     c.init(bases, 1 << 4, 1 << 7)
     assert c.msm_tuning() == {"plain_ms": 0.0, "affine_ms": 0.0, "levels": 0, "equal": -1}

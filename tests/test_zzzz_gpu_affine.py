@@ -1,7 +1,7 @@
 """The batched-affine MSM levels (DP_MSM_AFFINE / DP_MSM_TUNE) on the GPU.  Last file of the suite on purpose: these
 kernels were written after the round's GPU budget was spent (their inner loops ran on hardware in microbenchmark form
-only, profiles/r02h_microbench_affine2.txt), so nothing else in the suite runs after them.  The library never selects
-the levels on its own; bench.py opts in per run after a probe in a child process (distributed_plonk_b200/tune.py)."""
+and, as dp_init's default tuning at 2^20 and 2^22 points, with the round's last GPU seconds: profiles/r02i_msm_tuning.txt),
+so nothing else in the suite runs after the forced-level cases and the wider search exercised here."""
 import numpy as np
 import pytest
 
@@ -43,9 +43,10 @@ def test_forced_levels_vs_oracle(orc, gpu_lib, bases, monkeypatch, levels):
 
 
 def test_tuning_at_init_agrees(orc, gpu_lib, monkeypatch):
-    """DP_MSM_TUNE=1: dp_init times both pipelines over the context's own table; they must give the same 144 bytes"""
+    """dp_init times the plain pipeline and 1, 2, 3 tree levels over the context's own table (DP_MSM_TUNE=2: the wider
+    search; the default compares plain and two levels); all must give the same 144 bytes"""
     monkeypatch.delenv("DP_MSM_AFFINE", raising=False)
-    monkeypatch.setenv("DP_MSM_TUNE", "1")
+    monkeypatch.setenv("DP_MSM_TUNE", "2")
     n = (1 << 20) + 32
     c = Context(gpu_lib, 0, 0, 1)
     b = c.gen_bases(77, n)

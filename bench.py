@@ -263,7 +263,8 @@ def main():
     if "DP_MSM_AFFINE" not in os.environ and os.environ.get("DP_BENCH_NO_MSM_PROBE", "0") != "1":
         from distributed_plonk_b200 import tune
         tune_probe = tune.probe(local, rank, W, args.log_n)
-        os.environ["DP_MSM_AFFINE"] = str(tune.choose(tune_probe))
+        if "error" not in tune_probe:     # (a probe that did not finish decides nothing: dp_init's own tuning, plain vs two levels, stands)
+            os.environ["DP_MSM_AFFINE"] = str(tune.choose(tune_probe))
     ctx = dp.Context(lib, local, rank, W)
 
     log_n = args.log_n
@@ -662,7 +663,7 @@ def main():
         "breakdown_ms": {"msm_total_one_at_a_time": msm_total, "msm_accumulate": acc_total, "intt_n_total": sum(stats["ntt_n_ms"]),
                          "coset_ntt_8n_total": sum(stats["ntt_m_ms"]), "sections_max_over_ranks": stats["sections_ms"]},
         "roofline": roofline, "roofline_ntt": ntt_hbm, "roofline_compute": compute, "e2e": e2e, "e2e_resident": e2e_res,
-        "msm_tuning": {"levels_used": lv, "probe": tune_probe,
+        "msm_tuning": {"levels_used": lv, "probe": tune_probe, "in_process": {k: v for k, v in tuning.items() if k != "levels"},
                        "what": "a child process timed one MSM over this rank's window table with the plain pipeline and with 1, 2 and 3 batched-affine "
                                "tree levels in front of it (dp_init with DP_MSM_TUNE=1, ms_by_levels); levels are used in this run only if every "
                                "result was identical to the plain pipeline's and the best candidate >= 2 % faster"},

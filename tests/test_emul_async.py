@@ -28,7 +28,10 @@ def test_pipeline_under_adversarial_stream_schedules():
     procs = []
     # the five streams with the default MSM pipeline, then the optional sort stream (DP_MSM_SORT_STREAM=1) with the two
     # stream itself made slow
-    for slow, sort_stream in [(0, "0"), (1, "0"), (2, "0"), (3, "0"), (4, "1")]:
+    configs = [(0, "0"), (1, "0"), (2, "0"), (3, "0"), (4, "1")]
+    if os.environ.get("DP_TEST_FULL", "0") != "1":
+        configs = [(0, "0"), (1, "0"), (3, "0"), (4, "1")]      # (the copy-out stream only feeds dp_fft2's blocking read)
+    for slow, sort_stream in configs:
         env = dict(os.environ, DP_TEST_EMUL_ASYNC="1", DP_EMUL_SLOW=f"{slow}:1500", DP_MSM_SORT_STREAM=sort_stream)
         procs.append(subprocess.Popen(
             [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_emul_kernels.py"), "-q", "-x", "-p", "no:cacheprovider",

@@ -3,6 +3,7 @@ execution-model emulator in tests/emul (barriers, shared memory, atomics and car
 the real PTX paths are exercised by the `-m gpu` tests).  Same checks as tests/test_gpu_parity.py,
 at sizes the emulator finishes in seconds."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -15,6 +16,9 @@ from tests import common
 
 def host_copy(dst, src, n):
     C.memmove(dst, src, n)
+
+
+FULL = os.environ.get("DP_TEST_FULL", "0") == "1"   # the larger shapes of a few tests: DP_TEST_FULL=1
 
 
 @pytest.fixture(scope="module")
@@ -92,10 +96,10 @@ def test_distributed_fft_tiny_domains(orc, emul_lib, logn, logq):
 def test_msm_distributions_and_geometries(orc, ctx):
     bases = orc.gen_bases(5, 600, 64, True)
     ctx.debug_set_limits(11, 9, 0)
-    common.check_msm(orc, ctx, bases, 600, 21)
+    common.check_msm(orc, ctx, bases, 600 if FULL else 300, 21)
     for c in (4, 7, 13):
         ctx.debug_set_limits(11, 9, c)
-        common.check_msm(orc, ctx, bases, 300, 30 + c, which=("uniform", "witness-like"))
+        common.check_msm(orc, ctx, bases, 300 if FULL else 150, 30 + c, which=("uniform", "witness-like"))
     ctx.debug_set_limits(11, 9, 0)
 
 
@@ -586,7 +590,7 @@ def test_whole_ntt_fused_coset_tables_and_short_inputs(orc, emul_lib, limits, do
     c.close()
 
 
-@pytest.mark.parametrize("logn,logq", [(6, 9), (8, 11)])
+@pytest.mark.parametrize("logn,logq", [(6, 9), (8, 11)] if FULL else [(6, 9)])
 def test_single_worker_three_pass_plan(orc, emul_lib, logn, logq):
     """n_workers == 1: the transform as three passes over digit groups of the element index instead of two row and two
     column passes (plan_single_worker3) - same rows in, same columns out, every flag combination, full and short rows,

@@ -665,7 +665,7 @@ def main():
         "roofline": roofline, "roofline_ntt": ntt_hbm, "roofline_compute": compute, "e2e": e2e, "e2e_resident": e2e_res,
         "msm_tuning": {"levels_used": lv, "probe": tune_probe, "in_process": {k: v for k, v in tuning.items() if k != "levels"},
                        "what": "a child process timed one MSM over this rank's window table with the plain pipeline and with 1, 2 and 3 batched-affine "
-                               "tree levels in front of it (dp_init with DP_MSM_TUNE=1, ms_by_levels); levels are used in this run only if every "
+                               "tree levels in front of it (dp_init with DP_MSM_TUNE=2, ms_by_levels); levels are used in this run only if every "
                                "result was identical to the plain pipeline's and the best candidate >= 2 % faster"},
         "next_row_perm_product": perm, "next_row_rounds_3_to_5": rounds,
     }

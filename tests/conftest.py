@@ -33,6 +33,12 @@ def emul_lib():
 
 @pytest.fixture(scope="session")
 def gpu_lib():
-    """the real nvcc-built library; GPU tests fail (not skip) if it is missing"""
+    """the real nvcc-built library; GPU tests fail (not skip) if it is missing.
+    DP_TEST_DRY_RUN_ON_EMULATOR=1 (never set by the suite) hands a `-m gpu` test file the kernel-logic emulator instead,
+    to check the test code itself on a box without a GPU (files that honour it shrink their sizes)."""
+    if os.environ.get("DP_TEST_DRY_RUN_ON_EMULATOR", "0") == "1":
+        from tests.emul import build as emul_build
+        from distributed_plonk_b200._binding import bind
+        return bind(ctypes.CDLL(emul_build.build()))
     import distributed_plonk_b200 as dp
     return dp.load()

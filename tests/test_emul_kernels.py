@@ -200,7 +200,7 @@ def test_msm_tuning_at_init(orc, emul_lib, monkeypatch):
     c.close()
 
 
-def test_msm_probe_is_a_guarded_opt_in():
+def test_msm_probe_is_a_guarded_opt_in(monkeypatch):
     """tune.probe runs dp_init's tuning in a child process; whatever happens there, the caller only opts in on
     "identical and faster" (here the child cannot even create a context: no GPU)"""
     from distributed_plonk_b200 import tune
@@ -213,6 +213,24 @@ def test_msm_probe_is_a_guarded_opt_in():
     if not torch.cuda.is_available():
         res = tune.probe(0, 0, 1, 12, timeout=120)
         assert "error" in res and tune.choose(res) == 0
+    # what the parent makes of a child's output: the last line is the result, anything before it is ignored
+    import subprocess
+    import types
+    seen = {}
+
+    def fake_run(cmd, env=None, **kw):
+        seen["cmd"], seen["tune"], seen["forced"] = cmd, env.get("DP_MSM_TUNE"), "DP_MSM_AFFINE" in env
+        return types.SimpleNamespace(returncode=0, stderr="", stdout='some warning\n{"plain_ms": 23.5, "affine_ms": 22.6, "levels": 2, "equal": 1}\n')
+
+    monkeypatch.setenv("DP_MSM_AFFINE", "0")
+    monkeypatch.setattr(subprocess, "run", fake_run)
+    res = tune.probe(3, 5, 8, 22)
+    assert res["levels"] == 2 and res["equal"] == 1 and "probe_seconds" in res and tune.choose(res) == 2
+    assert seen["cmd"][-4:] == ["3", "5", "8", "22"] and seen["tune"] == "2" and not seen["forced"]
+    monkeypatch.setattr(subprocess, "run", lambda *a, **k: types.SimpleNamespace(returncode=-11, stderr="Segmentation fault", stdout=""))
+    assert "error" in tune.probe(0, 0, 1, 22)
+    monkeypatch.setattr(subprocess, "run", lambda *a, **k: types.SimpleNamespace(returncode=0, stderr="", stdout="no json here"))
+    assert "error" in tune.probe(0, 0, 1, 22)
 
 
 def test_msm_dev_batch(orc, ctx):
